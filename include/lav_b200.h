@@ -1,0 +1,139 @@
+/* lav_b200 — C ABI of the B200-native LAV frame-path kernels (sm_100a).
+ *
+ * The reference (dotchen/LAV) has no FFI: its boundary is Python (torch modules).  A
+ * reference-side maintainer binds these entry points with ctypes;
+ * lav_b200/capi.py is that binding.  Every pointer named d_* is a DEVICE pointer,
+ * h_* is a HOST pointer read synchronously during the call.  `stream` is a
+ * cudaStream_t passed as void* (0 = legacy default stream).  All functions return 0
+ * on success and a non-zero code otherwise; lavb_last_error() gives the message
+ * (thread-local).  No global mutable state; safe from several host threads
+ * (nn.DataParallel-style) as long as each uses its own stream/workspace.
+ *
+ * Layouts: activations are NHWC ("channels last"); `*_cstride` is the number of
+ * channels of the underlying buffer (pixel stride in elements) and `*_coff` the first
+ * channel this call reads/writes, so concatenations are written in place.
+ */
+#ifndef LAV_B200_H
+#define LAV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAVB_ABI_VERSION 1
+
+int lavb_abi_version(void);
+const char* lavb_last_error(void);
+/* compute capability major*10+minor of the current device, or <0 when no device */
+int lavb_device_cc(void);
+
+/* ---------------------------------------------------------------- element types */
+enum { LAVB_F32 = 0, LAVB_BF16 = 1 };
+
+/* ---------------------------------------------------------------- point painting
+ * replaces: InferModel.point_painting / forward_paint (team_code_v2/model_inference.py:44-50,75-93),
+ *           CoordConverter.forward (model_inference.py:280-297),
+ *           point_painting() (lav/utils/point_painting.py:46-66).
+ * h_cams: ncam x 41 floats = K(3x3 row-major) | lidar_to_world(4x4) | world_to_cam(4x4).
+ * sem element (cam,c,v,u) lives at d_sem[cam*s_cam + c*s_c + v*s_y + u*s_x].
+ * mode 0: gather c_in channels as they are           -> c_in outputs
+ * mode 1: d_sem holds softmax probabilities (c_in>=2) -> c_in-1 outputs p[1+j]*(1-p[0])
+ * mode 2: d_sem holds logits; softmax over c_in then as mode 1
+ * Row i of the output receives `copy_cols` leading columns of point i, then the painted
+ * channels at column `out_col0`; later cameras overwrite earlier ones; unseen points get 0. */
+int lavb_paint(const float* d_pts, int n, int pt_stride,
+               const float* d_sem, int ncam, int c_in, int h, int w,
+               long long s_cam, long long s_c, long long s_y, long long s_x,
+               const float* h_cams, int mode,
+               float* d_out, int out_stride, int out_col0, int copy_cols, void* stream);
+
+/* ---------------------------------------------------------------- sweep stacking
+ * replaces: LAVAgent.get_stacked_lidar + move_lidar_points (team_code_v2/lav_agent_fast.py:363-383,547-565)
+ * and the ego-roof filter LAVAgent.preprocess (lav_agent.py:448-457, roof_filter!=0 marks dropped rows x=NaN).
+ * dst row = [xyz @ R + (dx,dy,0) | src cols 3..src_cols | one_hot(time_idx, n_time)];  h_R is 3x3 row-major. */
+int lavb_stack_sweep(const float* d_src, int n, int src_cols, const float* h_R, float dx, float dy,
+                     int time_idx, int n_time, int roof_filter, float* d_dst, void* stream);
+
+/* ---------------------------------------------------------------- PointPillars voxeliser + pillar encoder
+ * replaces: PointPillarNet.forward (lav/models/point_pillar.py:92-116) incl. grid_locations :70-79,
+ *           pillar_generation/decorate :55-68,81-85, DynamicPointNet.forward :28-35 (torch_scatter
+ *           scatter_mean/scatter_max), scatter_points :87-90.
+ * Clouds: cloud b = rows [h_cloud_start[b], +h_cloud_count[b]) of d_pts (row stride pt_stride floats,
+ * first `d` columns used).  MLP: Linear(d+5,h1) -> affine(s1,t1) -> ReLU -> Linear(h1,h2) -> affine -> ReLU
+ * with d_w1 [h1][d+5], d_w2 [h2][h1] row-major (nn.Linear layout); the affine is BatchNorm1d expressed as
+ * y*s+t (bias folded into t).  Output canvas NHWC [B][ny][nx][h2] (row = ny-1-xi, col = yi), fully written.
+ * Workspace: lavb_pillar_workspace_bytes(B, nx, ny) bytes, contents irrelevant on entry. */
+size_t lavb_pillar_workspace_bytes(int batch, int nx, int ny);
+int lavb_pillar_forward(const float* d_pts, int pt_stride, int d,
+                        const long long* h_cloud_start, const int* h_cloud_count, int batch,
+                        float min_x, float max_x, float min_y, float max_y, float ppm, int nx, int ny,
+                        const float* d_w1, const float* d_s1, const float* d_t1, int h1,
+                        const float* d_w2, const float* d_s2, const float* d_t2, int h2,
+                        void* d_canvas, int canvas_dtype, void* d_workspace, void* stream);
+
+/* training-mode pieces (BatchNorm1d batch statistics over all in-window points, arg-routed backward).
+ * stage 0: voxelise + decorate -> d_feat [M][d+5] (M = number of in-window points, returned in *h_m),
+ *          d_cell [M] int32 canvas cell id (b*ny*nx + row*nx + col), -1 never appears.
+ * The Linear/BN1d/ReLU stack then runs on d_feat with autograd; stage 1 max-pools rows into the canvas and
+ * records the arg-max row per (cell, channel) for the backward. */
+int lavb_pillar_decorate(const float* d_pts, int pt_stride, int d,
+                         const long long* h_cloud_start, const int* h_cloud_count, int batch,
+                         float min_x, float max_x, float min_y, float max_y, float ppm, int nx, int ny,
+                         float* d_feat, int* d_cell, int* h_m, void* d_workspace, void* stream);
+int lavb_pillar_scatter_max(const float* d_h, const int* d_cell, int m, int c, long long n_cells,
+                            float* d_canvas, int* d_argmax, void* stream);
+int lavb_pillar_scatter_max_bwd(const float* d_gcanvas, const int* d_argmax, const int* d_cell, int m, int c,
+                                float* d_gh, void* stream);
+
+/* ---------------------------------------------------------------- generic tap-list convolution (CUDA cores)
+ * replaces: every nn.Conv2d / nn.ConvTranspose2d (+ the ReLU / BatchNorm / residual that follows it) of
+ *           ERFNet (lav/models/erfnet.py:12-134), ConvBackbone and Head (lav/models/lidar.py:48-164).
+ * out[n, oy*out_sy+out_oy, ox*out_sx+out_ox, out_coff+co] = epi( sum_t sum_ci
+ *        in[n, oy*in_sy+dy[t], ox*in_sx+dx[t], in_coff+ci] * w[t][ci][co] )   (zero outside the input)
+ * epi(a): a += bias[co]; if pre_relu a=max(a,0); a = a*scale[co]+shift[co]; a += res[...]; if post_relu
+ *         a=max(a,0); if sigmoid a=1/(1+exp(-a)).   Null pointers skip a step.
+ * d_w: [ntaps][cin][cout_pad] fp32 with cout_pad = cout rounded up to 16.
+ * A strided Conv2d uses in_s=stride, dy=ky*dil-pad; a ConvTranspose2d is issued once per output phase with
+ * in_s=1, out_s=stride (lav_b200/packing.py builds the tap lists). */
+typedef struct {
+  const void* in; int in_dtype; int n, hin, win, cin, in_cstride, in_coff;
+  void* out; int out_dtype; int hout, wout, cout, out_cstride, out_coff;
+  int hog, wog;                 /* output-grid extent visited by this call */
+  int in_sy, in_sx, out_sy, out_sx, out_oy, out_ox;
+  int ntaps; int dy[16]; int dx[16];
+  const float* w; const float* bias; const float* scale; const float* shift;
+  const void* res; int res_dtype; int res_cstride, res_coff;
+  int pre_relu, post_relu, sigmoid;
+} lavb_conv_desc;
+int lavb_conv_taps(const lavb_conv_desc* h_desc, void* stream);
+
+/* 2x2/2 max-pool -> y*scale[c]+shift[c] -> ReLU into a channel slice (ERFNet DownsamplerBlock, erfnet.py:20-23) */
+int lavb_pool2_affine_relu(const void* d_in, int dtype, int n, int hin, int win, int c, int in_cstride, int in_coff,
+                           const float* d_scale, const float* d_shift,
+                           void* d_out, int out_cstride, int out_coff, void* stream);
+
+/* RGB ingest: uint8 NHWC (n,h,w,3) or float NCHW (n,3,h,w) in 0..255 -> (x/255-.5)*2 as NHWC with 4 channels
+ * (4th = 0).  replaces RGBSegmentationModel.normalize (lav/models/rgb.py:41). */
+int lavb_rgb_normalize(const void* d_rgb, int src_is_u8_nhwc, int n, int h, int w, void* d_out, int out_dtype,
+                       void* stream);
+
+/* dtype / layout helpers */
+int lavb_convert(const void* d_src, int src_dtype, void* d_dst, int dst_dtype, long long count, void* stream);
+
+/* ---------------------------------------------------------------- tcgen05 implicit-GEMM 3x3 convolution
+ * replaces: the stride-1 3x3 Conv2d -> ReLU -> BatchNorm2d layers of ConvBackbone (lidar.py:60-112) and the fused
+ *           4-head 384->256 conv (lidar.py:152-154) on the bf16 path.
+ * in: NHWC bf16 [n][h][w][cin] (cin multiple of 64), w: bf16 [9][cout][cin] (tap-major, K contiguous),
+ * out: NHWC bf16 [n][h][w][out_cstride] slice; epilogue relu(acc)*scale+shift.  h % 8 == 0, w % 16 == 0.
+ * TMA descriptors are built inside the call (cuTensorMapEncodeTiled via the driver entry point). */
+int lavb_conv3x3_umma(const void* d_in, int n, int h, int w, int cin,
+                      const void* d_w, int cout, const float* d_scale, const float* d_shift, int relu_first,
+                      void* d_out, int out_cstride, int out_coff, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAV_B200_H */

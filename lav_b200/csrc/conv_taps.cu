@@ -1,0 +1,280 @@
+// Generic "tap-list" convolution on the CUDA cores (fp32 accumulate), NHWC.
+//
+// One kernel covers every Conv2d / ConvTranspose2d shape of ERFNet, the BEV backbone and the heads
+// (lav/models/erfnet.py, lav/models/lidar.py): the host expresses a layer as a list of taps
+// (dy,dx,weight block) over an output grid; strided convs set in_s = stride, transposed convs are
+// issued once per output phase with out_s = stride.  The GEMM view is M = n*hog*wog pixels,
+// N = cout, K = ntaps*cin; tiles BM x BN x 16 with a register-prefetched, double-buffered smem
+// pipeline and a fused epilogue (bias, ReLU, BN affine, residual, ReLU, sigmoid).
+// This is the exact-fp32 workhorse (parity path and all HBM-bound layers); the tensor-core
+// layers of the bf16 path live in conv_umma.cu.
+#include "common.cuh"
+
+namespace lavb {
+
+struct ConvArgs {
+  const void* in; void* out; const void* res;
+  const float* w; const float* bias; const float* scale; const float* shift;
+  int n, hin, win, cin, in_cstride, in_coff;
+  int hout, wout, cout, cout_pad, out_cstride, out_coff;
+  int hog, wog, in_sy, in_sx, out_sy, out_sx, out_oy, out_ox;
+  int res_cstride, res_coff;
+  int ntaps;
+  int dy[16], dx[16];
+  int pre_relu, post_relu, sigmoid;
+};
+
+constexpr int BK = 16;
+
+template <typename TIn, typename TOut, int BM, int BN, int TM, int NH>
+__global__ void __launch_bounds__((BM / TM) * (BN / (4 * NH))) conv_taps_kernel(const __grid_constant__ ConvArgs a) {
+  constexpr int TXN = BN / (4 * NH);       // threads along channels
+  constexpr int NT = (BM / TM) * TXN;      // threads per block
+  constexpr int PPT = BM / NT;             // pixels each thread stages per k-step
+  constexpr int BV4 = BK * BN / 4;         // float4 in one B stage
+  constexpr int BV = (BV4 + NT - 1) / NT;  // float4 of B each thread stages per k-step
+  static_assert(BM % NT == 0, "tile/threads mismatch");
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TXN, ty = tid / TXN;
+  const long long M = (long long)a.n * a.hog * a.wog;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int co0 = blockIdx.y * BN;
+
+  // pixels this thread stages
+  int pn[PPT], py[PPT], px[PPT];
+  bool pv[PPT];
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    const long long m = m0 + tid + i * NT;
+    pv[i] = m < M;
+    const long long mm = pv[i] ? m : 0;
+    const int hw = a.hog * a.wog;
+    pn[i] = (int)(mm / hw);
+    const int r = (int)(mm - (long long)pn[i] * hw);
+    py[i] = (r / a.wog) * a.in_sy;
+    px[i] = (r % a.wog) * a.in_sx;
+  }
+  const TIn* in = reinterpret_cast<const TIn*>(a.in);
+  const int kchunks = (a.cin + BK - 1) / BK;
+  const int nk = a.ntaps * kchunks;
+
+  float4 ra[PPT][4];
+  float4 rb[BV];
+
+  auto load_stage = [&](int kit) {
+    const int t = kit / kchunks, ci0 = (kit - t * kchunks) * BK;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const int iy = py[i] + a.dy[t], ix = px[i] + a.dx[t];
+      const bool ok = pv[i] && iy >= 0 && iy < a.hin && ix >= 0 && ix < a.win;
+      const TIn* p = in + (((long long)pn[i] * a.hin + iy) * a.win + ix) * a.in_cstride + a.in_coff + ci0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        ra[i][q] = (ok && ci0 + q * 4 < a.cin) ? load4<TIn>(p + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int v = 0; v < BV; ++v) {
+      const int idx = tid + v * NT;            // float4 index inside the BK x BN tile
+      const int kk = idx / (BN / 4), c4 = idx % (BN / 4);
+      const int ci = ci0 + kk;
+      rb[v] = (idx < BV4 && ci < a.cin) ? __ldg(reinterpret_cast<const float4*>(a.w + ((long long)t * a.cin + ci) * a.cout_pad + co0) + c4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_stage = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const int m = tid + i * NT;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        As[buf][q * 4 + 0][m] = ra[i][q].x; As[buf][q * 4 + 1][m] = ra[i][q].y;
+        As[buf][q * 4 + 2][m] = ra[i][q].z; As[buf][q * 4 + 3][m] = ra[i][q].w;
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < BV; ++v) {
+      const int idx = tid + v * NT;
+      const int kk = idx / (BN / 4), c4 = idx % (BN / 4);
+      if (idx < BV4) *reinterpret_cast<float4*>(&Bs[buf][kk][c4 * 4]) = rb[v];
+    }
+  };
+
+  float acc[TM][4 * NH];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4 * NH; ++j) acc[i][j] = 0.f;
+
+  load_stage(0);
+  store_stage(0);
+  __syncthreads();
+  for (int kit = 0; kit < nk; ++kit) {
+    const int buf = kit & 1;
+    if (kit + 1 < nk) load_stage(kit + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float av[TM], bv[4 * NH];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + i]);
+        av[i] = t4.x; av[i + 1] = t4.y; av[i + 2] = t4.z; av[i + 3] = t4.w;
+      }
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const float4 t4 = *reinterpret_cast<const float4*>(&Bs[buf][k][h * (BN / NH) + tx * 4]);
+        bv[h * 4] = t4.x; bv[h * 4 + 1] = t4.y; bv[h * 4 + 2] = t4.z; bv[h * 4 + 3] = t4.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4 * NH; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kit + 1 < nk) store_stage(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue
+  TOut* out = reinterpret_cast<TOut*>(a.out);
+  const TOut* res = reinterpret_cast<const TOut*>(a.res);
+  const bool vec_ok = (a.cout % 4 == 0) && (a.out_coff % 4 == 0) && (a.out_cstride % 4 == 0) &&
+                      (res == nullptr || (a.res_coff % 4 == 0 && a.res_cstride % 4 == 0));
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const long long m = m0 + ty * TM + i;
+    if (m >= M) continue;
+    const int hw = a.hog * a.wog;
+    const int nn = (int)(m / hw);
+    const int r = (int)(m - (long long)nn * hw);
+    const int oy = (r / a.wog) * a.out_sy + a.out_oy, ox = (r % a.wog) * a.out_sx + a.out_ox;
+    if (oy >= a.hout || ox >= a.wout) continue;
+    const long long pix = ((long long)nn * a.hout + oy) * a.wout + ox;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      const int co = co0 + h * (BN / NH) + tx * 4;
+      if (co >= a.cout) continue;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = co + j;
+        float x = acc[i][h * 4 + j];
+        if (c < a.cout) {
+          if (a.bias) x += __ldg(a.bias + c);
+          if (a.pre_relu) x = fmaxf(x, 0.f);
+          if (a.scale) x = fmaf(x, __ldg(a.scale + c), __ldg(a.shift + c));
+        }
+        v[j] = x;
+      }
+      if (vec_ok) {
+        if (res) {
+          const float4 rr = load4<TOut>(res + pix * a.res_cstride + a.res_coff + co);
+          v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (a.post_relu) v[j] = fmaxf(v[j], 0.f);
+          if (a.sigmoid) v[j] = 1.f / (1.f + expf(-v[j]));
+        }
+        store4<TOut>(out + pix * a.out_cstride + a.out_coff + co, make_float4(v[0], v[1], v[2], v[3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = co + j;
+          if (c >= a.cout) continue;
+          float x = v[j];
+          if (res) x += to_f32<TOut>(res[pix * a.res_cstride + a.res_coff + c]);
+          if (a.post_relu) x = fmaxf(x, 0.f);
+          if (a.sigmoid) x = 1.f / (1.f + expf(-x));
+          out[pix * a.out_cstride + a.out_coff + c] = from_f32<TOut>(x);
+        }
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pool2_kernel(const T* __restrict__ in, int n, int hin, int win, int c, int in_cstride,
+                                                    int in_coff, const float* __restrict__ scale,
+                                                    const float* __restrict__ shift, T* __restrict__ out, int out_cstride,
+                                                    int out_coff) {
+  const int ho = hin / 2, wo = win / 2;
+  const long long total = (long long)n * ho * wo * c;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = (int)(i % c);
+  long long p = i / c;
+  const int ox = (int)(p % wo); p /= wo;
+  const int oy = (int)(p % ho);
+  const int nn = (int)(p / ho);
+  const T* s = in + (((long long)nn * hin + oy * 2) * win + ox * 2) * in_cstride + in_coff + ch;
+  const float v = fmaxf(fmaxf(to_f32<T>(s[0]), to_f32<T>(s[in_cstride])),
+                        fmaxf(to_f32<T>(s[(long long)win * in_cstride]), to_f32<T>(s[(long long)(win + 1) * in_cstride])));
+  const float y = fmaxf(fmaf(v, __ldg(scale + ch), __ldg(shift + ch)), 0.f);
+  out[(((long long)nn * ho + oy) * wo + ox) * out_cstride + out_coff + ch] = from_f32<T>(y);
+}
+
+template <typename TIn, typename TOut>
+static int launch_conv(const ConvArgs& a, cudaStream_t st) {
+  const long long M = (long long)a.n * a.hog * a.wog;
+  if (a.cout_pad % 64 == 0) {
+    dim3 grid(ceil_div(M, 128), a.cout_pad / 64);
+    conv_taps_kernel<TIn, TOut, 128, 64, 8, 2><<<grid, 128, 0, st>>>(a);
+  } else {
+    dim3 grid(ceil_div(M, 256), a.cout_pad / 16);
+    conv_taps_kernel<TIn, TOut, 256, 16, 8, 1><<<grid, 128, 0, st>>>(a);
+  }
+  LAVB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace lavb
+
+using namespace lavb;
+
+extern "C" int lavb_conv_taps(const lavb_conv_desc* d, void* stream) {
+  LAVB_CHECK_ARG(d != nullptr, "conv_taps: null descriptor");
+  LAVB_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= 16, "conv_taps: ntaps must be 1..16 (got %d)", d->ntaps);
+  LAVB_CHECK_ARG(d->cin % 4 == 0 && d->in_coff % 4 == 0 && d->in_cstride % 4 == 0,
+                 "conv_taps: cin/in_coff/in_cstride must be multiples of 4 (got %d/%d/%d)", d->cin, d->in_coff, d->in_cstride);
+  LAVB_CHECK_ARG(d->in_coff + d->cin <= d->in_cstride && d->out_coff + d->cout <= d->out_cstride, "conv_taps: channel slice out of range");
+  LAVB_CHECK_ARG((d->scale == nullptr) == (d->shift == nullptr), "conv_taps: scale and shift come together");
+  LAVB_CHECK_ARG(d->n > 0 && d->hog > 0 && d->wog > 0 && d->cout > 0, "conv_taps: empty problem");
+  ConvArgs a;
+  a.in = d->in; a.out = d->out; a.res = d->res; a.w = d->w; a.bias = d->bias; a.scale = d->scale; a.shift = d->shift;
+  a.n = d->n; a.hin = d->hin; a.win = d->win; a.cin = d->cin; a.in_cstride = d->in_cstride; a.in_coff = d->in_coff;
+  a.hout = d->hout; a.wout = d->wout; a.cout = d->cout; a.cout_pad = (d->cout + 15) / 16 * 16;
+  a.out_cstride = d->out_cstride; a.out_coff = d->out_coff;
+  a.hog = d->hog; a.wog = d->wog; a.in_sy = d->in_sy; a.in_sx = d->in_sx; a.out_sy = d->out_sy; a.out_sx = d->out_sx;
+  a.out_oy = d->out_oy; a.out_ox = d->out_ox; a.res_cstride = d->res_cstride; a.res_coff = d->res_coff;
+  a.ntaps = d->ntaps;
+  for (int t = 0; t < 16; ++t) { a.dy[t] = d->dy[t]; a.dx[t] = d->dx[t]; }
+  a.pre_relu = d->pre_relu; a.post_relu = d->post_relu; a.sigmoid = d->sigmoid;
+  LAVB_CHECK_ARG(d->res == nullptr || d->res_dtype == d->out_dtype, "conv_taps: residual dtype must equal output dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->in_dtype == LAVB_F32 && d->out_dtype == LAVB_F32) return launch_conv<float, float>(a, st);
+  if (d->in_dtype == LAVB_BF16 && d->out_dtype == LAVB_BF16) return launch_conv<__nv_bfloat16, __nv_bfloat16>(a, st);
+  if (d->in_dtype == LAVB_F32 && d->out_dtype == LAVB_BF16) return launch_conv<float, __nv_bfloat16>(a, st);
+  if (d->in_dtype == LAVB_BF16 && d->out_dtype == LAVB_F32) return launch_conv<__nv_bfloat16, float>(a, st);
+  LAVB_CHECK_ARG(false, "conv_taps: unsupported dtype combination");
+}
+
+extern "C" int lavb_pool2_affine_relu(const void* d_in, int dtype, int n, int hin, int win, int c, int in_cstride, int in_coff,
+                                      const float* d_scale, const float* d_shift, void* d_out, int out_cstride, int out_coff,
+                                      void* stream) {
+  LAVB_CHECK_ARG(hin % 2 == 0 && win % 2 == 0, "pool2: odd input size");
+  const long long total = (long long)n * (hin / 2) * (win / 2) * c;
+  if (total == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == LAVB_F32)
+    pool2_kernel<float><<<ceil_div(total, 256), 256, 0, st>>>((const float*)d_in, n, hin, win, c, in_cstride, in_coff, d_scale,
+                                                               d_shift, (float*)d_out, out_cstride, out_coff);
+  else if (dtype == LAVB_BF16)
+    pool2_kernel<__nv_bfloat16><<<ceil_div(total, 256), 256, 0, st>>>((const __nv_bfloat16*)d_in, n, hin, win, c, in_cstride,
+                                                                       in_coff, d_scale, d_shift, (__nv_bfloat16*)d_out,
+                                                                       out_cstride, out_coff);
+  else LAVB_CHECK_ARG(false, "pool2: bad dtype");
+  LAVB_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,239 @@
+// Point painting, sweep stacking and small ingest kernels (HBM-bound, one thread per point / element).
+//
+// paint: restates CoordConverter.forward + InferModel.point_painting
+// (team_code_v2/model_inference.py:75-93,280-297) as ONE kernel: 3 camera projections in the
+// reference's fp32 operation order (k-sequential FMA chains, IEEE division, truncation toward
+// zero, bounds test on the truncated integers, later camera wins), then one gather.
+#include "common.cuh"
+
+namespace lavb {
+
+struct CamSet {
+  float m[4][41];  // K(9) | lidar_to_world(16) | world_to_cam(16)
+  int ncam;
+};
+
+// row-vector dot in the order a BLAS sgemm with a k-loop produces: ((a0*b0 + a1*b1) + a2*b2) + a3*b3 with FMA
+__device__ __forceinline__ float dot4(const float* r, float x, float y, float z, float w) {
+  float acc = __fmul_rn(r[0], x);
+  acc = __fmaf_rn(r[1], y, acc);
+  acc = __fmaf_rn(r[2], z, acc);
+  acc = __fmaf_rn(r[3], w, acc);
+  return acc;
+}
+__device__ __forceinline__ float dot3(const float* r, float x, float y, float z) {
+  float acc = __fmul_rn(r[0], x);
+  acc = __fmaf_rn(r[1], y, acc);
+  acc = __fmaf_rn(r[2], z, acc);
+  return acc;
+}
+
+// float -> int64 the way x86 cvttss2si does for the cases that matter: NaN / inf / |v| >= 2^63 give the
+// "indefinite" INT64_MIN (which then fails every >= 0 test in the reference).
+__device__ __forceinline__ long long trunc_i64(float v) {
+  if (!(fabsf(v) < 9.2233720368547758e18f)) return (long long)0x8000000000000000ull;
+  return (long long)v;  // cvt.rzi
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) paint_kernel(const float* __restrict__ pts, int n, int pt_stride,
+                                                    const float* __restrict__ sem, int c_in, int H, int W,
+                                                    long long s_cam, long long s_c, long long s_y, long long s_x,
+                                                    const __grid_constant__ CamSet cams, float* __restrict__ out,
+                                                    int out_stride, int out_col0, int copy_cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = pts + (size_t)i * pt_stride;
+  float x, y, z;
+  float4 p4;
+  const bool vec = (pt_stride == 4);
+  if (vec) {
+    p4 = __ldg(reinterpret_cast<const float4*>(p));
+    x = p4.x; y = p4.y; z = p4.z;
+  } else {
+    x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+  }
+  int hit_cam = -1, hit_u = 0, hit_v = 0;
+#pragma unroll 1
+  for (int c = 0; c < cams.ncam; ++c) {
+    const float* K = cams.m[c];
+    const float* L = cams.m[c] + 9;
+    const float* Wc = cams.m[c] + 25;
+    // world = lidar_to_world @ [x,y,z,1]
+    const float w0 = dot4(L + 0, x, y, z, 1.f), w1 = dot4(L + 4, x, y, z, 1.f), w2 = dot4(L + 8, x, y, z, 1.f),
+                w3 = dot4(L + 12, x, y, z, 1.f);
+    // cam = world_to_cam @ world ; re-axis (cam_y, -cam_z, cam_x)
+    const float c0 = dot4(Wc + 0, w0, w1, w2, w3), c1 = dot4(Wc + 4, w0, w1, w2, w3), c2 = dot4(Wc + 8, w0, w1, w2, w3);
+    const float a0 = c1, a1 = -c2, a2 = c0;
+    // cam_2d = K @ cam
+    const float q0 = dot3(K + 0, a0, a1, a2), q1 = dot3(K + 3, a0, a1, a2), q2 = dot3(K + 6, a0, a1, a2);
+    const float den = __fadd_rn(1e-5f, q2);
+    const long long u = trunc_i64(__fdiv_rn(q0, den));
+    const long long v = trunc_i64(__fdiv_rn(q1, den));
+    const long long zi = trunc_i64(q2);
+    if (zi >= 0 && u >= 0 && u < W && v >= 0 && v < H) {
+      hit_cam = c; hit_u = (int)u; hit_v = (int)v;
+    }
+  }
+  float* o = out + (size_t)i * out_stride;
+  if (copy_cols == 4 && vec && out_col0 >= 4 && (out_stride % 4) == 0) {
+    *reinterpret_cast<float4*>(o) = p4;
+  } else {
+    for (int k = 0; k < copy_cols; ++k) o[k] = __ldg(p + k);
+  }
+  const int c_out = (MODE == 0) ? c_in : c_in - 1;
+  o += out_col0;
+  if (hit_cam < 0) {
+    for (int k = 0; k < c_out; ++k) o[k] = 0.f;
+    return;
+  }
+  const float* s = sem + hit_cam * s_cam + hit_v * s_y + hit_u * s_x;
+  if (MODE == 0) {
+    for (int k = 0; k < c_out; ++k) o[k] = __ldg(s + k * s_c);
+  } else {
+    float pr[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pr[k] = (k < c_in) ? __ldg(s + k * s_c) : 0.f;
+    if (MODE == 2) {  // softmax over c_in logits (torch.softmax: exp(x-max)/sum)
+      float mx = pr[0];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) if (k < c_in) mx = fmaxf(mx, pr[k]);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if (k < c_in) { pr[k] = expf(pr[k] - mx); sum += pr[k]; }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if (k < c_in) pr[k] = __fdiv_rn(pr[k], sum);
+    }
+    const float bg = __fsub_rn(1.f, pr[0]);  // pred_sem[:,1:] * (1 - pred_sem[:,:1]), model_inference.py:45
+#pragma unroll
+    for (int k = 1; k < 8; ++k) if (k < c_in) o[k - 1] = __fmul_rn(pr[k], bg);
+  }
+}
+
+struct StackParams { float R[9]; float dx, dy; };
+
+__global__ void __launch_bounds__(256) stack_kernel(const float* __restrict__ src, int n, int src_cols,
+                                                    const __grid_constant__ StackParams P, int time_idx, int n_time,
+                                                    int roof_filter, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* s = src + (size_t)i * src_cols;
+  const int dcols = src_cols + n_time;
+  float* d = dst + (size_t)i * dcols;
+  const float x = __ldg(s), y = __ldg(s + 1), z = __ldg(s + 2);
+  // lidar @ R  (row vector times matrix, k-sequential), then += dloc: lav_agent_fast.py:555-563
+  float nx = __fmaf_rn(z, P.R[6], __fmaf_rn(y, P.R[3], __fmul_rn(x, P.R[0])));
+  float ny = __fmaf_rn(z, P.R[7], __fmaf_rn(y, P.R[4], __fmul_rn(x, P.R[1])));
+  float nz = __fmaf_rn(z, P.R[8], __fmaf_rn(y, P.R[5], __fmul_rn(x, P.R[2])));
+  nx = __fadd_rn(nx, P.dx);
+  ny = __fadd_rn(ny, P.dy);
+  if (roof_filter) {  // LAVAgent.preprocess, lav_agent.py:450 — on the sensor-frame coordinates
+    if (x > -2.4f && x < 0.f && y > -0.8f && y < 0.8f && z > -1.5f && z < -1.f) nx = __int_as_float(0x7fc00000);
+  }
+  d[0] = nx; d[1] = ny; d[2] = nz;
+  for (int k = 3; k < src_cols; ++k) d[k] = __ldg(s + k);
+  for (int k = 0; k < n_time; ++k) d[src_cols + k] = (k == time_idx) ? 1.f : 0.f;
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(256) rgb_norm_kernel(const void* __restrict__ rgb, int src_u8_nhwc, int n, int h, int w,
+                                                       TOut* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // pixel index
+  const long long npix = (long long)n * h * w;
+  if (i >= npix) return;
+  float r, g, b;
+  if (src_u8_nhwc) {
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(rgb) + i * 3;
+    r = p[0]; g = p[1]; b = p[2];
+  } else {
+    const long long hw = (long long)h * w;
+    const long long img = i / hw, pix = i - img * hw;
+    const float* p = reinterpret_cast<const float*>(rgb) + img * 3 * hw + pix;
+    r = __ldg(p); g = __ldg(p + hw); b = __ldg(p + 2 * hw);
+  }
+  // (x/255. - .5)*2 , rgb.py:41 — same three fp32 roundings
+  float4 v;
+  v.x = __fmul_rn(__fsub_rn(__fdiv_rn(r, 255.f), .5f), 2.f);
+  v.y = __fmul_rn(__fsub_rn(__fdiv_rn(g, 255.f), .5f), 2.f);
+  v.z = __fmul_rn(__fsub_rn(__fdiv_rn(b, 255.f), .5f), 2.f);
+  v.w = 0.f;
+  store4<TOut>(out + i * 4, v);
+}
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) convert_kernel(const TS* __restrict__ s, TD* __restrict__ d, long long count) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < count) {
+    store4<TD>(d + i, load4<TS>(s + i));
+  } else {
+    for (; i < count; ++i) d[i] = from_f32<TD>(to_f32<TS>(s[i]));
+  }
+}
+
+}  // namespace lavb
+
+using namespace lavb;
+
+extern "C" int lavb_paint(const float* d_pts, int n, int pt_stride, const float* d_sem, int ncam, int c_in, int h, int w,
+                          long long s_cam, long long s_c, long long s_y, long long s_x, const float* h_cams, int mode,
+                          float* d_out, int out_stride, int out_col0, int copy_cols, void* stream) {
+  LAVB_CHECK_ARG(n >= 0 && pt_stride >= 3, "paint: bad n/pt_stride");
+  LAVB_CHECK_ARG(ncam >= 1 && ncam <= 4, "paint: ncam must be 1..4 (got %d)", ncam);
+  LAVB_CHECK_ARG(mode >= 0 && mode <= 2, "paint: mode must be 0..2");
+  LAVB_CHECK_ARG(c_in >= (mode ? 2 : 1) && c_in <= 8, "paint: c_in out of range (got %d)", c_in);
+  const int c_out = mode ? c_in - 1 : c_in;
+  LAVB_CHECK_ARG(copy_cols >= 0 && copy_cols <= pt_stride && out_col0 >= copy_cols && out_col0 + c_out <= out_stride,
+                 "paint: output row layout inconsistent");
+  if (n == 0) return 0;
+  CamSet cs;
+  memcpy(cs.m, h_cams, sizeof(float) * 41 * ncam);
+  cs.ncam = ncam;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = ceil_div(n, 256);
+#define LAUNCH(M) paint_kernel<M><<<blocks, 256, 0, st>>>(d_pts, n, pt_stride, d_sem, c_in, h, w, s_cam, s_c, s_y, s_x, cs, \
+                                                           d_out, out_stride, out_col0, copy_cols)
+  if (mode == 0) LAUNCH(0); else if (mode == 1) LAUNCH(1); else LAUNCH(2);
+#undef LAUNCH
+  LAVB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int lavb_stack_sweep(const float* d_src, int n, int src_cols, const float* h_R, float dx, float dy, int time_idx,
+                                int n_time, int roof_filter, float* d_dst, void* stream) {
+  LAVB_CHECK_ARG(n >= 0 && src_cols >= 3 && n_time >= 0 && time_idx >= 0 && (n_time == 0 || time_idx < n_time),
+                 "stack_sweep: bad arguments");
+  if (n == 0) return 0;
+  StackParams P;
+  memcpy(P.R, h_R, sizeof(float) * 9);
+  P.dx = dx; P.dy = dy;
+  stack_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(d_src, n, src_cols, P, time_idx, n_time, roof_filter, d_dst);
+  LAVB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int lavb_rgb_normalize(const void* d_rgb, int src_is_u8_nhwc, int n, int h, int w, void* d_out, int out_dtype,
+                                  void* stream) {
+  const long long npix = (long long)n * h * w;
+  if (npix == 0) return 0;
+  const int blocks = ceil_div(npix, 256);
+  if (out_dtype == LAVB_F32)
+    rgb_norm_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_rgb, src_is_u8_nhwc, n, h, w, (float*)d_out);
+  else if (out_dtype == LAVB_BF16)
+    rgb_norm_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_rgb, src_is_u8_nhwc, n, h, w, (__nv_bfloat16*)d_out);
+  else LAVB_CHECK_ARG(false, "rgb_normalize: bad dtype");
+  LAVB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int lavb_convert(const void* d_src, int src_dtype, void* d_dst, int dst_dtype, long long count, void* stream) {
+  if (count == 0) return 0;
+  const int blocks = ceil_div(ceil_div(count, 4), 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_dtype == LAVB_F32 && dst_dtype == LAVB_BF16)
+    convert_kernel<float, __nv_bfloat16><<<blocks, 256, 0, st>>>((const float*)d_src, (__nv_bfloat16*)d_dst, count);
+  else if (src_dtype == LAVB_BF16 && dst_dtype == LAVB_F32)
+    convert_kernel<__nv_bfloat16, float><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)d_src, (float*)d_dst, count);
+  else LAVB_CHECK_ARG(false, "convert: unsupported dtype pair");
+  LAVB_LAUNCH_OK();
+  return 0;
+}

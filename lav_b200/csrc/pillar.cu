@@ -1,0 +1,373 @@
+// PointPillars dynamic voxeliser + pillar encoder (lav/models/point_pillar.py:55-116) without sort/unique:
+// a pillar is addressed directly by (b, xi, yi); pass 1 accumulates the per-pillar centroid sums, pass 2
+// decorates each point, runs the 2-layer point MLP and max-pools into the NHWC canvas.
+#include "common.cuh"
+
+namespace lavb {
+
+constexpr int kMaxBatch = 128;
+
+struct Clouds {
+  long long start[kMaxBatch];  // first row of cloud b in the point buffer
+  int cum[kMaxBatch + 1];      // exclusive prefix of cloud sizes
+  int batch;
+};
+
+struct Grid {
+  float min_x, max_x, min_y, max_y, ppm;
+  int nx, ny;
+};
+
+__device__ __forceinline__ int find_cloud(const Clouds& c, int i) {
+  int lo = 0, hi = c.batch - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (c.cum[mid] <= i) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// grid_locations, point_pillar.py:70-79: half-open window test on the raw fp32 coordinates, then
+// trunc((v - min) * ppm) in fp32.  Returns false for dropped points (NaN fails every comparison).
+__device__ __forceinline__ bool locate(const Grid& g, float x, float y, int& xi, int& yi) {
+  if (!(x >= g.min_x && x < g.max_x && y >= g.min_y && y < g.max_y)) return false;
+  xi = (int)__fmul_rn(__fsub_rn(x, g.min_x), g.ppm);
+  yi = (int)__fmul_rn(__fsub_rn(y, g.min_y), g.ppm);
+  return true;
+}
+
+// pillar key space: xi in [0,nx], yi in [0,ny]  (index == n can occur by rounding)
+__device__ __forceinline__ long long pillar_key(const Grid& g, int b, int xi, int yi) {
+  return ((long long)b * (g.nx + 1) + xi) * (g.ny + 1) + yi;
+}
+// scatter_points, point_pillar.py:87-90: row = clamp(ny-1-xi), col = clamp(yi)
+__device__ __forceinline__ long long canvas_cell(const Grid& g, int b, int xi, int yi) {
+  int row = g.ny - 1 - xi; row = row < 0 ? 0 : (row > g.ny - 1 ? g.ny - 1 : row);
+  int col = yi < 0 ? 0 : (yi > g.nx - 1 ? g.nx - 1 : yi);
+  return ((long long)b * g.ny + row) * g.nx + col;
+}
+
+__global__ void __launch_bounds__(256) pillar_stats_kernel(const float* __restrict__ pts, int pt_stride,
+                                                           const __grid_constant__ Clouds clouds,
+                                                           const __grid_constant__ Grid g, float4* __restrict__ stats) {
+  const int total = clouds.cum[clouds.batch];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = find_cloud(clouds, i);
+    const float* p = pts + (clouds.start[b] + (i - clouds.cum[b])) * pt_stride;
+    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    int xi, yi;
+    if (!locate(g, x, y, xi, yi)) continue;
+    atomicAdd(&stats[pillar_key(g, b, xi, yi)], make_float4(x, y, z, 1.f));  // red.global.add.v4.f32 (sm_90+)
+  }
+}
+
+// decorate, point_pillar.py:55-68: [pt(D) | xyz - centroid | x - (yi/ppm + min_x) | y - (xi/ppm + min_y)]
+// (the cell-origin terms use the OTHER axis' index and no +0.5 — replicated on purpose).
+template <int D>
+__device__ __forceinline__ void decorate(const Grid& g, const float* __restrict__ p, int xi, int yi, float4 st,
+                                         float* f) {
+#pragma unroll
+  for (int k = 0; k < D; ++k) f[k] = __ldg(p + k);
+  f[D + 0] = __fsub_rn(f[0], __fdiv_rn(st.x, st.w));
+  f[D + 1] = __fsub_rn(f[1], __fdiv_rn(st.y, st.w));
+  f[D + 2] = __fsub_rn(f[2], __fdiv_rn(st.z, st.w));
+  f[D + 3] = __fsub_rn(f[0], __fadd_rn(__fdiv_rn((float)yi, g.ppm), g.min_x));
+  f[D + 4] = __fsub_rn(f[1], __fadd_rn(__fdiv_rn((float)xi, g.ppm), g.min_y));
+}
+
+// One thread per point; both weight matrices live in shared memory k-major so that a thread reads the
+// weights of 4 consecutive output channels with one broadcast LDS.128.
+template <int D, int H1, int H2>
+__global__ void __launch_bounds__(128) pillar_encode_kernel(const float* __restrict__ pts, int pt_stride,
+                                                            const __grid_constant__ Clouds clouds,
+                                                            const __grid_constant__ Grid g,
+                                                            const float4* __restrict__ stats,
+                                                            const float* __restrict__ w1, const float* __restrict__ s1,
+                                                            const float* __restrict__ t1, const float* __restrict__ w2,
+                                                            const float* __restrict__ s2, const float* __restrict__ t2,
+                                                            float* __restrict__ canvas) {
+  constexpr int F = D + 5;
+  __shared__ __align__(16) float w1s[F][H1];
+  __shared__ __align__(16) float w2s[H1][H2];
+  __shared__ float s1s[H1], t1s[H1], s2s[H2], t2s[H2];
+  for (int i = threadIdx.x; i < F * H1; i += blockDim.x) w1s[i % F][i / F] = __ldg(w1 + i);   // w1 is [H1][F]
+  for (int i = threadIdx.x; i < H1 * H2; i += blockDim.x) w2s[i % H1][i / H1] = __ldg(w2 + i); // w2 is [H2][H1]
+  for (int i = threadIdx.x; i < H1; i += blockDim.x) { s1s[i] = __ldg(s1 + i); t1s[i] = __ldg(t1 + i); }
+  for (int i = threadIdx.x; i < H2; i += blockDim.x) { s2s[i] = __ldg(s2 + i); t2s[i] = __ldg(t2 + i); }
+  __syncthreads();
+  const int total = clouds.cum[clouds.batch];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = find_cloud(clouds, i);
+    const float* p = pts + (clouds.start[b] + (i - clouds.cum[b])) * pt_stride;
+    int xi, yi;
+    if (!locate(g, __ldg(p), __ldg(p + 1), xi, yi)) continue;
+    const float4 st = __ldg(&stats[pillar_key(g, b, xi, yi)]);
+    float f[F];
+    decorate<D>(g, p, xi, yi, st, f);
+    float h[H1];
+#pragma unroll
+    for (int j = 0; j < H1; ++j) h[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < F; ++k) {
+#pragma unroll
+      for (int j = 0; j < H1; j += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(&w1s[k][j]);
+        h[j] = fmaf(f[k], w.x, h[j]); h[j + 1] = fmaf(f[k], w.y, h[j + 1]);
+        h[j + 2] = fmaf(f[k], w.z, h[j + 2]); h[j + 3] = fmaf(f[k], w.w, h[j + 3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < H1; ++j) { const float v = fmaf(h[j], s1s[j], t1s[j]); h[j] = v > 0.f ? v : 0.f; }
+    float* cell = canvas + canvas_cell(g, b, xi, yi) * H2;
+#pragma unroll 1
+    for (int j0 = 0; j0 < H2; j0 += 16) {
+      float o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < H1; ++k) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(&w2s[k][j0 + j]);
+          o[j] = fmaf(h[k], w.x, o[j]); o[j + 1] = fmaf(h[k], w.y, o[j + 1]);
+          o[j + 2] = fmaf(h[k], w.z, o[j + 2]); o[j + 3] = fmaf(h[k], w.w, o[j + 3]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float v = fmaf(o[j], s2s[j0 + j], t2s[j0 + j]);
+        // post-ReLU values are >= +0, so float max == signed-int max on the bit pattern and the zero-filled
+        // canvas is both the identity of the max and the value of empty cells.
+        if (v > 0.f) atomicMax(reinterpret_cast<int*>(cell + j0 + j), __float_as_int(v));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- training-mode pieces
+// order-preserving compaction of the in-window points: per-block counts -> single-block scan -> write
+constexpr int kCompactBlock = 1024;
+
+__global__ void __launch_bounds__(kCompactBlock) keep_count_kernel(const float* __restrict__ pts, int pt_stride,
+                                                                   const __grid_constant__ Clouds clouds,
+                                                                   const __grid_constant__ Grid g, int* __restrict__ block_count) {
+  const int total = clouds.cum[clouds.batch];
+  const int i = blockIdx.x * kCompactBlock + threadIdx.x;
+  int keep = 0;
+  if (i < total) {
+    const int b = find_cloud(clouds, i);
+    const float* p = pts + (clouds.start[b] + (i - clouds.cum[b])) * pt_stride;
+    int xi, yi;
+    keep = locate(g, __ldg(p), __ldg(p + 1), xi, yi) ? 1 : 0;
+  }
+  const int c = __syncthreads_count(keep);
+  if (threadIdx.x == 0) block_count[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(int* __restrict__ block_count, int nblocks, int* __restrict__ total_out) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblocks ? block_count[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = warp_sum[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += y; }
+      warp_sum[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int warp_off = (threadIdx.x >> 5) ? warp_sum[(threadIdx.x >> 5) - 1] : 0;
+    const int carry = carry_s;
+    if (i < nblocks) block_count[i] = carry + warp_off + x - v;  // exclusive
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_off + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = carry_s;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kCompactBlock) decorate_write_kernel(const float* __restrict__ pts, int pt_stride,
+                                                                       const __grid_constant__ Clouds clouds,
+                                                                       const __grid_constant__ Grid g,
+                                                                       const float4* __restrict__ stats,
+                                                                       const int* __restrict__ block_off,
+                                                                       float* __restrict__ feat, int* __restrict__ cell) {
+  constexpr int F = D + 5;
+  __shared__ int warp_cnt[32];
+  const int total = clouds.cum[clouds.batch];
+  const int i = blockIdx.x * kCompactBlock + threadIdx.x;
+  int keep = 0, xi = 0, yi = 0, b = 0;
+  const float* p = nullptr;
+  if (i < total) {
+    b = find_cloud(clouds, i);
+    p = pts + (clouds.start[b] + (i - clouds.cum[b])) * pt_stride;
+    keep = locate(g, __ldg(p), __ldg(p + 1), xi, yi) ? 1 : 0;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_cnt[warp] = __popc(m);
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_cnt[lane], x = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    warp_cnt[lane] = x - w;
+  }
+  __syncthreads();
+  if (!keep) return;
+  const int row = block_off[blockIdx.x] + warp_cnt[warp] + __popc(m & ((1u << lane) - 1u));
+  float f[F];
+  decorate<D>(g, p, xi, yi, __ldg(&stats[pillar_key(g, b, xi, yi)]), f);
+#pragma unroll
+  for (int k = 0; k < F; ++k) feat[(size_t)row * F + k] = f[k];
+  cell[row] = (int)canvas_cell(g, b, xi, yi);
+}
+
+__global__ void __launch_bounds__(256) scatter_max_kernel(const float* __restrict__ h, const int* __restrict__ cell,
+                                                          long long mc, int c, float* __restrict__ canvas) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mc) return;
+  const int row = (int)(i / c), ch = (int)(i - (long long)row * c);
+  const float v = __ldg(h + i);
+  if (v > 0.f) atomicMax(reinterpret_cast<int*>(canvas + (long long)__ldg(cell + row) * c + ch), __float_as_int(v));
+}
+__global__ void __launch_bounds__(256) scatter_arg_kernel(const float* __restrict__ h, const int* __restrict__ cell,
+                                                          long long mc, int c, const float* __restrict__ canvas,
+                                                          int* __restrict__ argmax) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mc) return;
+  const int row = (int)(i / c), ch = (int)(i - (long long)row * c);
+  const long long o = (long long)__ldg(cell + row) * c + ch;
+  const float v = __ldg(h + i);
+  const float top = canvas[o];
+  if (v == top || (!(v > 0.f) && top == 0.f)) atomicMin(argmax + o, row);  // ties -> smallest row (deterministic)
+}
+__global__ void __launch_bounds__(256) scatter_bwd_kernel(const float* __restrict__ gcanvas, const int* __restrict__ argmax,
+                                                          const int* __restrict__ cell, long long mc, int c,
+                                                          float* __restrict__ gh) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mc) return;
+  const int row = (int)(i / c), ch = (int)(i - (long long)row * c);
+  const long long o = (long long)__ldg(cell + row) * c + ch;
+  gh[i] = (__ldg(argmax + o) == row) ? __ldg(gcanvas + o) : 0.f;
+}
+
+static int fill_clouds(Clouds& c, const long long* start, const int* count, int batch) {
+  if (batch < 1 || batch > kMaxBatch) { set_error("pillar: batch must be 1..%d (got %d)", kMaxBatch, batch); return 1; }
+  c.batch = batch;
+  long long cum = 0;
+  for (int b = 0; b < batch; ++b) {
+    if (count[b] < 0 || start[b] < 0) { set_error("pillar: negative cloud start/count"); return 1; }
+    c.start[b] = start[b];
+    c.cum[b] = (int)cum;
+    cum += count[b];
+    if (cum > 0x7fffffffLL) { set_error("pillar: more than 2^31 points"); return 1; }
+  }
+  c.cum[batch] = (int)cum;
+  return 0;
+}
+
+static size_t stats_bytes(int batch, int nx, int ny) { return (size_t)batch * (nx + 1) * (ny + 1) * sizeof(float4); }
+
+}  // namespace lavb
+
+using namespace lavb;
+
+extern "C" size_t lavb_pillar_workspace_bytes(int batch, int nx, int ny) {
+  // centroid sums + compaction scratch (block counts for up to 2^31 points / 1024) + total
+  return stats_bytes(batch, nx, ny) + ((size_t)(1 << 21) + 16) * sizeof(int);
+}
+
+extern "C" int lavb_pillar_forward(const float* d_pts, int pt_stride, int d, const long long* h_cloud_start,
+                                   const int* h_cloud_count, int batch, float min_x, float max_x, float min_y, float max_y,
+                                   float ppm, int nx, int ny, const float* d_w1, const float* d_s1, const float* d_t1, int h1,
+                                   const float* d_w2, const float* d_s2, const float* d_t2, int h2, void* d_canvas,
+                                   int canvas_dtype, void* d_workspace, void* stream) {
+  Clouds clouds;
+  if (fill_clouds(clouds, h_cloud_start, h_cloud_count, batch)) return 1;
+  LAVB_CHECK_ARG(d == 11 && h1 == 64 && h2 == 64, "pillar_forward: only the v2 configuration (D=11, features [64,64]) is built (got D=%d [%d,%d])", d, h1, h2);
+  LAVB_CHECK_ARG(canvas_dtype == LAVB_F32, "pillar_forward: canvas must be fp32");
+  LAVB_CHECK_ARG(pt_stride >= d, "pillar_forward: pt_stride < d");
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g{min_x, max_x, min_y, max_y, ppm, nx, ny};
+  float4* stats = reinterpret_cast<float4*>(d_workspace);
+  LAVB_CUDA_OK(cudaMemsetAsync(stats, 0, stats_bytes(batch, nx, ny), st));
+  LAVB_CUDA_OK(cudaMemsetAsync(d_canvas, 0, (size_t)batch * nx * ny * h2 * sizeof(float), st));
+  const int total = clouds.cum[batch];
+  if (total == 0) return 0;
+  const int blocks1 = min(ceil_div(total, 256), kNumSMs * 8);
+  pillar_stats_kernel<<<blocks1, 256, 0, st>>>(d_pts, pt_stride, clouds, g, stats);
+  LAVB_LAUNCH_OK();
+  const int blocks2 = min(ceil_div(total, 128), kNumSMs * 4);
+  pillar_encode_kernel<11, 64, 64><<<blocks2, 128, 0, st>>>(d_pts, pt_stride, clouds, g, stats, d_w1, d_s1, d_t1, d_w2, d_s2,
+                                                              d_t2, reinterpret_cast<float*>(d_canvas));
+  LAVB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int lavb_pillar_decorate(const float* d_pts, int pt_stride, int d, const long long* h_cloud_start,
+                                    const int* h_cloud_count, int batch, float min_x, float max_x, float min_y, float max_y,
+                                    float ppm, int nx, int ny, float* d_feat, int* d_cell, int* h_m, void* d_workspace,
+                                    void* stream) {
+  Clouds clouds;
+  if (fill_clouds(clouds, h_cloud_start, h_cloud_count, batch)) return 1;
+  LAVB_CHECK_ARG(d == 11, "pillar_decorate: only D=11 is built (got %d)", d);
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g{min_x, max_x, min_y, max_y, ppm, nx, ny};
+  float4* stats = reinterpret_cast<float4*>(d_workspace);
+  int* scratch = reinterpret_cast<int*>(reinterpret_cast<char*>(d_workspace) + stats_bytes(batch, nx, ny));
+  const int total = clouds.cum[batch];
+  *h_m = 0;
+  if (total == 0) return 0;
+  const int nblk = ceil_div(total, kCompactBlock);
+  LAVB_CHECK_ARG(nblk <= (1 << 21), "pillar_decorate: too many points");
+  int* d_total = scratch + (1 << 21);
+  LAVB_CUDA_OK(cudaMemsetAsync(stats, 0, stats_bytes(batch, nx, ny), st));
+  pillar_stats_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, st>>>(d_pts, pt_stride, clouds, g, stats);
+  LAVB_LAUNCH_OK();
+  keep_count_kernel<<<nblk, kCompactBlock, 0, st>>>(d_pts, pt_stride, clouds, g, scratch);
+  LAVB_LAUNCH_OK();
+  scan_blocks_kernel<<<1, 1024, 0, st>>>(scratch, nblk, d_total);
+  LAVB_LAUNCH_OK();
+  if (d_feat != nullptr) {
+    decorate_write_kernel<11><<<nblk, kCompactBlock, 0, st>>>(d_pts, pt_stride, clouds, g, stats, scratch, d_feat, d_cell);
+    LAVB_LAUNCH_OK();
+  }
+  LAVB_CUDA_OK(cudaMemcpyAsync(h_m, d_total, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LAVB_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int lavb_pillar_scatter_max(const float* d_h, const int* d_cell, int m, int c, long long n_cells, float* d_canvas,
+                                       int* d_argmax, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  LAVB_CUDA_OK(cudaMemsetAsync(d_canvas, 0, (size_t)n_cells * c * sizeof(float), st));
+  if (d_argmax) LAVB_CUDA_OK(cudaMemsetAsync(d_argmax, 0x7f, (size_t)n_cells * c * sizeof(int), st));
+  const long long mc = (long long)m * c;
+  if (mc == 0) return 0;
+  scatter_max_kernel<<<ceil_div(mc, 256), 256, 0, st>>>(d_h, d_cell, mc, c, d_canvas);
+  LAVB_LAUNCH_OK();
+  if (d_argmax) {
+    scatter_arg_kernel<<<ceil_div(mc, 256), 256, 0, st>>>(d_h, d_cell, mc, c, d_canvas, d_argmax);
+    LAVB_LAUNCH_OK();
+  }
+  return 0;
+}
+
+extern "C" int lavb_pillar_scatter_max_bwd(const float* d_gcanvas, const int* d_argmax, const int* d_cell, int m, int c,
+                                                 float* d_gh, void* stream) {
+  const long long mc = (long long)m * c;
+  if (mc == 0) return 0;
+  scatter_bwd_kernel<<<ceil_div(mc, 256), 256, 0, (cudaStream_t)stream>>>(d_gcanvas, d_argmax, d_cell, mc, c, d_gh);
+  LAVB_LAUNCH_OK();
+  return 0;
+}

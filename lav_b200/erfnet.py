@@ -1,0 +1,157 @@
+"""ERFNet — drop-in mirror of lav/models/erfnet.py (same class names, constructors, state_dict keys).
+
+The module tree only holds parameters; ``ERFNet.forward_nhwc`` runs the whole network as a
+sequence of tap-list convolutions with fused epilogues (bias / folded eval BatchNorm / residual /
+ReLU) in hand-written CUDA.  Eval mode only (the seg model is frozen on the LAV frame path,
+lav_agent.py:116-124); no CPU path.
+"""
+import torch
+from torch import nn
+
+from . import ops
+from .capi import LavbError
+from .layers import PlanMixin, TapConv, bn_affine
+
+_DT = {"fp32": torch.float32, "bf16": torch.bfloat16}
+
+
+class DownsamplerBlock(nn.Module):
+    def __init__(self, ninput, noutput):
+        super().__init__()
+        self.conv = nn.Conv2d(ninput, noutput - ninput, (3, 3), stride=2, padding=1, bias=True)
+        self.pool = nn.MaxPool2d(2, stride=2)
+        self.bn = nn.BatchNorm2d(noutput, eps=1e-3)
+
+
+class non_bottleneck_1d(nn.Module):
+    def __init__(self, chann, dropprob, dilated):
+        super().__init__()
+        self.conv3x1_1 = nn.Conv2d(chann, chann, (3, 1), stride=1, padding=(1, 0), bias=True)
+        self.conv1x3_1 = nn.Conv2d(chann, chann, (1, 3), stride=1, padding=(0, 1), bias=True)
+        self.bn1 = nn.BatchNorm2d(chann, eps=1e-03)
+        self.conv3x1_2 = nn.Conv2d(chann, chann, (3, 1), stride=1, padding=(1 * dilated, 0), bias=True, dilation=(dilated, 1))
+        self.conv1x3_2 = nn.Conv2d(chann, chann, (1, 3), stride=1, padding=(0, 1 * dilated), bias=True, dilation=(1, dilated))
+        self.bn2 = nn.BatchNorm2d(chann, eps=1e-03)
+        self.dropout = nn.Dropout2d(dropprob)
+
+
+class Encoder(nn.Module):
+    def __init__(self, num_classes):
+        super().__init__()
+        self.initial_block = DownsamplerBlock(3, 16)
+        self.layers = nn.ModuleList()
+        self.layers.append(DownsamplerBlock(16, 64))
+        for x in range(0, 5):
+            self.layers.append(non_bottleneck_1d(64, 0.03, 1))
+        self.layers.append(DownsamplerBlock(64, 128))
+        for x in range(0, 2):
+            self.layers.append(non_bottleneck_1d(128, 0.3, 2))
+            self.layers.append(non_bottleneck_1d(128, 0.3, 4))
+            self.layers.append(non_bottleneck_1d(128, 0.3, 8))
+            self.layers.append(non_bottleneck_1d(128, 0.3, 16))
+        # present in the checkpoint, unused by the decoder path (erfnet.py:85, predict=False)
+        self.output_conv = nn.Conv2d(128, num_classes, 1, stride=1, padding=0, bias=True)
+
+
+class UpsamplerBlock(nn.Module):
+    def __init__(self, ninput, noutput):
+        super().__init__()
+        self.conv = nn.ConvTranspose2d(ninput, noutput, 3, stride=2, padding=1, output_padding=1, bias=True)
+        self.bn = nn.BatchNorm2d(noutput, eps=1e-3)
+
+
+class Decoder(nn.Module):
+    def __init__(self, num_classes):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        self.layers.append(UpsamplerBlock(128, 64))
+        self.layers.append(non_bottleneck_1d(64, 0, 1))
+        self.layers.append(non_bottleneck_1d(64, 0, 1))
+        self.layers.append(UpsamplerBlock(64, 16))
+        self.layers.append(non_bottleneck_1d(16, 0, 1))
+        self.layers.append(non_bottleneck_1d(16, 0, 1))
+        self.output_conv = nn.ConvTranspose2d(16, num_classes, 2, stride=2, padding=0, output_padding=0, bias=True)
+
+
+class _Down:
+    def __init__(self, m):
+        s, t = bn_affine(m.bn)
+        nconv = m.conv.out_channels
+        cin = m.conv.in_channels
+        self.cin, self.nconv, self.nout = cin, nconv, m.bn.num_features
+        self.conv = TapConv(m.conv.weight, False, 2, 1, bias=m.conv.bias, scale=s[:nconv].clone(), shift=t[:nconv].clone(),
+                            post_relu=True, cin_pad=(cin + 3) // 4 * 4)
+        self.ps, self.pt = s[nconv:].contiguous(), t[nconv:].contiguous()
+
+    def __call__(self, x, dt):
+        n, h, w, _ = x.shape
+        out = torch.empty((n, h // 2, w // 2, self.nout), dtype=dt, device=x.device)
+        self.conv(x, out=out)
+        if x.dtype != dt:   # pool kernel is single-dtype; only the fp32 RGB ingest of a bf16 net hits this
+            x = ops.convert(x, dt)
+        ops.pool2_affine_relu(x, self.cin, 0, self.ps, self.pt, out, self.nconv)
+        return out
+
+
+class _NB1D:
+    def __init__(self, m):
+        d = m.conv3x1_2.dilation[0]
+        s1, t1 = bn_affine(m.bn1)
+        s2, t2 = bn_affine(m.bn2)
+        self.a = TapConv(m.conv3x1_1.weight, False, 1, (1, 0), bias=m.conv3x1_1.bias, post_relu=True)
+        self.b = TapConv(m.conv1x3_1.weight, False, 1, (0, 1), bias=m.conv1x3_1.bias, scale=s1, shift=t1, post_relu=True)
+        self.c = TapConv(m.conv3x1_2.weight, False, 1, (d, 0), (d, 1), bias=m.conv3x1_2.bias, post_relu=True)
+        self.d = TapConv(m.conv1x3_2.weight, False, 1, (0, d), (1, d), bias=m.conv1x3_2.bias, scale=s2, shift=t2, post_relu=True)
+
+    def __call__(self, x, dt):
+        y = self.a(x)
+        y = self.b(y)
+        y = self.c(y)
+        return self.d(y, res=x)   # relu(bn2(conv) + x), erfnet.py:61
+
+
+class _Up:
+    def __init__(self, m):
+        s, t = bn_affine(m.bn)
+        self.conv = TapConv(m.conv.weight, True, 2, 1, 1, 1, bias=m.conv.bias, scale=s, shift=t, post_relu=True)
+
+    def __call__(self, x, dt):
+        return self.conv(x)
+
+
+class ERFNet(PlanMixin, nn.Module):
+    def __init__(self, num_classes):
+        super().__init__()
+        self.encoder = Encoder(num_classes)
+        self.decoder = Decoder(num_classes)
+        self.precision = "fp32"
+
+    def _build(self, device):
+        def wrap(m):
+            if isinstance(m, DownsamplerBlock):
+                return _Down(m)
+            if isinstance(m, non_bottleneck_1d):
+                return _NB1D(m)
+            return _Up(m)
+        seq = [wrap(self.encoder.initial_block)] + [wrap(m) for m in self.encoder.layers] + [wrap(m) for m in self.decoder.layers]
+        oc = self.decoder.output_conv
+        return seq, TapConv(oc.weight, True, 2, 0, 1, 0, bias=oc.bias)
+
+    def forward_nhwc(self, x):
+        """x: (N,H,W,4) normalised RGB (4th channel ignored) -> logits NHWC (N,H,W,num_classes) fp32."""
+        if self.training:
+            raise LavbError("lav_b200.ERFNet is inference-only (the seg model is frozen on the frame path)")
+        seq, out_conv = self._plan_get(x.device, self._build)
+        dt = _DT[self.precision]
+        for blk in seq:
+            x = blk(x, dt)
+        return out_conv(x, out_dtype=torch.float32)
+
+    def forward(self, input):
+        """input: normalised NCHW float (as erfnet.py:144-146)."""
+        if not input.is_cuda:
+            raise LavbError("lav_b200.ERFNet needs CUDA tensors (no CPU fallback)")
+        n, c, h, w = input.shape
+        x = torch.zeros((n, h, w, 4), dtype=torch.float32, device=input.device)
+        x[..., :3] = input.permute(0, 2, 3, 1)
+        return self.forward_nhwc(x).permute(0, 3, 1, 2)

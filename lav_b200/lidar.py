@@ -1,0 +1,175 @@
+"""LiDARModel / ConvBackbone / Head — drop-in mirrors of lav/models/lidar.py.
+
+Same constructors, forward signatures and ``state_dict`` keys; every conv / transposed conv
+(+ReLU+BatchNorm epilogue) runs in hand-written CUDA (csrc/conv_taps.cu; csrc/conv_umma.cu on the
+bf16 path).  Tensors keep the reference's logical NCHW shapes but are stored channels-last.
+``precision`` = 'fp32' (exact path, default) or 'bf16' (tensor-core path).
+"""
+import torch
+from torch import nn
+
+from .capi import LavbError
+from .layers import PlanMixin, TapConv, bn_affine
+from .point_pillar import PointPillarNet
+
+_DT = {"fp32": torch.float32, "bf16": torch.bfloat16}
+
+
+def _nhwc(x):
+    """logical NCHW tensor -> contiguous NHWC buffer (free for channels-last inputs)."""
+    if not x.is_cuda:
+        raise LavbError("lav_b200 modules need CUDA tensors (no CPU fallback)")
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+class ConvBackbone(PlanMixin, nn.Module):
+    def __init__(self, num_feature=64, norm_cfg={'eps': 1e-3, 'momentum': 0.01}):
+        super().__init__()
+        nf = num_feature
+
+        def stage(cin, cout, n):
+            L = []
+            for i in range(n):
+                L += [nn.Conv2d(cin if i == 0 else cout, cout, 3, 2 if i == 0 else 1, 1, bias=False), nn.ReLU(inplace=True),
+                      nn.BatchNorm2d(cout, **norm_cfg)]
+            return nn.Sequential(*L)
+        self.conv1 = stage(nf, nf, 4)
+        self.conv2 = stage(nf, 2 * nf, 6)
+        self.conv3 = stage(2 * nf, 2 * nf, 6)
+        self.upconv1 = nn.Sequential(nn.ConvTranspose2d(nf, 2 * nf, 1, 1, bias=False), nn.ReLU(inplace=True),
+                                     nn.BatchNorm2d(2 * nf, **norm_cfg))
+        self.upconv2 = nn.Sequential(nn.ConvTranspose2d(2 * nf, 2 * nf, 4, 2, 1, bias=False), nn.ReLU(inplace=True),
+                                     nn.BatchNorm2d(2 * nf, **norm_cfg))
+        self.upconv3 = nn.Sequential(nn.ConvTranspose2d(2 * nf, 2 * nf, 4, 4, 1, 2, bias=False), nn.ReLU(inplace=True),
+                                     nn.BatchNorm2d(2 * nf, **norm_cfg))
+        self.precision = "fp32"
+
+    def _build(self, device):
+        def crb(conv, bn):
+            s, t = bn_affine(bn)
+            return TapConv(conv.weight, isinstance(conv, nn.ConvTranspose2d), conv.stride, conv.padding, conv.dilation,
+                           getattr(conv, "output_padding", 0), None, pre_relu=True, scale=s, shift=t)
+        plan = {}
+        for name in ("conv1", "conv2", "conv3"):
+            seq = getattr(self, name)
+            plan[name] = [crb(seq[i], seq[i + 2]) for i in range(0, len(seq), 3)]
+        for name in ("upconv1", "upconv2", "upconv3"):
+            seq = getattr(self, name)
+            plan[name] = crb(seq[0], seq[2])
+        return plan
+
+    def forward_nhwc(self, x):
+        """x: NHWC canvas buffer -> NHWC (B, H/2, W/2, 6*nf) feature buffer."""
+        if self.training:
+            raise LavbError("ConvBackbone: training-mode forward goes through lav_b200.train (autograd path)")
+        plan = self._plan_get(x.device, self._build)
+        dt = _DT[self.precision]
+        xs = []
+        for name in ("conv1", "conv2", "conv3"):
+            for layer in plan[name]:
+                x = layer(x, out_dtype=dt)
+            xs.append(x)
+        n, h, w, _ = xs[0].shape
+        ctot = plan["upconv1"].cout + plan["upconv2"].cout + plan["upconv3"].cout
+        out = torch.empty((n, h, w, ctot), dtype=dt, device=x.device)
+        off = 0
+        for name, xi in zip(("upconv1", "upconv2", "upconv3"), xs):
+            plan[name](xi, out=out, out_coff=off)
+            off += plan[name].cout
+        return out
+
+    def forward(self, x):
+        return self.forward_nhwc(_nhwc(x)).permute(0, 3, 1, 2)
+
+
+class Head(PlanMixin, nn.Module):
+    def __init__(self, num_input, num_output, num_hidden=64, norm_cfg={'eps': 1e-3, 'momentum': 0.01}, output_activation=None):
+        super().__init__()
+        self.net = nn.Sequential(
+            nn.Conv2d(num_input, num_hidden, 3, 1, 1, bias=False),
+            nn.ReLU(inplace=True),
+            nn.BatchNorm2d(num_hidden, **norm_cfg),
+            nn.ConvTranspose2d(num_hidden, num_output, 3, 2, 1, 1),
+        )
+        self.output_activation = output_activation
+        self.precision = "fp32"
+
+    def _is_sigmoid(self):
+        if self.output_activation is None:
+            return False
+        if self.output_activation is torch.sigmoid or self.output_activation is torch.nn.functional.sigmoid:
+            return True
+        raise LavbError("Head: only output_activation in (None, torch.sigmoid) is built (lidar.py:29-32)")
+
+    def _build(self, device):
+        s, t = bn_affine(self.net[2])
+        conv = TapConv(self.net[0].weight, False, 1, 1, pre_relu=True, scale=s, shift=t)
+        up = TapConv(self.net[3].weight, True, 2, 1, 1, 1, bias=self.net[3].bias, sigmoid=self._is_sigmoid())
+        return conv, up
+
+    def forward_nhwc(self, x):
+        if self.training:
+            raise LavbError("Head: training-mode forward goes through lav_b200.train (autograd path)")
+        conv, up = self._plan_get(x.device, self._build)
+        return up(conv(x, out_dtype=_DT[self.precision]), out_dtype=torch.float32)
+
+    def forward(self, x):
+        return self.forward_nhwc(_nhwc(x)).permute(0, 3, 1, 2)
+
+
+class LiDARModel(PlanMixin, nn.Module):
+    def __init__(self, num_input=9, num_features=[32, 32], backbone='swin', min_x=-10, max_x=70, min_y=-40, max_y=40,
+                 pixels_per_meter=4):
+        super().__init__()
+        self.point_pillar_net = PointPillarNet(num_input, num_features, min_x=min_x, max_x=max_x, min_y=min_y, max_y=max_y,
+                                               pixels_per_meter=pixels_per_meter)
+        num_feature = num_features[-1]
+        if backbone == 'cnn':
+            self.backbone = ConvBackbone(num_feature=num_feature)
+        else:
+            raise NotImplementedError
+        self.center_head = Head(6 * num_feature, 2)
+        self.box_head = Head(6 * num_feature, 2)
+        self.ori_head = Head(6 * num_feature, 2)
+        self.seg_head = Head(6 * num_feature, 3, output_activation=torch.sigmoid)
+        self.precision = "fp32"
+
+    def set_precision(self, precision):
+        assert precision in _DT
+        for m in self.modules():
+            if hasattr(m, "precision"):
+                m.precision = precision
+        self.invalidate_plan()
+        return self
+
+    def _heads(self):
+        return (self.center_head, self.box_head, self.ori_head, self.seg_head)
+
+    def _build(self, device):
+        """one 384->256 conv for the four heads (reads the feature map once), then four small ConvT."""
+        ws, ss, ts = [], [], []
+        for h in self._heads():
+            s, t = bn_affine(h.net[2])
+            ws.append(h.net[0].weight)
+            ss.append(s)
+            ts.append(t)
+        conv = TapConv(torch.cat(ws, 0), False, 1, 1, pre_relu=True, scale=torch.cat(ss), shift=torch.cat(ts))
+        ups = [TapConv(h.net[3].weight, True, 2, 1, 1, 1, bias=h.net[3].bias, sigmoid=h._is_sigmoid()) for h in self._heads()]
+        return conv, ups
+
+    def heads_nhwc(self, feats):
+        conv, ups = self._plan_get(feats.device, self._build)
+        hid = conv(feats, out_dtype=_DT[self.precision])
+        nh = self.center_head.net[0].out_channels
+        return [up(hid, in_coff=i * nh, out_dtype=torch.float32) for i, up in enumerate(ups)]
+
+    def forward_nhwc(self, lidars, num_points):
+        canvas = self.point_pillar_net(lidars, num_points).permute(0, 2, 3, 1)   # NHWC view of the canvas
+        feats = self.backbone.forward_nhwc(canvas.contiguous())
+        return (feats, *self.heads_nhwc(feats))
+
+    def forward(self, lidars, num_points):
+        if self.training:
+            from .train import lidar_model_train_forward
+            return lidar_model_train_forward(self, lidars, num_points)
+        return tuple(t.permute(0, 3, 1, 2) for t in self.forward_nhwc(lidars, num_points))

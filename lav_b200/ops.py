@@ -1,0 +1,221 @@
+"""Torch-tensor front ends of the C-ABI kernels (device pointers + current stream in, tensors out).
+
+PyTorch is plumbing here: allocation, streams, views.  Every function launches hand-written
+sm_100a kernels through lav_b200.capi; nothing falls back to torch math.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import BF16, F32, ConvDesc, check, lib
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise capi.LavbError("lav_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def launches():
+    """number of kernel launches issued through this module (bench.py reports it)."""
+    return _COUNT[0]
+
+
+_COUNT = [0]
+
+
+# ----------------------------------------------------------------------------- painting
+def paint(points, sem, cams, mode, copy_cols=0, out=None, out_col0=None):
+    """points (N,>=3) fp32; sem (ncam,C,H,W)-shaped tensor with ANY strides (NCHW or channels-last);
+    cams (ncam,41) float32 numpy (K|lidar_to_world|world_to_cam).  See lavb_paint in include/lav_b200.h."""
+    _need_cuda(points, sem)
+    assert points.dtype == torch.float32 and sem.dtype == torch.float32 and points.dim() == 2
+    assert points.stride(1) == 1
+    ncam, c_in, h, w = sem.shape
+    c_out = c_in if mode == 0 else c_in - 1
+    n = points.shape[0]
+    if out_col0 is None:
+        out_col0 = copy_cols
+    if out is None:
+        out = torch.empty((n, out_col0 + c_out), dtype=torch.float32, device=points.device)
+    assert out.stride(1) == 1
+    cams = np.ascontiguousarray(cams, dtype=np.float32)
+    assert cams.shape == (ncam, 41)
+    s = sem.stride()
+    check(lib().lavb_paint(_ptr(points), n, points.stride(0), _ptr(sem), ncam, c_in, h, w, s[0], s[1], s[2], s[3],
+                           cams.ctypes.data_as(C.c_void_p), mode, _ptr(out), out.stride(0), out_col0, copy_cols, _stream()),
+          "lavb_paint")
+    _COUNT[0] += 1
+    return out
+
+
+def stack_sweep(src, R, dx, dy, time_idx, n_time, dst, roof_filter=False):
+    """dst (n, src_cols+n_time) <- [src[:, :3] @ R + (dx,dy,0) | src[:,3:] | one_hot(time_idx)]"""
+    _need_cuda(src, dst)
+    assert src.is_contiguous() and dst.is_contiguous() and dst.shape == (src.shape[0], src.shape[1] + n_time)
+    R = np.ascontiguousarray(R, dtype=np.float32)
+    check(lib().lavb_stack_sweep(_ptr(src), src.shape[0], src.shape[1], R.ctypes.data_as(C.c_void_p), float(dx), float(dy),
+                                 time_idx, n_time, int(roof_filter), _ptr(dst), _stream()), "lavb_stack_sweep")
+    _COUNT[0] += 1
+    return dst
+
+
+# ----------------------------------------------------------------------------- pillars
+_WS = {}
+
+
+def _workspace(device, nbytes):
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
+def _clouds(starts, counts):
+    b = len(counts)
+    st = (C.c_longlong * b)(*[int(s) for s in starts])
+    ct = (C.c_int * b)(*[int(c) for c in counts])
+    return b, st, ct
+
+
+def pillar_forward(pts, starts, counts, grid, w1, s1, t1, w2, s2, t2):
+    """pts: 2-D fp32 row buffer (rows of >= D floats); cloud b = rows [starts[b], starts[b]+counts[b]).
+    Returns the NHWC canvas (B, ny, nx, H2) fp32."""
+    _need_cuda(pts, w1, w2)
+    assert pts.dtype == torch.float32 and pts.dim() == 2 and pts.stride(1) == 1
+    min_x, max_x, min_y, max_y, ppm, nx, ny = grid
+    d = w1.shape[1] - 5
+    b, st, ct = _clouds(starts, counts)
+    canvas = torch.empty((b, ny, nx, w2.shape[0]), dtype=torch.float32, device=pts.device)
+    ws = _workspace(pts.device, lib().lavb_pillar_workspace_bytes(b, nx, ny))
+    check(lib().lavb_pillar_forward(_ptr(pts), pts.stride(0), d, st, ct, b, min_x, max_x, min_y, max_y, ppm, nx, ny,
+                                    _ptr(w1), _ptr(s1), _ptr(t1), w1.shape[0], _ptr(w2), _ptr(s2), _ptr(t2), w2.shape[0],
+                                    _ptr(canvas), F32, _ptr(ws), _stream()), "lavb_pillar_forward")
+    _COUNT[0] += 4
+    return canvas
+
+
+def pillar_decorate(pts, starts, counts, grid, d):
+    """training stage 0: returns (feat (M,d+5) fp32, cell (M,) int32)."""
+    _need_cuda(pts)
+    min_x, max_x, min_y, max_y, ppm, nx, ny = grid
+    b, st, ct = _clouds(starts, counts)
+    ws = _workspace(pts.device, lib().lavb_pillar_workspace_bytes(b, nx, ny))
+    total = int(sum(int(c) for c in counts))
+    feat = torch.empty((total, d + 5), dtype=torch.float32, device=pts.device)
+    cell = torch.empty((total,), dtype=torch.int32, device=pts.device)
+    m = C.c_int(0)
+    check(lib().lavb_pillar_decorate(_ptr(pts), pts.stride(0), d, st, ct, b, min_x, max_x, min_y, max_y, ppm, nx, ny,
+                                     _ptr(feat), _ptr(cell), C.byref(m), _ptr(ws), _stream()), "lavb_pillar_decorate")
+    _COUNT[0] += 4
+    return feat[:m.value], cell[:m.value]
+
+
+def pillar_scatter_max(h, cell, n_cells, want_argmax=True):
+    _need_cuda(h, cell)
+    h = h.contiguous()
+    m, c = h.shape
+    canvas = torch.empty((n_cells, c), dtype=torch.float32, device=h.device)
+    arg = torch.empty((n_cells, c), dtype=torch.int32, device=h.device) if want_argmax else None
+    check(lib().lavb_pillar_scatter_max(_ptr(h), _ptr(cell), m, c, n_cells, _ptr(canvas), _ptr(arg), _stream()),
+          "lavb_pillar_scatter_max")
+    _COUNT[0] += 2
+    return canvas, arg
+
+
+def pillar_scatter_max_bwd(gcanvas, arg, cell, m):
+    gcanvas = gcanvas.contiguous()
+    c = gcanvas.shape[-1]
+    gh = torch.empty((m, c), dtype=torch.float32, device=gcanvas.device)
+    check(lib().lavb_pillar_scatter_max_bwd(_ptr(gcanvas), _ptr(arg), _ptr(cell), m, c, _ptr(gh), _stream()),
+          "lavb_pillar_scatter_max_bwd")
+    _COUNT[0] += 1
+    return gh
+
+
+# ----------------------------------------------------------------------------- convolution
+def conv_taps(x, cin, in_coff, out, cout, out_coff, hog, wog, in_s, out_s, out_o, taps, w, bias=None, scale=None, shift=None,
+              res=None, res_coff=0, pre_relu=False, post_relu=False, sigmoid=False):
+    """x, out, res: contiguous NHWC buffers (N,H,W,Ctot).  taps: list of (dy,dx); w: (ntaps,cin,cout_pad) fp32."""
+    _need_cuda(x, out, w)
+    assert x.is_contiguous() and out.is_contiguous() and w.is_contiguous() and w.dtype == torch.float32
+    d = ConvDesc()
+    d.inp, d.in_dtype = x.data_ptr(), _DT[x.dtype]
+    d.n, d.hin, d.win, d.in_cstride = x.shape
+    d.cin, d.in_coff = cin, in_coff
+    d.out, d.out_dtype = out.data_ptr(), _DT[out.dtype]
+    assert out.shape[0] == x.shape[0]
+    _, d.hout, d.wout, d.out_cstride = out.shape
+    d.cout, d.out_coff = cout, out_coff
+    d.hog, d.wog = hog, wog
+    d.in_sy, d.in_sx = in_s
+    d.out_sy, d.out_sx = out_s
+    d.out_oy, d.out_ox = out_o
+    d.ntaps = len(taps)
+    assert w.shape[0] == len(taps) and w.shape[1] == cin and w.shape[2] == (cout + 15) // 16 * 16
+    for i, (dy, dx) in enumerate(taps):
+        d.dy[i], d.dx[i] = dy, dx
+    d.w = w.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.scale = scale.data_ptr() if scale is not None else None
+    d.shift = shift.data_ptr() if shift is not None else None
+    if res is not None:
+        assert res.is_contiguous() and res.shape[:3] == out.shape[:3]
+        d.res, d.res_dtype, d.res_cstride, d.res_coff = res.data_ptr(), _DT[res.dtype], res.shape[3], res_coff
+    d.pre_relu, d.post_relu, d.sigmoid = int(pre_relu), int(post_relu), int(sigmoid)
+    check(lib().lavb_conv_taps(C.byref(d), _stream()), "lavb_conv_taps")
+    _COUNT[0] += 1
+    return out
+
+
+def pool2_affine_relu(x, c, in_coff, scale, shift, out, out_coff):
+    _need_cuda(x, out)
+    n, h, w, cs = x.shape
+    check(lib().lavb_pool2_affine_relu(_ptr(x), _DT[x.dtype], n, h, w, c, cs, in_coff, _ptr(scale), _ptr(shift), _ptr(out),
+                                       out.shape[3], out_coff, _stream()), "lavb_pool2_affine_relu")
+    _COUNT[0] += 1
+    return out
+
+
+def rgb_normalize(rgb, out_dtype=torch.float32):
+    """uint8 (N,H,W,3) or float (N,3,H,W) in 0..255 -> NHWC4 normalised ((x/255-.5)*2, 4th channel 0)."""
+    _need_cuda(rgb)
+    if rgb.dtype == torch.uint8:
+        assert rgb.dim() == 4 and rgb.shape[3] == 3
+        n, h, w, _ = rgb.shape
+        u8 = 1
+        rgb = rgb.contiguous()
+    else:
+        assert rgb.dim() == 4 and rgb.shape[1] == 3
+        n, _, h, w = rgb.shape
+        u8 = 0
+        rgb = rgb.float().contiguous()
+    out = torch.empty((n, h, w, 4), dtype=out_dtype, device=rgb.device)
+    check(lib().lavb_rgb_normalize(_ptr(rgb), u8, n, h, w, _ptr(out), _DT[out_dtype], _stream()), "lavb_rgb_normalize")
+    _COUNT[0] += 1
+    return out
+
+
+def convert(src, dtype):
+    _need_cuda(src)
+    src = src.contiguous()
+    if src.dtype == dtype:
+        return src
+    dst = torch.empty(src.shape, dtype=dtype, device=src.device)
+    check(lib().lavb_convert(_ptr(src), _DT[src.dtype], _ptr(dst), _DT[dtype], src.numel(), _stream()), "lavb_convert")
+    _COUNT[0] += 1
+    return dst

@@ -1,0 +1,157 @@
+"""GPU parity: painting, sweep stacking and the pillar encoder against the oracle, through the C-ABI."""
+import numpy as np
+import pytest
+import torch
+
+from lav_b200 import synth
+from oracle import lav_ref as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _flip_ok(lidar, convs, bad_rows, tol=2e-3):
+    """every mismatching point must sit within `tol` px of an integer boundary in some camera (fp32 rounding
+    of the projection differs between BLAS orderings); anything else is a bug."""
+    for i in bad_rows.tolist():
+        near = False
+        for K, l2w, w2c in convs:
+            p = np.r_[lidar[i, :3].double().numpy(), 1.0]
+            cam = w2c @ (l2w @ p)
+            cam = np.array([cam[1], -cam[2], cam[0]])
+            q = K @ cam
+            for val in (q[0] / (1e-5 + q[2]), q[1] / (1e-5 + q[2]), q[2]):
+                if abs(val - round(val)) < tol * max(1.0, abs(val) * 1e-3):
+                    near = True
+        if not near:
+            return False
+    return True
+
+
+def test_paint_matches_oracle_and_reference(cuda, golden_dir):
+    from lav_b200 import point_painting as PP
+    lidar, sem5, gold = util.paint_inputs()
+    convs_o = O.default_converters()
+    convs = PP.make_converters()
+    sem4 = O.suppress_background(sem5)
+    got = PP.point_painting(lidar.to(cuda), sem4.to(cuda), convs).cpu()
+    want = torch.from_numpy(gold["painted"])              # REFERENCE output (fp32 torch twin)
+    bad = (got != want).any(dim=1).nonzero()[:, 0]
+    assert len(bad) <= max(2, len(lidar) // 5000), f"{len(bad)} painted rows differ"
+    assert _flip_ok(lidar, convs_o, bad)
+    # fused background suppression (mode 1) and fused softmax (mode 2)
+    fused = PP.forward_paint(lidar.to(cuda), sem5.to(cuda), convs).cpu()
+    wantf = torch.from_numpy(gold["fused"])
+    badf = (fused != wantf).any(dim=1).nonzero()[:, 0]
+    assert set(badf.tolist()) <= set(bad.tolist())
+    logits = torch.randn(3, 5, 288, 256, generator=synth._gen(5, "logits"))
+    f2 = PP.forward_paint(lidar.to(cuda), logits.to(cuda), convs, logits=True).cpu()
+    w2 = O.forward_paint(lidar, torch.softmax(logits, 1), convs_o)
+    ok = torch.ones(len(lidar), dtype=torch.bool)
+    ok[bad] = False
+    assert torch.allclose(f2[ok], w2[ok], rtol=0, atol=2e-6)
+    # channels-last semantic maps (what the CUDA ERFNet emits) give the same result
+    sem_cl = sem4.to(cuda).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    got_cl = PP.point_painting(lidar.to(cuda), sem_cl, convs).cpu()
+    assert torch.equal(got_cl, got)
+
+
+def test_paint_edge_cases(cuda):
+    from lav_b200 import point_painting as PP
+    convs = PP.make_converters()
+    sem = synth.sem_probs(tag="e").to(cuda)[:, 1:]
+    empty = PP.point_painting(torch.zeros((0, 4), device=cuda), sem, convs)
+    assert empty.shape == (0, 4)
+    weird = torch.tensor([[float("nan"), 0, 0, 0], [float("inf"), 0, 0, 0], [1e30, 1e30, 1e30, 0], [-1e30, 0, 0, 0],
+                          [1.5, 0, 0, 0]], device=cuda)
+    out = PP.point_painting(weird, sem, convs).cpu()
+    want = O.point_painting_f32(weird.cpu(), sem.cpu(), O.default_converters())
+    assert torch.equal(out, want)
+
+
+def test_stack_sweep_matches_oracle(cuda):
+    from lav_b200 import ops
+    import math
+    sweeps = [synth.painted_sweep(3000, tag=f"s{i}") for i in range(3)]
+    loc, ori = synth.ego_motion(3, tag="stk")
+    want = O.stack_lidar(sweeps, loc, ori)
+    dst = torch.empty((9000, 11), device=cuda)
+    for i, s in enumerate(sweeps):
+        d = ori[i] - ori[0]
+        R = np.array([[math.cos(d), math.sin(d), 0], [-math.sin(d), math.cos(d), 0], [0, 0, 1]])
+        c0, s0 = math.cos(ori[0]), math.sin(ori[0])
+        dl = (loc[i] - loc[0]) @ np.array([[c0, -s0], [s0, c0]])
+        ops.stack_sweep(s.to(cuda), R, dl[0], dl[1], i, 3, dst[i * 3000:(i + 1) * 3000])
+    assert torch.allclose(dst.cpu(), want, rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("form", ["list", "padded", "single"])
+def test_pillar_canvas_matches_oracle(cuda, form):
+    m, sd = util.lidar_model(cuda)
+    clouds = util.pillar_clouds()
+    if form == "single":
+        clouds = clouds[:1]
+    npts = [len(c) for c in clouds]
+    with torch.no_grad():
+        want = O.pillar_net(sd, clouds, npts, **util.GRID)
+        if form == "padded":
+            P = max(npts) + 17
+            pad = torch.full((len(clouds), P, 11), 3.0)        # padding rows are in-window on purpose
+            for b, c in enumerate(clouds):
+                pad[b, :len(c)] = c
+            got = m.point_pillar_net(pad.to(cuda), torch.tensor(npts))
+        else:
+            got = m.point_pillar_net([c.to(cuda) for c in clouds], npts)
+    assert got.shape == want.shape
+    got = got.cpu()
+    assert torch.equal((got != 0).any(1), (want != 0).any(1)), "occupied cells differ"
+    assert util.rel_err(got, want) < 1e-5
+
+
+def test_pillar_matches_reference_golden(cuda, golden_dir):
+    import os
+    gold = np.load(os.path.join(golden_dir, "lidar_model.npz"))
+    m, _ = util.lidar_model(cuda)
+    clouds = util.pillar_clouds()
+    with torch.no_grad():
+        got = m.point_pillar_net([c.to(cuda) for c in clouds], [len(c) for c in clouds]).cpu()
+    idx = torch.from_numpy(gold["pillar_idx"]).long()
+    vals = got.permute(0, 2, 3, 1)[idx[:, 0], idx[:, 1], idx[:, 2]]
+    np.testing.assert_allclose(vals.numpy(), gold["pillar_val"], rtol=1e-4, atol=1e-4)
+    assert int((got != 0).any(1).sum()) == len(idx)
+
+
+@pytest.mark.parametrize("mode", ["uniform", "adversarial", "empty", "all_outside"])
+def test_pillar_edge_distributions(cuda, mode):
+    m, sd = util.lidar_model(cuda)
+    if mode == "empty":
+        pts = torch.zeros((0, 11))
+    elif mode == "all_outside":
+        pts = synth.stacked_lidar(500, tag="o")
+        pts[:, 0] += 500
+    else:
+        xyz = synth.lidar_sweep(6000, tag=mode, mode=mode)
+        pts = torch.cat([xyz, torch.rand(6000, 7, generator=synth._gen(3, mode))], 1)
+    with torch.no_grad():
+        got = m.point_pillar_net([pts.to(cuda)], [len(pts)]).cpu()
+        if len(pts) and mode != "all_outside":
+            want = O.pillar_net(sd, [pts], [len(pts)], **util.GRID)
+            assert util.rel_err(got, want) < 1e-5
+        else:
+            assert float(got.abs().max()) == 0.0
+
+
+def test_pillar_full_size_properties(cuda):
+    """BASELINE config 2 size (B=32 x 40k points): properties that need no oracle run."""
+    m, _ = util.lidar_model(cuda)
+    base = torch.cat([synth.painted_sweep(40000, tag="full"), torch.tensor([[1., 0, 0]]).expand(40000, 3)], 1)
+    B = 32
+    batch = base.to(cuda)[None].repeat(B, 1, 1)
+    with torch.no_grad():
+        can = m.point_pillar_net(batch, [40000] * B)
+        assert can.shape == (B, 64, 320, 320)
+        assert torch.equal(can[0], can[B - 1]) or util.rel_err(can[0], can[B - 1]) < 1e-6   # batch items independent
+        perm = torch.randperm(40000, generator=synth._gen(1, "perm")).to(cuda)
+        can_p = m.point_pillar_net(batch[:1, perm], [40000])
+        assert util.rel_err(can_p[0], can[0]) < 1e-5                                        # point order irrelevant
+        assert float(can.min()) >= 0.0
