@@ -123,15 +123,14 @@ int lavb_rgb_normalize(const void* d_rgb, int src_is_u8_nhwc, int n, int h, int 
 /* dtype / layout helpers */
 int lavb_convert(const void* d_src, int src_dtype, void* d_dst, int dst_dtype, long long count, void* stream);
 
-/* ---------------------------------------------------------------- tcgen05 implicit-GEMM 3x3 convolution
- * replaces: the stride-1 3x3 Conv2d -> ReLU -> BatchNorm2d layers of ConvBackbone (lidar.py:60-112) and the fused
- *           4-head 384->256 conv (lidar.py:152-154) on the bf16 path.
- * in: NHWC bf16 [n][h][w][cin] (cin multiple of 64), w: bf16 [9][cout][cin] (tap-major, K contiguous),
- * out: NHWC bf16 [n][h][w][out_cstride] slice; epilogue relu(acc)*scale+shift.  h % 8 == 0, w % 16 == 0.
- * TMA descriptors are built inside the call (cuTensorMapEncodeTiled via the driver entry point). */
-int lavb_conv3x3_umma(const void* d_in, int n, int h, int w, int cin,
-                      const void* d_w, int cout, const float* d_scale, const float* d_shift, int relu_first,
-                      void* d_out, int out_cstride, int out_coff, void* stream);
+/* ---------------------------------------------------------------- tcgen05 implicit-GEMM tap-list convolution
+ * replaces (bf16 path): the Conv2d -> ReLU -> BatchNorm2d layers of ConvBackbone (lidar.py:57-131), the fused 4-head
+ *           384->256 conv (lidar.py:152-154) and the 64/128-channel factorised convs of ERFNet (erfnet.py:31-61).
+ * Same descriptor and epilogue semantics as lavb_conv_taps, with these differences: input is bf16 NHWC, cin % 64 == 0,
+ * cout % 32 == 0 and <= 256, channel offsets/strides multiples of 8; d->w points to BF16 weights laid out
+ * [ntaps][cout][cin] (K contiguous).  Tiles are 8 x 16 output-grid pixels; operands are fetched by TMA
+ * (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint), accumulators live in TMEM. */
+int lavb_conv_umma(const lavb_conv_desc* h_desc, void* stream);
 
 #ifdef __cplusplus
 }

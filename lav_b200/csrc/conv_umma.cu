@@ -1,7 +1,337 @@
-// tcgen05 implicit-GEMM 3x3 convolution — placeholder until the kernel lands (returns an error, never computes).
+// tcgen05 / TMEM / TMA implicit-GEMM tap-list convolution (bf16 in, fp32 accumulate in TMEM).
+//
+// GEMM view of one CTA tile: M = 128 output-grid pixels (an 8 x 16 spatial patch), N = cout (<= 256),
+// K = ntaps * cin walked in blocks of 64 channels.  No im2col buffer exists anywhere: for tap (dy,dx) the
+// A operand of a K-block is ONE 4-D TMA box {64 ch, 16 px, 8 rows, 1 image} of the NHWC activation tensor whose
+// start coordinate is shifted by the tap offset (out-of-bounds rows/columns are zero-filled by TMA, which IS the
+// conv padding); with SWIZZLE_128B the box lands in shared memory exactly in the K-major layout tcgen05.mma reads
+// (128 rows x 128 B).  Strided convs use the tensor map's element strides; a transposed conv is issued per output
+// phase with its own tap list (same host packing as conv_taps.cu).
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0   : TMA producer (one lane)      — smem ring of `stages` {A 16 KB, B cout*128 B}
+//   warp 1   : TMEM allocator + MMA issuer  — 4 x tcgen05.mma (M128,N=cout,K16) per K-block, commit -> empty barrier
+//   warps 2-5: epilogue                     — tcgen05.ld 32x32b.x32, bias/ReLU/BN-affine/residual, 16 B global stores
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include "common.cuh"
-extern "C" int lavb_conv3x3_umma(const void*, int, int, int, int, const void*, int, const float*, const float*, int, void*, int,
-                                 int, void*) {
-  lavb::set_error("conv3x3_umma: not built yet");
-  return 4;
+
+namespace lavb {
+
+constexpr int kTileH = 8, kTileW = 16, kBlockM = 128, kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kMaxTaps = 16;
+
+struct UmmaArgs {
+  int n, hog, wog, tiles_x, tiles_y, num_tiles;
+  int hout, wout, cin, cout, kchunks, ntaps, stages, tmem_cols;
+  int in_sy, in_sx, out_sy, out_sx, out_oy, out_ox;
+  int out_cstride, out_coff, out_is_f32, res_cstride, res_coff;
+  int pre_relu, post_relu, sigmoid;
+  int dy[kMaxTaps], dx[kMaxTaps];
+  void* out; const __nv_bfloat16* res;
+  const float* bias; const float* scale; const float* shift;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) = 0 | SBO>>4 [32,46) = 1024>>4 | version=1 [46,48) | layout=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  const uint32_t lo = (saddr & 0x3FFFFu) >> 4;
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                           const __grid_constant__ CUtensorMap tmap_b,
+                                                           const __grid_constant__ UmmaArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B operands need 1024 B alignment
+  const int b_bytes = p.cout * kBlockK * 2;
+  const int stage_bytes = kABytes + b_bytes;
+  const uint32_t ctrl = base + p.stages * stage_bytes;
+  const uint32_t full_bar = ctrl, empty_bar = ctrl + 8 * kMaxStages, tfull_bar = ctrl + 16 * kMaxStages,
+                 tempty_bar = tfull_bar + 16, tmem_slot = tempty_bar + 16;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+  float* ep_bias = reinterpret_cast<float*>(gen + (tmem_slot - base) + 16);
+  float* ep_scale = ep_bias + 256;
+  float* ep_shift = ep_scale + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int c = threadIdx.x; c < p.cout; c += blockDim.x) {
+    ep_bias[c] = p.bias ? __ldg(p.bias + c) : 0.f;
+    ep_scale[c] = p.scale ? __ldg(p.scale + c) : 1.f;
+    ep_shift[c] = p.shift ? __ldg(p.shift + c) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_p;
+  const int nkb = p.ntaps * p.kchunks;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+        const int y0 = (r / p.tiles_x) * kTileH * p.in_sy, x0 = (r % p.tiles_x) * kTileW * p.in_sx;
+        for (int t = 0; t < p.ntaps; ++t) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+            const uint32_t sa = base + stage * stage_bytes;
+            mbar_expect_tx(full_bar + 8 * stage, stage_bytes);
+            tma_load_4d(sa, &tmap_a, full_bar + 8 * stage, kc * kBlockK, x0 + p.dx[t], y0 + p.dy[t], img);
+            tma_load_2d(sa + kABytes, &tmap_b, full_bar + 8 * stage, kc * kBlockK, t * p.cout);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both, N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.cout >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.cout);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * stage_bytes;
+          const uint64_t a_desc = make_sw128_desc(sa), b_desc = make_sw128_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)   // +32 B per K16 step inside the 128 B swizzle atom
+            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar + 8 * stage);      // frees the smem slot once these MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar + 8 * acc);          // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;                        // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int py = row / kTileW, px = row % kTileW;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+      const int gy = (r / p.tiles_x) * kTileH + py, gx = (r % p.tiles_x) * kTileW + px;
+      const int oy = gy * p.out_sy + p.out_oy, ox = gx * p.out_sx + p.out_ox;
+      const bool valid = gy < p.hog && gx < p.wog && oy < p.hout && ox < p.wout;
+      const long long pix = ((long long)img * p.hout + oy) * p.wout + ox;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      for (int c0 = 0; c0 < p.cout; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.cout + c0), v);
+        if (valid) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) + ep_bias[c0 + j];
+            if (p.pre_relu) x = fmaxf(x, 0.f);
+            f[j] = fmaf(x, ep_scale[c0 + j], ep_shift[c0 + j]);
+          }
+          if (p.res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_cstride + p.res_coff + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 rr = __ldg(rp + j);
+              const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                f[j * 8 + e * 2] += t2.x; f[j * 8 + e * 2 + 1] += t2.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (p.post_relu) f[j] = fmaxf(f[j], 0.f);
+            if (p.sigmoid) f[j] = 1.f / (1.f + expf(-f[j]));
+          }
+          if (p.out_is_f32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_cstride + p.out_coff + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cstride + p.out_coff + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
+                w[e] = *reinterpret_cast<const uint32_t*>(&b2);
+              }
+              op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+}  // namespace lavb
+
+using namespace lavb;
+
+extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
+  LAVB_CHECK_ARG(d != nullptr, "conv_umma: null descriptor");
+  LAVB_CHECK_ARG(d->in_dtype == LAVB_BF16, "conv_umma: input must be bf16");
+  LAVB_CHECK_ARG(d->out_dtype == LAVB_BF16 || d->out_dtype == LAVB_F32, "conv_umma: bad output dtype");
+  LAVB_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= kMaxTaps, "conv_umma: ntaps must be 1..16");
+  LAVB_CHECK_ARG(d->cin % 64 == 0 && d->cin > 0, "conv_umma: cin must be a multiple of 64 (got %d)", d->cin);
+  LAVB_CHECK_ARG(d->cout % 32 == 0 && d->cout >= 32 && d->cout <= 256, "conv_umma: cout must be 32..256, multiple of 32 (got %d)", d->cout);
+  LAVB_CHECK_ARG(d->in_cstride % 8 == 0 && d->in_coff % 8 == 0 && d->in_coff + d->cin <= d->in_cstride, "conv_umma: input slice misaligned");
+  LAVB_CHECK_ARG(d->out_cstride % 8 == 0 && d->out_coff % 8 == 0 && d->out_coff + d->cout <= d->out_cstride, "conv_umma: output slice misaligned");
+  LAVB_CHECK_ARG(d->res == nullptr || (d->res_dtype == LAVB_BF16 && d->res_cstride % 8 == 0 && d->res_coff % 8 == 0), "conv_umma: residual must be bf16, 16 B aligned");
+  LAVB_CHECK_ARG((d->scale == nullptr) == (d->shift == nullptr), "conv_umma: scale and shift come together");
+  LAVB_CHECK_ARG(d->in_sy >= 1 && d->in_sy <= 8 && d->in_sx >= 1 && d->in_sx <= 8, "conv_umma: bad input stride");
+  auto encode = get_encode();
+  LAVB_CHECK_ARG(encode != nullptr, "conv_umma: cuTensorMapEncodeTiled not available from the driver");
+
+  CUtensorMap tmap_a, tmap_b;
+  {
+    const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(d->in) + d->in_coff;
+    cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->win, (cuuint64_t)d->hin, (cuuint64_t)d->n};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_cstride * 2, (cuuint64_t)d->win * d->in_cstride * 2,
+                             (cuuint64_t)d->hin * d->win * d->in_cstride * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(kTileW * d->in_sx), (cuuint32_t)(kTileH * d->in_sy), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->in_sx, (cuuint32_t)d->in_sy, 1};
+    CUresult r = encode(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LAVB_CHECK_ARG(r == CUDA_SUCCESS, "conv_umma: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->cin, (cuuint64_t)d->ntaps * d->cout};
+    cuuint64_t strides[1] = {(cuuint64_t)d->cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)d->cout};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<float*>(d->w), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LAVB_CHECK_ARG(r == CUDA_SUCCESS, "conv_umma: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  UmmaArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = d->n; a.hog = d->hog; a.wog = d->wog;
+  a.tiles_x = ceil_div(d->wog, kTileW); a.tiles_y = ceil_div(d->hog, kTileH);
+  a.num_tiles = a.n * a.tiles_x * a.tiles_y;
+  a.hout = d->hout; a.wout = d->wout; a.cin = d->cin; a.cout = d->cout; a.kchunks = d->cin / kBlockK; a.ntaps = d->ntaps;
+  const int stage_bytes = kABytes + d->cout * kBlockK * 2;
+  a.stages = min(kMaxStages, (196 * 1024) / stage_bytes);
+  int cols = 32;
+  while (cols < 2 * d->cout) cols <<= 1;
+  a.tmem_cols = cols;
+  a.in_sy = d->in_sy; a.in_sx = d->in_sx; a.out_sy = d->out_sy; a.out_sx = d->out_sx; a.out_oy = d->out_oy; a.out_ox = d->out_ox;
+  a.out_cstride = d->out_cstride; a.out_coff = d->out_coff; a.out_is_f32 = d->out_dtype == LAVB_F32;
+  a.res_cstride = d->res_cstride; a.res_coff = d->res_coff;
+  a.pre_relu = d->pre_relu; a.post_relu = d->post_relu; a.sigmoid = d->sigmoid;
+  for (int t = 0; t < d->ntaps; ++t) { a.dy[t] = d->dy[t]; a.dx[t] = d->dx[t]; }
+  a.out = d->out; a.res = reinterpret_cast<const __nv_bfloat16*>(d->res);
+  a.bias = d->bias; a.scale = d->scale; a.shift = d->shift;
+  if (a.num_tiles == 0) return 0;
+  const size_t smem = (size_t)a.stages * stage_bytes + 1024 /*align*/ + 16 * kMaxStages + 64 + 3 * 256 * sizeof(float);
+  LAVB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = min(a.num_tiles, kNumSMs);
+  conv_umma_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmap_a, tmap_b, a);
+  LAVB_LAUNCH_OK();
+  return 0;
 }

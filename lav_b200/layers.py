@@ -9,6 +9,8 @@ import torch
 
 from . import ops
 
+USE_UMMA = True   # tests flip this to compare the tcgen05 path with the CUDA-core path
+
 
 def bn_affine(bn, eps=None):
     """eval-mode BatchNorm as y*scale+shift (fp64 math, fp32 result)."""
@@ -73,6 +75,11 @@ class TapConv:
                                             out_o=(oy, ox)))
         for ph in self.phases:
             assert len(ph["taps"]) <= 16, "tap list longer than the kernel's table"
+        # tcgen05 path (bf16 activations): weights [ntaps][cout][cin] bf16, K contiguous
+        self.umma_ok = USE_UMMA and self.cin_k % 64 == 0 and self.cout % 32 == 0 and self.cout <= 256
+        if self.umma_ok:
+            for ph in self.phases:
+                ph["w_umma"] = ph["w"][:, :, :self.cout].permute(0, 2, 1).contiguous().to(torch.bfloat16)
 
     def _block(self, w_ci_co):
         if self.cin_k == self.cin:
@@ -98,9 +105,11 @@ class TapConv:
             osy, osx = ph["out_s"]
             ooy, oox = ph["out_o"]
             hog, wog = (hout - ooy + osy - 1) // osy, (wout - oox + osx - 1) // osx
+            umma = (self.umma_ok and x.dtype == torch.bfloat16 and (res is None or res.dtype == torch.bfloat16)
+                    and ph["in_s"] == (1, 1))
             ops.conv_taps(x, self.cin_k, in_coff, out, self.cout, out_coff, hog, wog, ph["in_s"], ph["out_s"], ph["out_o"],
-                          ph["taps"], ph["w"], self.bias, self.scale, self.shift, res, res_coff, self.pre_relu, self.post_relu,
-                          self.sigmoid)
+                          ph["taps"], ph["w_umma"] if umma else ph["w"], self.bias, self.scale, self.shift, res, res_coff,
+                          self.pre_relu, self.post_relu, self.sigmoid, umma=umma)
         return out
 
 

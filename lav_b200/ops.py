@@ -149,10 +149,12 @@ def pillar_scatter_max_bwd(gcanvas, arg, cell, m):
 
 # ----------------------------------------------------------------------------- convolution
 def conv_taps(x, cin, in_coff, out, cout, out_coff, hog, wog, in_s, out_s, out_o, taps, w, bias=None, scale=None, shift=None,
-              res=None, res_coff=0, pre_relu=False, post_relu=False, sigmoid=False):
-    """x, out, res: contiguous NHWC buffers (N,H,W,Ctot).  taps: list of (dy,dx); w: (ntaps,cin,cout_pad) fp32."""
+              res=None, res_coff=0, pre_relu=False, post_relu=False, sigmoid=False, umma=False):
+    """x, out, res: contiguous NHWC buffers (N,H,W,Ctot).  taps: list of (dy,dx).
+    umma=False: CUDA-core kernel, w (ntaps,cin,cout_pad16) fp32.
+    umma=True : tcgen05 kernel, x bf16, w (ntaps,cout,cin) bf16."""
     _need_cuda(x, out, w)
-    assert x.is_contiguous() and out.is_contiguous() and w.is_contiguous() and w.dtype == torch.float32
+    assert x.is_contiguous() and out.is_contiguous() and w.is_contiguous()
     d = ConvDesc()
     d.inp, d.in_dtype = x.data_ptr(), _DT[x.dtype]
     d.n, d.hin, d.win, d.in_cstride = x.shape
@@ -166,7 +168,10 @@ def conv_taps(x, cin, in_coff, out, cout, out_coff, hog, wog, in_s, out_s, out_o
     d.out_sy, d.out_sx = out_s
     d.out_oy, d.out_ox = out_o
     d.ntaps = len(taps)
-    assert w.shape[0] == len(taps) and w.shape[1] == cin and w.shape[2] == (cout + 15) // 16 * 16
+    if umma:
+        assert w.dtype == torch.bfloat16 and tuple(w.shape) == (len(taps), cout, cin) and x.dtype == torch.bfloat16
+    else:
+        assert w.dtype == torch.float32 and tuple(w.shape) == (len(taps), cin, (cout + 15) // 16 * 16)
     for i, (dy, dx) in enumerate(taps):
         d.dy[i], d.dx[i] = dy, dx
     d.w = w.data_ptr()
@@ -177,7 +182,10 @@ def conv_taps(x, cin, in_coff, out, cout, out_coff, hog, wog, in_s, out_s, out_o
         assert res.is_contiguous() and res.shape[:3] == out.shape[:3]
         d.res, d.res_dtype, d.res_cstride, d.res_coff = res.data_ptr(), _DT[res.dtype], res.shape[3], res_coff
     d.pre_relu, d.post_relu, d.sigmoid = int(pre_relu), int(post_relu), int(sigmoid)
-    check(lib().lavb_conv_taps(C.byref(d), _stream()), "lavb_conv_taps")
+    if umma:
+        check(lib().lavb_conv_umma(C.byref(d), _stream()), "lavb_conv_umma")
+    else:
+        check(lib().lavb_conv_taps(C.byref(d), _stream()), "lavb_conv_taps")
     _COUNT[0] += 1
     return out
 
