@@ -120,6 +120,14 @@ int lavb_pool2_affine_relu(const void* d_in, int dtype, int n, int hin, int win,
 int lavb_rgb_normalize(const void* d_rgb, int src_is_u8_nhwc, int n, int h, int w, void* d_out, int out_dtype,
                        void* stream);
 
+/* ---------------------------------------------------------------- rotated bilinear crop
+ * replaces: UniPlanner.crop_feature (team_code_v2/models/uniplanner.py:303-340; model_inference.py:204-238) =
+ *           F.affine_grid(theta, align_corners=True) + F.grid_sample(bilinear, zeros padding, align_corners=True).
+ * d_feat NHWC [b][h][w][c]; crop k samples frame d_frame_idx[k] with the 2x3 affine d_theta[k]; out NHWC
+ * [k][crop][crop][c] in the feature dtype. */
+int lavb_crop_bilinear(const void* d_feat, int dtype, int b, int h, int w, int c, const int* d_frame_idx,
+                       const float* d_theta, int k, int crop, void* d_out, void* stream);
+
 /* dtype / layout helpers */
 int lavb_convert(const void* d_src, int src_dtype, void* d_dst, int dst_dtype, long long count, void* stream);
 

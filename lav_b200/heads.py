@@ -1,0 +1,302 @@
+"""PyTorch heads of the LAV frame path (north_star: "autograd on the heads" stays PyTorch):
+ResNet-18 embedder, UniPlanner (+ its frozen BEVPlanner teacher as a weight container), the
+brake predictor.  Written fresh against the reference's behaviour with identical ``state_dict``
+keys (tests/golden/keys_uniplanner.json, keys_brake.json):
+
+  resnet18            lav/models/resnet.py:144-283 (num_channels stem, returns the layer4 map)
+  UniPlanner          team_code_v2/models/uniplanner.py (infer path) — crop -> embed -> cast/plan GRUs
+  BEVPlanner          team_code_v2/models/bev_planner.py (parameters only; teacher is used in training)
+  RGBBrakePredictionModel, Attention, SegmentationHead
+                      team_code_v2/models/rgb.py:48-83, lav/models/attention.py, segmentation.py
+
+Only the crop (bilinear rotated window gather) is a lav_b200 CUDA kernel; convs/GRUs here are cuDNN.
+"""
+import math
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+
+# ----------------------------------------------------------------------------- ResNet-18
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = downsample
+
+    def forward(self, x):
+        idt = x if self.downsample is None else self.downsample(x)
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        return self.relu(out + idt)
+
+
+class ResNet18(nn.Module):
+    def __init__(self, num_channels=3, num_classes=1000):
+        super().__init__()
+        self.conv1 = nn.Conv2d(num_channels, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        inpl = 64
+        for i, (planes, stride) in enumerate(((64, 1), (128, 2), (256, 2), (512, 2)), 1):
+            ds = None
+            if stride != 1 or inpl != planes:
+                ds = nn.Sequential(nn.Conv2d(inpl, planes, 1, stride, bias=False), nn.BatchNorm2d(planes))
+            setattr(self, f"layer{i}", nn.Sequential(BasicBlock(inpl, planes, stride, ds), BasicBlock(planes, planes)))
+            inpl = planes
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))       # present in the reference module tree, unused
+        self.fc = nn.Linear(512, num_classes)             # keys exist in the checkpoints, unused (resnet.py:235-247)
+
+    def forward(self, x):
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        return self.layer4(self.layer3(self.layer2(self.layer1(x))))
+
+
+def resnet18(pretrained=False, num_channels=3, **kw):
+    return ResNet18(num_channels=num_channels)
+
+
+# ----------------------------------------------------------------------------- planners
+def transform_points(locs, oris):
+    cos, sin = torch.cos(oris), torch.sin(oris)
+    R = torch.stack([torch.stack([cos, sin], dim=-1), torch.stack([-sin, cos], dim=-1)], dim=-2)
+    return locs @ R
+
+
+def crop_theta(rel_locs, rel_oris, H, W, pixels_per_meter, crop_size, offset_x, offset_y):
+    """affine theta (K,2,3) of UniPlanner.crop_feature (team_code_v2/models/uniplanner.py:303-333)."""
+    rel_locs = rel_locs.view(-1, 2) * pixels_per_meter / torch.tensor([H / 2, W / 2]).type_as(rel_locs).to(rel_locs.device)
+    cos, sin = torch.cos(rel_oris), torch.sin(rel_oris)
+    rel_x, rel_y = rel_locs[..., 0], rel_locs[..., 1]
+    k = crop_size / H
+    rot_x_offset = -k * offset_x * cos + k * offset_y * sin + offset_x
+    rot_y_offset = -k * offset_x * sin - k * offset_y * cos + offset_y
+    return torch.stack([torch.stack([k * cos, k * -sin, rot_x_offset + rel_x], dim=-1),
+                        torch.stack([k * sin, k * cos, rot_y_offset + rel_y], dim=-1)], dim=-2)
+
+
+class BEVPlanner(nn.Module):
+    """Weight container for the privileged teacher nested in the UniPlanner checkpoint (bev_planner.*)."""
+
+    def __init__(self, pixels_per_meter=2, crop_size=64, x_offset=0, y_offset=0.75, feature_x_jitter=1, feature_angle_jitter=10,
+                 num_plan=10, k=16, num_out_feature=64, num_cmds=6, max_num_cars=5, num_plan_iter=1, num_frame_stack=0):
+        super().__init__()
+        self.num_cmds, self.num_plan, self.num_plan_iter = num_cmds, num_plan, num_plan_iter
+        self.pixels_per_meter, self.crop_size = pixels_per_meter, crop_size
+        self.offset_x = nn.Parameter(torch.tensor(x_offset).float(), requires_grad=False)
+        self.offset_y = nn.Parameter(torch.tensor(y_offset).float(), requires_grad=False)
+        self.bev_conv_emb = nn.Sequential(resnet18(num_channels=3 + 2 * (num_frame_stack + 1)), nn.AdaptiveAvgPool2d((1, 1)), nn.Flatten())
+        self.plan_gru = nn.GRU(4, 512, batch_first=True)
+        self.plan_mlp = nn.Linear(512, 2)
+        self.cast_grus = nn.ModuleList([nn.GRU(512, 64, batch_first=True) for _ in range(num_cmds)])
+        self.cast_mlps = nn.ModuleList([nn.Linear(64, 2) for _ in range(num_cmds)])
+        self.cast_cmd_pred = nn.Sequential(nn.Linear(512, num_cmds), nn.Sigmoid())
+
+
+class UniPlanner(nn.Module):
+    def __init__(self, bev_planner, pixels_per_meter=2, crop_size=64, x_offset=0, y_offset=0.75, feature_x_jitter=1,
+                 feature_angle_jitter=10, num_plan=10, k=16, num_input_feature=96, num_out_feature=64, num_cmds=6,
+                 max_num_cars=4, num_plan_iter=1):
+        super().__init__()
+        self.num_cmds, self.num_plan, self.num_plan_iter, self.max_num_cars = num_cmds, num_plan, num_plan_iter, max_num_cars
+        self.bev_planner = bev_planner
+        self.num_out_feature = num_out_feature
+        self.pixels_per_meter, self.crop_size = pixels_per_meter, crop_size
+        self.feature_x_jitter = feature_x_jitter
+        self.feature_angle_jitter = np.deg2rad(feature_angle_jitter)
+        self.offset_x = nn.Parameter(torch.tensor(x_offset).float(), requires_grad=False)
+        self.offset_y = nn.Parameter(torch.tensor(y_offset).float(), requires_grad=False)
+        self.lidar_conv_emb = nn.Sequential(resnet18(num_channels=num_input_feature), nn.AdaptiveAvgPool2d((1, 1)), nn.Flatten())
+        self.plan_gru = nn.GRU(4, 512, batch_first=True)
+        self.plan_mlp = nn.Linear(512, 2)
+        self.cast_grus_ego = nn.ModuleList([nn.GRU(512, 64, batch_first=True) for _ in range(num_cmds)])
+        self.cast_mlps_ego = nn.ModuleList([nn.Linear(64, 2) for _ in range(num_cmds)])
+        self.cast_grus_other = nn.ModuleList([nn.GRU(512, 64, batch_first=True) for _ in range(num_cmds)])   # dead weights, kept
+        self.cast_mlps_other = nn.ModuleList([nn.Linear(64, 2) for _ in range(num_cmds)])
+        self.cast_cmd_pred = nn.Sequential(nn.Linear(512, num_cmds), nn.Sigmoid())
+
+    # -- crop: one CUDA kernel on channels-last features (or grid_sample for generic callers)
+    def crop_feature(self, features, rel_locs, rel_oris, pixels_per_meter=4, crop_size=96, frame_idx=None):
+        """features: logical (B,C,H,W).  With ``frame_idx`` (K,) the K crops read features[frame_idx[k]] without
+        materialising an expanded copy."""
+        B, C, H, W = features.size()
+        theta = crop_theta(rel_locs, rel_oris, H, W, pixels_per_meter, crop_size, self.offset_x, self.offset_y)
+        if features.is_cuda:
+            from . import ops
+            feats_nhwc = features.permute(0, 2, 3, 1)
+            if feats_nhwc.is_contiguous():
+                if frame_idx is None:
+                    frame_idx = torch.arange(theta.shape[0], device=features.device, dtype=torch.int32) % B
+                return ops.crop_bilinear(feats_nhwc, frame_idx, theta, crop_size).permute(0, 3, 1, 2)
+        if frame_idx is not None:
+            features = features[frame_idx.long()]
+        grids = F.affine_grid(theta, torch.Size((theta.shape[0], C, crop_size, crop_size)), align_corners=True)
+        return F.grid_sample(features, grids, align_corners=True)
+
+    def cast(self, embd, mode='ego'):
+        B = embd.size(0)
+        u = embd.expand(self.num_plan, B, -1).permute(1, 0, 2)
+        locs = []
+        for gru, mlp in zip(self.cast_grus_ego, self.cast_mlps_ego):     # 'other' re-uses the ego GRUs (uniplanner.py:296-300)
+            out, _ = gru(u.contiguous())
+            locs.append(torch.cumsum(mlp(out), dim=1))
+        return torch.stack(locs, dim=1)
+
+    def _plan(self, embd, nxp, cast_locs, pixels_per_meter=4, crop_size=96):
+        B = embd.size(0)
+        h0, u0 = embd, nxp * pixels_per_meter / crop_size * 2 - 1
+        # the six command branches share plan_gru/plan_mlp: run them as one batch of 6*B sequences
+        u = torch.cat([u0[:, None, None].expand(B, self.num_cmds, self.num_plan, 2), cast_locs], dim=3)
+        out, _ = self.plan_gru(u.reshape(B * self.num_cmds, self.num_plan, 4),
+                               h0[:, None].expand(B, self.num_cmds, -1).reshape(1, B * self.num_cmds, -1).contiguous())
+        locs = torch.cumsum(self.plan_mlp(out), dim=1).view(B, self.num_cmds, self.num_plan, 2)
+        return locs + cast_locs
+
+    def plan(self, embd, nxp, cast_locs=None, pixels_per_meter=4, crop_size=96):
+        plan_loc = (self.cast(embd) if cast_locs is None else cast_locs).detach()
+        plan_locs = []
+        for _ in range(self.num_plan_iter):
+            plan_loc = self._plan(embd, nxp, plan_loc, pixels_per_meter=pixels_per_meter, crop_size=crop_size)
+            plan_locs.append(plan_loc)
+        return torch.stack(plan_locs, dim=1)
+
+    def det_to_locs(self, det, H, W):
+        """detections -> (locs list, oris list) in ego metres (uniplanner.py:195-214)."""
+        center_x = float(W / 2 + self.offset_x * W / 2)
+        center_y = float(H / 2 + self.offset_y * H / 2)
+        locs, oris = [], []
+        for X, Y, h, w, cos, sin in det:
+            if np.linalg.norm([X - center_x, Y - center_y]) <= 4:
+                continue
+            locs.append([(X - center_x) / self.pixels_per_meter, (Y - center_y) / self.pixels_per_meter])
+            oris.append(float(np.arctan2(sin, cos)))
+        return locs, oris
+
+    @torch.no_grad()
+    def infer_batch(self, features, dets, cmds, nxps):
+        """Batched UniPlanner.infer: features logical (B,C,h,w); dets[b] = vehicle detections of frame b;
+        cmds (B,) ints; nxps (B,2).  All crops of the batch go through one embed / GRU roll-out.
+        Returns per-frame lists like infer(): (ego_embd, ego_plan_locs, ego_cast_locs, other_cast_locs, other_cast_cmds)."""
+        B = features.size(0)
+        dev = features.device
+        H, W = features.size(2) * 2, features.size(3) * 2
+        locs, oris, fidx, counts = [], [], [], []
+        for b, det in enumerate(dets):
+            l, o = self.det_to_locs(det, H, W)
+            locs += l
+            oris += o
+            fidx += [b] * len(l)
+            counts.append(len(l))
+        K = len(locs)
+        all_locs = torch.tensor(locs + [[0.0, 0.0]] * B, dtype=torch.float32).view(-1, 2).to(dev)
+        all_oris = torch.tensor(oris + [0.0] * B, dtype=torch.float32).to(dev)
+        all_fidx = torch.tensor(fidx + list(range(B)), dtype=torch.int32).to(dev)
+        crops = self.crop_feature(features, all_locs, all_oris, pixels_per_meter=self.pixels_per_meter / 2,
+                                  crop_size=self.crop_size, frame_idx=all_fidx)
+        embd = self.lidar_conv_emb(crops.to(self.lidar_conv_emb[0].conv1.weight.dtype)).float()
+        cast = self.cast(embd)
+        ego_embd, ego_cast = embd[K:], cast[K:]
+        ego_plan = self.plan(ego_embd, nxps.to(dev).float(), cast_locs=ego_cast, pixels_per_meter=self.pixels_per_meter,
+                             crop_size=self.crop_size * 2)[:, -1]
+        ar = torch.arange(B, device=dev)
+        cmds = torch.as_tensor(cmds, device=dev).long()
+        ego_plan_locs, ego_cast_locs = ego_plan[ar, cmds], ego_cast[ar, cmds]
+        if K > 0:
+            o_cast = transform_points(cast[:K], all_oris[:K, None].repeat(1, self.num_cmds)) + all_locs[:K].view(K, 1, 1, 2)
+            o_cmds = self.cast_cmd_pred(embd[:K])
+        else:
+            o_cast = torch.zeros((0, self.num_cmds, self.num_plan, 2), device=dev)
+            o_cmds = torch.zeros((0, self.num_cmds), device=dev)
+        return ego_embd, ego_plan_locs, ego_cast_locs, torch.split(o_cast, counts), torch.split(o_cmds, counts)
+
+    @torch.no_grad()
+    def infer(self, features, det, cmd, nxp):
+        """UniPlanner.infer (team_code_v2/models/uniplanner.py:186-247): features (C,h,w), B = 1."""
+        ee, epl, ecl, ocl, occ = self.infer_batch(features[None], [det], [cmd], nxp[None])
+        if len(ocl[0]) == 0:   # reference returns CPU zeros here (uniplanner.py:234-235)
+            return epl[0], ecl[0], torch.zeros((0, self.num_cmds, self.num_plan, 2)), torch.zeros((0, self.num_cmds))
+        return epl[0], ecl[0], ocl[0], occ[0]
+
+
+# ----------------------------------------------------------------------------- brake predictor
+def positionalencoding1d(d_model, length):
+    pe = torch.zeros(length, d_model)
+    position = torch.arange(0, length).unsqueeze(1)
+    div_term = torch.exp((torch.arange(0, d_model, 2, dtype=torch.float) * -(math.log(10000.0) / d_model)))
+    pe[:, 0::2] = torch.sin(position.float() * div_term)
+    pe[:, 1::2] = torch.cos(position.float() * div_term)
+    return pe
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, num_heads=8):
+        super().__init__()
+        dim_head = dim // num_heads
+        self.q = nn.Parameter(torch.randn(1, num_heads, 1, dim_head))
+        self.linear_kv = nn.Linear(dim, dim * 2)
+        self.num_heads, self.dim_head, self.scale = num_heads, dim_head, dim_head ** -0.5
+        self._pe = {}
+
+    def forward(self, x):
+        b, d, h, w = x.shape
+        x = x.flatten(2).transpose(1, 2)
+        k, v = self.linear_kv(x).chunk(2, dim=-1)
+        key = (h * w, x.device, x.dtype)
+        if key not in self._pe:
+            self._pe[key] = positionalencoding1d(d // self.num_heads, h * w).to(x.device, x.dtype)
+        k = k.view(b, h * w, self.num_heads, -1).transpose(1, 2) + self._pe[key]
+        v = v.view(b, h * w, self.num_heads, -1).transpose(1, 2)
+        dots = torch.matmul(self.q.to(x.dtype).expand(b, -1, -1, -1), k.transpose(-1, -2)) * self.scale
+        return torch.matmul(torch.softmax(dots, dim=-1), v).transpose(1, 2).reshape(b, d)
+
+
+class SegmentationHead(nn.Module):
+    def __init__(self, input_channels, num_labels):
+        super().__init__()
+        self.upconv = nn.Sequential(
+            nn.ConvTranspose2d(input_channels, 256, 3, 2, 1, 1), nn.BatchNorm2d(256), nn.ReLU(True),
+            nn.ConvTranspose2d(256, 128, 3, 2, 1, 1), nn.BatchNorm2d(128), nn.ReLU(True),
+            nn.ConvTranspose2d(128, 64, 3, 2, 1, 1), nn.BatchNorm2d(64), nn.ReLU(True),
+            nn.Conv2d(64, num_labels, 1, 1, 0))
+
+    def forward(self, x):
+        return self.upconv(x)
+
+
+class Normalize(nn.Module):
+    def __init__(self, mean, std):
+        super().__init__()
+        self.mean = nn.Parameter(torch.tensor(mean), requires_grad=False)
+        self.std = nn.Parameter(torch.tensor(std), requires_grad=False)
+
+    def forward(self, x):
+        return (x - self.mean[None, :, None, None]) / self.std[None, :, None, None]
+
+
+class RGBBrakePredictionModel(nn.Module):
+    def __init__(self, seg_channels, pretrained=False):
+        super().__init__()
+        self.conv_backbone = resnet18(pretrained=pretrained)
+        self.normalize = Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
+        self.seg_head = SegmentationHead(512, len(seg_channels) + 1)
+        self.attn1 = Attention(512, num_heads=8)
+        self.attn2 = Attention(512, num_heads=8)
+        self.classifier = nn.Sequential(nn.Linear(1024, 1), nn.Sigmoid())
+
+    def forward(self, rgb1, rgb2, mask=False):
+        dt = self.conv_backbone.conv1.weight.dtype
+        x1 = self.conv_backbone(self.normalize(rgb1 / 255.).to(dt))
+        x2 = self.conv_backbone(self.normalize(rgb2 / 255.).to(dt))
+        pred_bra = self.classifier(torch.cat([self.attn1(x1), self.attn2(x2)], dim=1).float())
+        if mask:
+            return (pred_bra[:, 0], F.interpolate(self.seg_head(x1), scale_factor=4), F.interpolate(self.seg_head(x2), scale_factor=4))
+        return pred_bra[:, 0]

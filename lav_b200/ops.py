@@ -34,6 +34,22 @@ def launches():
 
 
 _COUNT = [0]
+PROFILE = None     # bench.py sets this to a list to collect (kind, work, start_event, end_event) per launch
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _prof_end(kind, work, e0):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        PROFILE.append((kind, work, e0, e1))
 
 
 # ----------------------------------------------------------------------------- painting
@@ -102,9 +118,12 @@ def pillar_forward(pts, starts, counts, grid, w1, s1, t1, w2, s2, t2):
     b, st, ct = _clouds(starts, counts)
     canvas = torch.empty((b, ny, nx, w2.shape[0]), dtype=torch.float32, device=pts.device)
     ws = _workspace(pts.device, lib().lavb_pillar_workspace_bytes(b, nx, ny))
+    e0 = _prof_begin()
     check(lib().lavb_pillar_forward(_ptr(pts), pts.stride(0), d, st, ct, b, min_x, max_x, min_y, max_y, ppm, nx, ny,
                                     _ptr(w1), _ptr(s1), _ptr(t1), w1.shape[0], _ptr(w2), _ptr(s2), _ptr(t2), w2.shape[0],
                                     _ptr(canvas), F32, _ptr(ws), _stream()), "lavb_pillar_forward")
+    # algorithmic bytes: read P x D fp32 points once + write the canvas once
+    _prof_end("pillar", float(sum(int(c) for c in counts)) * d * 4 + canvas.numel() * 4, e0)
     _COUNT[0] += 4
     return canvas
 
@@ -183,7 +202,9 @@ def conv_taps(x, cin, in_coff, out, cout, out_coff, hog, wog, in_s, out_s, out_o
         d.res, d.res_dtype, d.res_cstride, d.res_coff = res.data_ptr(), _DT[res.dtype], res.shape[3], res_coff
     d.pre_relu, d.post_relu, d.sigmoid = int(pre_relu), int(post_relu), int(sigmoid)
     if umma:
+        e0 = _prof_begin()
         check(lib().lavb_conv_umma(C.byref(d), _stream()), "lavb_conv_umma")
+        _prof_end("umma", 2.0 * x.shape[0] * hog * wog * cout * cin * len(taps), e0)
     else:
         check(lib().lavb_conv_taps(C.byref(d), _stream()), "lavb_conv_taps")
     _COUNT[0] += 1
@@ -227,3 +248,18 @@ def convert(src, dtype):
     check(lib().lavb_convert(_ptr(src), _DT[src.dtype], _ptr(dst), _DT[dtype], src.numel(), _stream()), "lavb_convert")
     _COUNT[0] += 1
     return dst
+
+
+def crop_bilinear(feats_nhwc, frame_idx, theta, crop_size):
+    """feats_nhwc (B,H,W,C) contiguous fp32/bf16; frame_idx (K,) int32; theta (K,2,3) fp32 -> (K,crop,crop,C)."""
+    _need_cuda(feats_nhwc, frame_idx, theta)
+    assert feats_nhwc.is_contiguous()
+    b, h, w, c = feats_nhwc.shape
+    k = theta.shape[0]
+    theta = theta.float().contiguous()
+    frame_idx = frame_idx.to(torch.int32).contiguous()
+    out = torch.empty((k, crop_size, crop_size, c), dtype=feats_nhwc.dtype, device=feats_nhwc.device)
+    check(lib().lavb_crop_bilinear(_ptr(feats_nhwc), _DT[feats_nhwc.dtype], b, h, w, c, _ptr(frame_idx), _ptr(theta), k, crop_size,
+                                   _ptr(out), _stream()), "lavb_crop_bilinear")
+    _COUNT[0] += 1
+    return out
