@@ -100,8 +100,14 @@ def run_reference(args, rank, world):
     """the reference's own CPU implementation of the frame path (oracle port of its PyTorch modules) on the host cores."""
     if rank != 0:
         return
+    if os.environ.get("BENCH_DEBUG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_DEBUG"]), exit=True)
     from oracle import lav_ref as O
-    cores = os.cpu_count() or 1
+    # all the host threads the path can USE: on the 2-socket 128-thread box oneDNN's small convs (ResNet-18 on 3x3..6x6
+    # maps) collapse under 128-way fork-join (measured: one 7x7 conv 0.02 s @32 threads, 0.28 s @128, the whole frame
+    # never finished in 100 s), so the port is timed at min(cpu_count, 32) threads and says so in `cores`.
+    cores = min(os.cpu_count() or 1, int(os.environ.get("LAVB_CPU_THREADS", 32)))
     torch.set_num_threads(cores)
     _, sds = build_models()
     sd_seg, sd_lid, sd_uni, sd_bra = sds
@@ -123,7 +129,9 @@ def run_reference(args, rank, world):
             bra = O.brake_model(sd_bra, wide, tels[:1].permute(0, 3, 1, 2).float())
             return out[1], bra
     for _ in range(args.warmup):
+        tw = time.perf_counter()
         frame()
+        _dbg(f"reference warm-up frame {time.perf_counter() - tw:.2f} s on {cores} threads")
     t0 = time.perf_counter()
     for _ in range(args.steps):
         frame()
@@ -147,7 +155,18 @@ def workload_config(B, precision):
             "parallelism": "replicas (one process per GPU, no data-path collective)"}
 
 
+def _dbg(msg):
+    if os.environ.get("BENCH_DEBUG"):
+        print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+_T0 = time.time()
+
+
 def main():
+    if os.environ.get("BENCH_DEBUG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_DEBUG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -237,13 +256,19 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms), t0, t1
 
+    _dbg("models + inputs ready")
+    step_resident(0)
+    torch.cuda.synchronize()
+    _dbg("first step done")
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = ops.launches()
     ms, t0, t1 = timed(step_resident, args.steps, args.warmup)
     launches = (ops.launches() - l0) // (args.steps + args.warmup) * args.steps
+    _dbg(f"timed resident loop done: {ms / args.steps:.2f} ms/step")
     clocks = sampler.stop(t0, t1) if sampler else None
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
 
+    _dbg(f"e2e loop done: {ms_e2e / args.steps:.2f} ms/step")
     # roofline of the dominant kernel (tcgen05 conv), timed per launch with CUDA events on the launch stream
     ops.PROFILE = []
     for i in range(max(2, args.steps // 4)):

@@ -68,6 +68,9 @@ class FramePipeline:
 
     def set_precision(self, precision):
         self.precision = precision
+        if precision == "fp32":   # exact path: keep cuDNN (PyTorch heads) out of TF32 as well
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
         self.seg_model.set_precision(precision)
         self.infer_model.lidar_model.set_precision(precision)
         dt = torch.bfloat16 if precision == "bf16" else torch.float32

@@ -24,4 +24,7 @@ def cuda():
         pytest.skip("no CUDA device")
     from lav_b200 import capi
     capi.lib()          # fail loudly if the extension is missing on a GPU box
+    # fp32 parity means fp32: cuDNN would otherwise run the PyTorch heads' convs / GRUs in TF32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     return torch.device("cuda:0")

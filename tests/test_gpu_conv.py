@@ -89,7 +89,7 @@ def test_lidar_model_bf16(cuda):
         rms = float(((a - b) ** 2).mean().sqrt() / (b ** 2).mean().sqrt())
         assert rms < 1e-2, (n, rms)
         if n != "seg":     # sigmoid of O(30) random-weight logits amplifies bf16 rounding; RMS bound covers it
-            assert util.rel_err(a, b) < 5e-2, (n, util.rel_err(a, b))
+            assert util.rel_err(a, b) < 1.2e-2, (n, util.rel_err(a, b))
 
 
 @pytest.mark.parametrize("weights", ["seeded", "real"])
