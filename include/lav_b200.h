@@ -50,12 +50,25 @@ int lavb_paint(const float* d_pts, int n, int pt_stride,
                const float* h_cams, int mode,
                float* d_out, int out_stride, int out_col0, int copy_cols, void* stream);
 
+/* the same for `frames` independent agents in one launch: frame f reads points at d_pts + f*pts_frame_stride (floats),
+ * semantic maps at d_sem + f*s_frame, writes rows at d_out + f*out_frame_stride (floats). */
+int lavb_paint_batched(const float* d_pts, int frames, int n, int pt_stride, long long pts_frame_stride,
+                       const float* d_sem, int ncam, int c_in, int h, int w, long long s_frame, long long s_cam,
+                       long long s_c, long long s_y, long long s_x, const float* h_cams, int mode, float* d_out,
+                       int out_stride, long long out_frame_stride, int out_col0, int copy_cols, void* stream);
+
 /* ---------------------------------------------------------------- sweep stacking
  * replaces: LAVAgent.get_stacked_lidar + move_lidar_points (team_code_v2/lav_agent_fast.py:363-383,547-565)
  * and the ego-roof filter LAVAgent.preprocess (lav_agent.py:448-457, roof_filter!=0 marks dropped rows x=NaN).
  * dst row = [xyz @ R + (dx,dy,0) | src cols 3..src_cols | one_hot(time_idx, n_time)];  h_R is 3x3 row-major. */
 int lavb_stack_sweep(const float* d_src, int n, int src_cols, const float* h_R, float dx, float dy,
                      int time_idx, int n_time, int roof_filter, float* d_dst, void* stream);
+
+/* table-driven variant: d_jobs is a DEVICE array of n_jobs 72-byte records
+ *   { const float* src; float* dst; int n; int time_idx; float R[9]; float dx, dy; int pad; }
+ * (one per (agent, sweep)); all jobs run in one launch and the table can be rewritten between replays of a captured
+ * CUDA graph (new poses, new ring-buffer slots) without touching kernel arguments. max_n = largest job. */
+int lavb_stack_jobs(const void* d_jobs, int n_jobs, int max_n, int src_cols, int n_time, int roof_filter, void* stream);
 
 /* ---------------------------------------------------------------- PointPillars voxeliser + pillar encoder
  * replaces: PointPillarNet.forward (lav/models/point_pillar.py:92-116) incl. grid_locations :70-79,
@@ -110,6 +123,14 @@ typedef struct {
 } lavb_conv_desc;
 int lavb_conv_taps(const lavb_conv_desc* h_desc, void* stream);
 
+/* grouped ConvTranspose2d(k3,s2,p1,op1) with <=4 output channels per group: the 4 head output layers in one launch.
+ * replaces: Head.net[3] x4 (lav/models/lidar.py:155,159-164) incl. bias and the seg head's sigmoid.
+ * d_in NHWC [n][h][w][in_cstride] (group g reads channels [g*cin_g,(g+1)*cin_g)); d_w fp32 [g][cin_g][9][4]
+ * (tap = ky*3+kx, cout padded to 4); d_bias [g][4]; output g: fp32 NHWC [n][2h][2w][n_out[g]]. */
+int lavb_deconv3x3s2_small(const void* d_in, int dtype, int n, int h, int w, int in_cstride, int groups, int cin_g,
+                           const float* d_w, const float* d_bias, const int* h_n_out, const int* h_sigmoid,
+                           float* const* h_out_ptrs, void* stream);
+
 /* 2x2/2 max-pool -> y*scale[c]+shift[c] -> ReLU into a channel slice (ERFNet DownsamplerBlock, erfnet.py:20-23) */
 int lavb_pool2_affine_relu(const void* d_in, int dtype, int n, int hin, int win, int c, int in_cstride, int in_coff,
                            const float* d_scale, const float* d_shift,
@@ -129,6 +150,9 @@ int lavb_crop_bilinear(const void* d_feat, int dtype, int b, int h, int w, int c
                        const float* d_theta, int k, int crop, void* d_out, void* stream);
 
 /* dtype / layout helpers */
+/* fp32 [rows][c] -> bf16 [rows][hi(c) | lo(c)] with hi = bf16(x), lo = bf16(x - hi) (error-free split of the canvas so the
+ * first tensor-core conv sees ~fp32 input precision; its weights are duplicated along cin by the host). */
+int lavb_split_bf16(const float* d_src, void* d_dst, long long rows, int c, void* stream);
 int lavb_convert(const void* d_src, int src_dtype, void* d_dst, int dst_dtype, long long count, void* stream);
 
 /* ---------------------------------------------------------------- tcgen05 implicit-GEMM tap-list convolution

@@ -38,6 +38,10 @@ _SIGS = {
     "lavb_paint": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                              C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int,
                              C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "lavb_paint_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "lavb_stack_jobs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "lavb_stack_sweep": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p]),
     "lavb_pillar_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
@@ -55,9 +59,12 @@ _SIGS = {
     "lavb_pool2_affine_relu": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "lavb_rgb_normalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "lavb_split_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "lavb_convert": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "lavb_crop_bilinear": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_int, C.c_void_p, C.c_void_p]),
+    "lavb_deconv3x3s2_small": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lavb_conv_umma": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
 }
 

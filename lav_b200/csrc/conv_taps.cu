@@ -215,9 +215,107 @@ __global__ void __launch_bounds__(256) pool2_kernel(const T* __restrict__ in, in
   out[(((long long)nn * ho + oy) * wo + ox) * out_cstride + out_coff + ch] = from_f32<T>(y);
 }
 
+// ---- small-channel direct convolution (cin <= 16): one thread per output-grid pixel, 16 output channels per pass.
+// The GEMM tiling above wastes its K loop on these layers (ERFNet's 3->13 / 16->48 entry convs, the 16-channel decoder
+// blocks and the 16->5 output ConvT, erfnet.py:67-71,116-124); they are pure HBM streams: coalesced 32-64 B per
+// thread in, same out, weights broadcast from shared memory.
+template <typename TIn, typename TOut, int CIN>
+__global__ void __launch_bounds__(256) conv_small_kernel(const __grid_constant__ ConvArgs a) {
+  extern __shared__ __align__(16) float wsm[];   // [ntaps][CIN][16] for the current cout chunk
+  const int co0 = blockIdx.y * 16;
+  for (int i = threadIdx.x; i < a.ntaps * CIN * 16; i += blockDim.x) {
+    const int t = i / (CIN * 16), r = i - t * CIN * 16, ci = r / 16, co = r % 16;
+    wsm[i] = (ci < a.cin) ? __ldg(a.w + ((long long)t * a.cin + ci) * a.cout_pad + co0 + co) : 0.f;
+  }
+  __syncthreads();
+  const long long M = (long long)a.n * a.hog * a.wog;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int hw = a.hog * a.wog;
+  const int nn = (int)(m / hw);
+  const int r = (int)(m - (long long)nn * hw);
+  const int gy = r / a.wog, gx = r % a.wog;
+  const TIn* in = reinterpret_cast<const TIn*>(a.in);
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (int t = 0; t < a.ntaps; ++t) {
+    const int iy = gy * a.in_sy + a.dy[t], ix = gx * a.in_sx + a.dx[t];
+    if (iy < 0 || iy >= a.hin || ix < 0 || ix >= a.win) continue;
+    const TIn* p = in + (((long long)nn * a.hin + iy) * a.win + ix) * a.in_cstride + a.in_coff;
+    float xv[CIN];
+#pragma unroll
+    for (int c = 0; c < CIN; c += 4) {
+      const float4 v = (c < a.cin) ? load4<TIn>(p + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xv[c] = v.x; xv[c + 1] = v.y; xv[c + 2] = v.z; xv[c + 3] = v.w;
+    }
+    const float4* wt = reinterpret_cast<const float4*>(wsm + (size_t)t * CIN * 16);
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w = wt[c * 4 + q];
+        acc[q * 4] = fmaf(xv[c], w.x, acc[q * 4]); acc[q * 4 + 1] = fmaf(xv[c], w.y, acc[q * 4 + 1]);
+        acc[q * 4 + 2] = fmaf(xv[c], w.z, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(xv[c], w.w, acc[q * 4 + 3]);
+      }
+    }
+  }
+  const int oy = gy * a.out_sy + a.out_oy, ox = gx * a.out_sx + a.out_ox;
+  if (oy >= a.hout || ox >= a.wout) return;
+  const long long pix = ((long long)nn * a.hout + oy) * a.wout + ox;
+  TOut* out = reinterpret_cast<TOut*>(a.out) + pix * a.out_cstride + a.out_coff;
+  const TOut* res = a.res ? reinterpret_cast<const TOut*>(a.res) + pix * a.res_cstride + a.res_coff : nullptr;
+  const bool vec_ok = (a.cout % 4 == 0) && (a.out_coff % 4 == 0) && (a.out_cstride % 4 == 0) &&
+                      (res == nullptr || (a.res_coff % 4 == 0 && a.res_cstride % 4 == 0));
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int co = co0 + q * 4;
+    if (co >= a.cout) break;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = co + j;
+      float x = acc[q * 4 + j];
+      if (c < a.cout) {
+        if (a.bias) x += __ldg(a.bias + c);
+        if (a.pre_relu) x = fmaxf(x, 0.f);
+        if (a.scale) x = fmaf(x, __ldg(a.scale + c), __ldg(a.shift + c));
+        if (res && !vec_ok) x += to_f32<TOut>(res[c]);
+      }
+      v[j] = x;
+    }
+    if (vec_ok) {
+      if (res) { const float4 rr = load4<TOut>(res + co); v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (a.post_relu) v[j] = fmaxf(v[j], 0.f);
+        if (a.sigmoid) v[j] = 1.f / (1.f + expf(-v[j]));
+      }
+      store4<TOut>(out + co, make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (co + j >= a.cout) continue;
+        float x = v[j];
+        if (a.post_relu) x = fmaxf(x, 0.f);
+        if (a.sigmoid) x = 1.f / (1.f + expf(-x));
+        out[co + j] = from_f32<TOut>(x);
+      }
+    }
+  }
+}
+
 template <typename TIn, typename TOut>
 static int launch_conv(const ConvArgs& a, cudaStream_t st) {
   const long long M = (long long)a.n * a.hog * a.wog;
+  if (a.cin <= 16) {
+    dim3 grid(ceil_div(M, 256), a.cout_pad / 16);
+    const size_t smem = (size_t)a.ntaps * 16 * 16 * sizeof(float);
+    if (a.cin <= 4) conv_small_kernel<TIn, TOut, 4><<<grid, 256, (size_t)a.ntaps * 4 * 16 * sizeof(float), st>>>(a);
+    else conv_small_kernel<TIn, TOut, 16><<<grid, 256, smem, st>>>(a);
+    LAVB_LAUNCH_OK();
+    return 0;
+  }
   if (a.cout_pad % 64 == 0) {
     dim3 grid(ceil_div(M, 128), a.cout_pad / 64);
     conv_taps_kernel<TIn, TOut, 128, 64, 8, 2><<<grid, 128, 0, st>>>(a);

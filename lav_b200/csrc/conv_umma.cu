@@ -329,7 +329,13 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   a.bias = d->bias; a.scale = d->scale; a.shift = d->shift;
   if (a.num_tiles == 0) return 0;
   const size_t smem = (size_t)a.stages * stage_bytes + 1024 /*align*/ + 16 * kMaxStages + 64 + 3 * 256 * sizeof(float);
-  LAVB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {  // once per process (never during a later stream capture): opt in to the full 227 KB of dynamic shared memory
+    static bool configured = false;
+    if (!configured) {
+      LAVB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      configured = true;
+    }
+  }
   const int grid = min(a.num_tiles, kNumSMs);
   conv_umma_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmap_a, tmap_b, a);
   LAVB_LAUNCH_OK();

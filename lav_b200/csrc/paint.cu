@@ -40,9 +40,15 @@ __global__ void __launch_bounds__(256) paint_kernel(const float* __restrict__ pt
                                                     const float* __restrict__ sem, int c_in, int H, int W,
                                                     long long s_cam, long long s_c, long long s_y, long long s_x,
                                                     const __grid_constant__ CamSet cams, float* __restrict__ out,
-                                                    int out_stride, int out_col0, int copy_cols) {
+                                                    int out_stride, int out_col0, int copy_cols,
+                                                    long long pts_frame_stride, long long sem_frame_stride,
+                                                    long long out_frame_stride) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  // blockIdx.y = frame of a batch of independent agents (each with its own sweep and semantic maps)
+  pts += blockIdx.y * pts_frame_stride;
+  sem += blockIdx.y * sem_frame_stride;
+  out += blockIdx.y * out_frame_stride;
   const float* p = pts + (size_t)i * pt_stride;
   float x, y, z;
   float4 p4;
@@ -170,13 +176,43 @@ __global__ void __launch_bounds__(256) convert_kernel(const TS* __restrict__ s, 
   }
 }
 
+// fp32 -> (hi, lo) bf16 pair per element, laid out [row][hi(C) | lo(C)]: hi = bf16(x), lo = bf16(x - hi).  Feeding both
+// halves to a tensor-core conv whose weights are duplicated along cin recovers ~16 mantissa bits of the input.
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                         long long rows, int c) {
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= rows * c) return;
+  const long long r = i4 / c;
+  const int ch = (int)(i4 - r * c);
+  const float4 v = __ldg(reinterpret_cast<const float4*>(src + i4));
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  float hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    hi[e] = __bfloat162float(__float2bfloat16_rn(x[e]));
+    lo[e] = x[e] - hi[e];
+  }
+  __nv_bfloat16* d = dst + r * 2 * c + ch;
+  store4<__nv_bfloat16>(d, make_float4(hi[0], hi[1], hi[2], hi[3]));
+  store4<__nv_bfloat16>(d + c, make_float4(lo[0], lo[1], lo[2], lo[3]));
+}
+
 }  // namespace lavb
 
 using namespace lavb;
 
-extern "C" int lavb_paint(const float* d_pts, int n, int pt_stride, const float* d_sem, int ncam, int c_in, int h, int w,
-                          long long s_cam, long long s_c, long long s_y, long long s_x, const float* h_cams, int mode,
-                          float* d_out, int out_stride, int out_col0, int copy_cols, void* stream) {
+extern "C" int lavb_split_bf16(const float* d_src, void* d_dst, long long rows, int c, void* stream) {
+  LAVB_CHECK_ARG(c % 4 == 0 && c > 0, "split_bf16: channels must be a multiple of 4");
+  if (rows == 0) return 0;
+  split_bf16_kernel<<<ceil_div(rows * c / 4, 256), 256, 0, (cudaStream_t)stream>>>(d_src, (__nv_bfloat16*)d_dst, rows, c);
+  LAVB_LAUNCH_OK();
+  return 0;
+}
+
+static int paint_impl(const float* d_pts, int n, int pt_stride, const float* d_sem, int ncam, int c_in, int h, int w,
+                      long long s_cam, long long s_c, long long s_y, long long s_x, const float* h_cams, int mode,
+                      float* d_out, int out_stride, int out_col0, int copy_cols, int frames, long long pts_fs, long long sem_fs,
+                      long long out_fs, void* stream) {
   LAVB_CHECK_ARG(n >= 0 && pt_stride >= 3, "paint: bad n/pt_stride");
   LAVB_CHECK_ARG(ncam >= 1 && ncam <= 4, "paint: ncam must be 1..4 (got %d)", ncam);
   LAVB_CHECK_ARG(mode >= 0 && mode <= 2, "paint: mode must be 0..2");
@@ -184,16 +220,68 @@ extern "C" int lavb_paint(const float* d_pts, int n, int pt_stride, const float*
   const int c_out = mode ? c_in - 1 : c_in;
   LAVB_CHECK_ARG(copy_cols >= 0 && copy_cols <= pt_stride && out_col0 >= copy_cols && out_col0 + c_out <= out_stride,
                  "paint: output row layout inconsistent");
-  if (n == 0) return 0;
+  if (n == 0 || frames == 0) return 0;
   CamSet cs;
   memcpy(cs.m, h_cams, sizeof(float) * 41 * ncam);
   cs.ncam = ncam;
   cudaStream_t st = (cudaStream_t)stream;
-  const int blocks = ceil_div(n, 256);
+  const dim3 blocks(ceil_div(n, 256), frames);
 #define LAUNCH(M) paint_kernel<M><<<blocks, 256, 0, st>>>(d_pts, n, pt_stride, d_sem, c_in, h, w, s_cam, s_c, s_y, s_x, cs, \
-                                                           d_out, out_stride, out_col0, copy_cols)
+                                                           d_out, out_stride, out_col0, copy_cols, pts_fs, sem_fs, out_fs)
   if (mode == 0) LAUNCH(0); else if (mode == 1) LAUNCH(1); else LAUNCH(2);
 #undef LAUNCH
+  LAVB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int lavb_paint(const float* d_pts, int n, int pt_stride, const float* d_sem, int ncam, int c_in, int h, int w,
+                          long long s_cam, long long s_c, long long s_y, long long s_x, const float* h_cams, int mode,
+                          float* d_out, int out_stride, int out_col0, int copy_cols, void* stream) {
+  return paint_impl(d_pts, n, pt_stride, d_sem, ncam, c_in, h, w, s_cam, s_c, s_y, s_x, h_cams, mode, d_out, out_stride, out_col0,
+                    copy_cols, 1, 0, 0, 0, stream);
+}
+
+extern "C" int lavb_paint_batched(const float* d_pts, int frames, int n, int pt_stride, long long pts_frame_stride,
+                                  const float* d_sem, int ncam, int c_in, int h, int w, long long s_frame, long long s_cam,
+                                  long long s_c, long long s_y, long long s_x, const float* h_cams, int mode, float* d_out,
+                                  int out_stride, long long out_frame_stride, int out_col0, int copy_cols, void* stream) {
+  LAVB_CHECK_ARG(frames >= 0 && frames <= 65535, "paint_batched: frames out of range");
+  return paint_impl(d_pts, n, pt_stride, d_sem, ncam, c_in, h, w, s_cam, s_c, s_y, s_x, h_cams, mode, d_out, out_stride, out_col0,
+                    copy_cols, frames, pts_frame_stride, s_frame, out_frame_stride, stream);
+}
+
+// ---- table-driven sweep stacking: every (frame, sweep) job of a batch in one launch; the job table lives in DEVICE
+// memory so a captured CUDA graph replays with new poses / ring-buffer slots after a small H2D table update.
+struct StackJob {            // 72 bytes
+  const float* src; float* dst; int n; int time_idx; float R[9]; float dx, dy; int pad;
+};
+static_assert(sizeof(StackJob) == 72, "StackJob layout is part of the ABI (lav_b200.h)");
+
+__global__ void __launch_bounds__(256) stack_jobs_kernel(const StackJob* __restrict__ jobs, int src_cols, int n_time,
+                                                         int roof_filter) {
+  const StackJob j = jobs[blockIdx.y];
+  const int dcols = src_cols + n_time;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.n; i += gridDim.x * blockDim.x) {
+    const float* s = j.src + (size_t)i * src_cols;
+    float* d = j.dst + (size_t)i * dcols;
+    const float x = __ldg(s), y = __ldg(s + 1), z = __ldg(s + 2);
+    float nx = __fmaf_rn(z, j.R[6], __fmaf_rn(y, j.R[3], __fmul_rn(x, j.R[0])));
+    float ny = __fmaf_rn(z, j.R[7], __fmaf_rn(y, j.R[4], __fmul_rn(x, j.R[1])));
+    const float nz = __fmaf_rn(z, j.R[8], __fmaf_rn(y, j.R[5], __fmul_rn(x, j.R[2])));
+    nx = __fadd_rn(nx, j.dx);
+    ny = __fadd_rn(ny, j.dy);
+    if (roof_filter && x > -2.4f && x < 0.f && y > -0.8f && y < 0.8f && z > -1.5f && z < -1.f) nx = __int_as_float(0x7fc00000);
+    d[0] = nx; d[1] = ny; d[2] = nz;
+    for (int k = 3; k < src_cols; ++k) d[k] = __ldg(s + k);
+    for (int k = 0; k < n_time; ++k) d[src_cols + k] = (k == j.time_idx) ? 1.f : 0.f;
+  }
+}
+
+extern "C" int lavb_stack_jobs(const void* d_jobs, int n_jobs, int max_n, int src_cols, int n_time, int roof_filter, void* stream) {
+  LAVB_CHECK_ARG(n_jobs >= 0 && n_jobs <= 65535 && src_cols >= 3 && n_time >= 0, "stack_jobs: bad arguments");
+  if (n_jobs == 0 || max_n == 0) return 0;
+  dim3 grid(min(ceil_div(max_n, 256), 64), n_jobs);
+  stack_jobs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const StackJob*>(d_jobs), src_cols, n_time, roof_filter);
   LAVB_LAUNCH_OK();
   return 0;
 }

@@ -74,9 +74,9 @@ def transform_points(locs, oris):
 
 def crop_theta(rel_locs, rel_oris, H, W, pixels_per_meter, crop_size, offset_x, offset_y):
     """affine theta (K,2,3) of UniPlanner.crop_feature (team_code_v2/models/uniplanner.py:303-333)."""
-    rel_locs = rel_locs.view(-1, 2) * pixels_per_meter / torch.tensor([H / 2, W / 2]).type_as(rel_locs).to(rel_locs.device)
+    rel_locs = rel_locs.view(-1, 2) * pixels_per_meter        # then / [H/2, W/2] per column (no host tensor: graph-capturable)
     cos, sin = torch.cos(rel_oris), torch.sin(rel_oris)
-    rel_x, rel_y = rel_locs[..., 0], rel_locs[..., 1]
+    rel_x, rel_y = rel_locs[..., 0] / (H / 2), rel_locs[..., 1] / (W / 2)
     k = crop_size / H
     rot_x_offset = -k * offset_x * cos + k * offset_y * sin + offset_x
     rot_y_offset = -k * offset_x * sin - k * offset_y * cos + offset_y
@@ -200,15 +200,25 @@ class UniPlanner(nn.Module):
         all_locs = torch.tensor(locs + [[0.0, 0.0]] * B, dtype=torch.float32).view(-1, 2).to(dev)
         all_oris = torch.tensor(oris + [0.0] * B, dtype=torch.float32).to(dev)
         all_fidx = torch.tensor(fidx + list(range(B)), dtype=torch.int32).to(dev)
+        cmds = torch.as_tensor(cmds, device=dev).long()
+        ee, epl, ecl, o_cast, o_cmds = self.infer_device(features, all_locs, all_oris, all_fidx, K, nxps.to(dev).float(), cmds)
+        return ee, epl, ecl, torch.split(o_cast, counts), torch.split(o_cmds, counts)
+
+    @torch.no_grad()
+    def infer_device(self, features, all_locs, all_oris, all_fidx, K, nxps, cmds):
+        """Device-only part of infer (capturable in a CUDA graph): rows [0,K) of all_* are detected vehicles, rows
+        [K,K+B) the egos.  Returns (ego_embd, ego_plan_locs (B,T,2), ego_cast_locs (B,T,2), other_cast_locs (K,6,T,2),
+        other_cast_cmds (K,6))."""
+        B = features.size(0)
+        dev = features.device
         crops = self.crop_feature(features, all_locs, all_oris, pixels_per_meter=self.pixels_per_meter / 2,
                                   crop_size=self.crop_size, frame_idx=all_fidx)
         embd = self.lidar_conv_emb(crops.to(self.lidar_conv_emb[0].conv1.weight.dtype)).float()
         cast = self.cast(embd)
         ego_embd, ego_cast = embd[K:], cast[K:]
-        ego_plan = self.plan(ego_embd, nxps.to(dev).float(), cast_locs=ego_cast, pixels_per_meter=self.pixels_per_meter,
+        ego_plan = self.plan(ego_embd, nxps, cast_locs=ego_cast, pixels_per_meter=self.pixels_per_meter,
                              crop_size=self.crop_size * 2)[:, -1]
         ar = torch.arange(B, device=dev)
-        cmds = torch.as_tensor(cmds, device=dev).long()
         ego_plan_locs, ego_cast_locs = ego_plan[ar, cmds], ego_cast[ar, cmds]
         if K > 0:
             o_cast = transform_points(cast[:K], all_oris[:K, None].repeat(1, self.num_cmds)) + all_locs[:K].view(K, 1, 1, 2)
@@ -216,7 +226,7 @@ class UniPlanner(nn.Module):
         else:
             o_cast = torch.zeros((0, self.num_cmds, self.num_plan, 2), device=dev)
             o_cmds = torch.zeros((0, self.num_cmds), device=dev)
-        return ego_embd, ego_plan_locs, ego_cast_locs, torch.split(o_cast, counts), torch.split(o_cmds, counts)
+        return ego_embd, ego_plan_locs, ego_cast_locs, o_cast, o_cmds
 
     @torch.no_grad()
     def infer(self, features, det, cmd, nxp):

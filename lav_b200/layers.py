@@ -10,6 +10,7 @@ import torch
 from . import ops
 
 USE_UMMA = True   # tests flip this to compare the tcgen05 path with the CUDA-core path
+UMMA_STRIDED = True   # stride-2 convs through the tensor map's element strides
 
 
 def bn_affine(bn, eps=None):
@@ -106,7 +107,7 @@ class TapConv:
             ooy, oox = ph["out_o"]
             hog, wog = (hout - ooy + osy - 1) // osy, (wout - oox + osx - 1) // osx
             umma = (self.umma_ok and x.dtype == torch.bfloat16 and (res is None or res.dtype == torch.bfloat16)
-                    and ph["in_s"] == (1, 1))
+                    and (UMMA_STRIDED or ph["in_s"] == (1, 1)))
             ops.conv_taps(x, self.cin_k, in_coff, out, self.cout, out_coff, hog, wog, ph["in_s"], ph["out_s"], ph["out_o"],
                           ph["taps"], ph["w_umma"] if umma else ph["w"], self.bias, self.scale, self.shift, res, res_coff,
                           self.pre_relu, self.post_relu, self.sigmoid, umma=umma)

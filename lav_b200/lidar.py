@@ -56,6 +56,13 @@ class ConvBackbone(PlanMixin, nn.Module):
         for name in ("upconv1", "upconv2", "upconv3"):
             seq = getattr(self, name)
             plan[name] = crb(seq[0], seq[2])
+        if self.precision == "bf16":
+            # first layer on tensor cores WITHOUT rounding the fp32 canvas to bf16: input = [hi | lo] split (2*cin channels),
+            # weights duplicated along cin, so conv(x_hi) + conv(x_lo) accumulate in TMEM (costs 1.9 extra GFLOP / frame)
+            c0, b0 = self.conv1[0], self.conv1[2]
+            s, t = bn_affine(b0)
+            plan["conv1_split"] = TapConv(torch.cat([c0.weight, c0.weight], 1), False, c0.stride, c0.padding, c0.dilation, 0, None,
+                                          pre_relu=True, scale=s, shift=t)
         return plan
 
     def forward_nhwc(self, x):
@@ -64,10 +71,14 @@ class ConvBackbone(PlanMixin, nn.Module):
             raise LavbError("ConvBackbone: training-mode forward goes through lav_b200.train (autograd path)")
         plan = self._plan_get(x.device, self._build)
         dt = _DT[self.precision]
+        first = None
+        if dt == torch.bfloat16 and x.dtype == torch.float32:
+            from . import ops
+            first = plan["conv1_split"](ops.split_bf16(x), out_dtype=dt)
         xs = []
         for name in ("conv1", "conv2", "conv3"):
-            for layer in plan[name]:
-                x = layer(x, out_dtype=dt)
+            for li, layer in enumerate(plan[name]):
+                x = first if (name == "conv1" and li == 0 and first is not None) else layer(x, out_dtype=dt)
             xs.append(x)
         n, h, w, _ = xs[0].shape
         ctot = plan["upconv1"].cout + plan["upconv2"].cout + plan["upconv3"].cout
@@ -154,14 +165,25 @@ class LiDARModel(PlanMixin, nn.Module):
             ss.append(s)
             ts.append(t)
         conv = TapConv(torch.cat(ws, 0), False, 1, 1, pre_relu=True, scale=torch.cat(ss), shift=torch.cat(ts))
-        ups = [TapConv(h.net[3].weight, True, 2, 1, 1, 1, bias=h.net[3].bias, sigmoid=h._is_sigmoid()) for h in self._heads()]
-        return conv, ups
+        # the four ConvTranspose2d(64 -> 2/2/2/3, k3 s2 p1 op1) output layers as ONE grouped kernel (deconv_small.cu)
+        nh = self.center_head.net[0].out_channels
+        wd = torch.zeros((4, nh, 9, 4), dtype=torch.float32, device=device)
+        bd = torch.zeros((4, 4), dtype=torch.float32, device=device)
+        n_outs = []
+        for g, h in enumerate(self._heads()):
+            ct = h.net[3]
+            assert ct.kernel_size == (3, 3) and ct.stride == (2, 2) and ct.padding == (1, 1) and ct.output_padding == (1, 1)
+            no = ct.out_channels
+            wd[g, :, :, :no] = ct.weight.detach().float().permute(0, 2, 3, 1).reshape(nh, 9, no)   # (cin,cout,ky,kx)->(cin,tap,cout)
+            bd[g, :no] = ct.bias.detach().float()
+            n_outs.append(no)
+        return conv, (wd.contiguous(), bd.contiguous(), n_outs, [h._is_sigmoid() for h in self._heads()], nh)
 
     def heads_nhwc(self, feats):
-        conv, ups = self._plan_get(feats.device, self._build)
-        hid = conv(feats, out_dtype=_DT[self.precision])
-        nh = self.center_head.net[0].out_channels
-        return [up(hid, in_coff=i * nh, out_dtype=torch.float32) for i, up in enumerate(ups)]
+        from . import ops
+        conv, (wd, bd, n_outs, sig, nh) = self._plan_get(feats.device, self._build)
+        hid = conv(feats, out_dtype=torch.float32)      # fp32 hidden map: one bf16 rounding less before the output layer
+        return ops.deconv3x3s2_small(hid, 4, nh, wd, bd, n_outs, sig)
 
     def forward_nhwc(self, lidars, num_points):
         canvas = self.point_pillar_net(lidars, num_points).permute(0, 2, 3, 1)   # NHWC view of the canvas

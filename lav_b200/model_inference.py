@@ -50,9 +50,10 @@ class InferModel(nn.Module):
         return PP.point_painting(lidar, sems, self.coord_converters)
 
     # ---- detection decode ----------------------------------------------------------------------------
-    def det_inference_batch(self, heatmaps, sizemaps, orimaps, min_score=0.2):
-        """heatmaps (B,2,H,W) already sigmoided; sizemaps/orimaps (B,2,H,W).  Same filters as
-        det_inference (model_inference.py:95-121); one D2H copy for the whole batch."""
+    @staticmethod
+    def pack_peaks(heatmaps, sizemaps, orimaps):
+        """device part of the decode: top-15 NMS peaks per class with the size/orientation values at the peaks,
+        packed as (B, 6, ncls*15) = score | flat index | w | h | cos | sin.  Capturable in a CUDA graph."""
         B, ncls, H, W = heatmaps.shape
         score, loc = extract_peak_batch(heatmaps.reshape(B * ncls, H, W).float())
         score, loc = score.view(B, ncls, -1), loc.view(B, ncls, -1)
@@ -60,8 +61,18 @@ class InferModel(nn.Module):
         sz, ori = flat(sizemaps), flat(orimaps)
         idx = loc.reshape(B, 1, -1).expand(B, 2, -1)                      # (B,2,ncls*max_det)
         packed = torch.cat([score.reshape(B, 1, -1), loc.reshape(B, 1, -1).float(), sz.gather(2, idx), ori.gather(2, idx)], 1)
-        packed = packed.cpu().numpy().astype(np.float64)                  # (B,6,ncls*max_det)
-        nd = score.shape[2]
+        return torch.cat([packed, packed.new_full((B, 1, packed.shape[2]), float(W))], 1)     # row 6 carries W
+
+    def det_inference_batch(self, heatmaps, sizemaps, orimaps, min_score=0.2):
+        """heatmaps (B,2,H,W) already sigmoided; sizemaps/orimaps (B,2,H,W).  Same filters as
+        det_inference (model_inference.py:95-121); one D2H copy for the whole batch."""
+        return self.decode_packed(self.pack_peaks(heatmaps, sizemaps, orimaps), heatmaps.shape[1], min_score)
+
+    def decode_packed(self, packed, ncls=2, min_score=0.2):
+        packed = packed.cpu().numpy().astype(np.float64)                  # the ONE device->host copy of the decode
+        B = packed.shape[0]
+        W = int(packed[0, 6, 0]) if B else 0
+        nd = packed.shape[2] // ncls
         out = []
         for b in range(B):
             dets = []

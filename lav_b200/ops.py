@@ -263,3 +263,56 @@ def crop_bilinear(feats_nhwc, frame_idx, theta, crop_size):
                                    _ptr(out), _stream()), "lavb_crop_bilinear")
     _COUNT[0] += 1
     return out
+
+
+def deconv3x3s2_small(x, groups, cin_g, w, bias, n_outs, sigmoids):
+    """x NHWC (N,H,W,Ctot); w fp32 (G,cin_g,9,4); bias (G,4) -> list of fp32 NHWC (N,2H,2W,n_out[g])."""
+    _need_cuda(x, w, bias)
+    assert x.is_contiguous() and w.is_contiguous() and bias.is_contiguous()
+    n, h, wd, cs = x.shape
+    outs = [torch.empty((n, 2 * h, 2 * wd, no), dtype=torch.float32, device=x.device) for no in n_outs]
+    ptrs = (C.c_void_p * groups)(*[o.data_ptr() for o in outs])
+    no = (C.c_int * groups)(*n_outs)
+    sg = (C.c_int * groups)(*[int(s) for s in sigmoids])
+    check(lib().lavb_deconv3x3s2_small(_ptr(x), _DT[x.dtype], n, h, wd, cs, groups, cin_g, _ptr(w), _ptr(bias), no, sg, ptrs,
+                                       _stream()), "lavb_deconv3x3s2_small")
+    _COUNT[0] += 1
+    return outs
+
+
+def paint_batched(points, sem, cams, mode, copy_cols, out):
+    """points (F,N,>=3) fp32 contiguous; sem logical (F,ncam,C,H,W) any strides; out (F,N,copy_cols+c_out) contiguous."""
+    _need_cuda(points, sem, out)
+    assert points.is_contiguous() and out.is_contiguous() and points.dtype == torch.float32 and sem.dtype == torch.float32
+    f, n, ps = points.shape
+    _, ncam, c_in, h, w = sem.shape
+    cams = np.ascontiguousarray(cams, dtype=np.float32)
+    s = sem.stride()
+    check(lib().lavb_paint_batched(_ptr(points), f, n, ps, n * ps, _ptr(sem), ncam, c_in, h, w, s[0], s[1], s[2], s[3], s[4],
+                                   cams.ctypes.data_as(C.c_void_p), mode, _ptr(out), out.shape[2], n * out.shape[2], copy_cols,
+                                   copy_cols, _stream()), "lavb_paint_batched")
+    _COUNT[0] += 1
+    return out
+
+
+STACK_JOB_DTYPE = np.dtype([("src", np.uint64), ("dst", np.uint64), ("n", np.int32), ("time_idx", np.int32), ("R", np.float32, 9),
+                            ("dx", np.float32), ("dy", np.float32), ("pad", np.int32)])
+assert STACK_JOB_DTYPE.itemsize == 72
+
+
+def stack_jobs(d_jobs, n_jobs, max_n, src_cols, n_time, roof_filter=False):
+    """d_jobs: uint8 device tensor holding n_jobs STACK_JOB_DTYPE records."""
+    _need_cuda(d_jobs)
+    check(lib().lavb_stack_jobs(_ptr(d_jobs), n_jobs, max_n, src_cols, n_time, int(roof_filter), _stream()), "lavb_stack_jobs")
+    _COUNT[0] += 1
+
+
+def split_bf16(x):
+    """fp32 (..., C) contiguous -> bf16 (..., 2C) = [hi | lo] error-free split (see lavb_split_bf16)."""
+    _need_cuda(x)
+    assert x.is_contiguous() and x.dtype == torch.float32
+    c = x.shape[-1]
+    out = torch.empty((*x.shape[:-1], 2 * c), dtype=torch.bfloat16, device=x.device)
+    check(lib().lavb_split_bf16(_ptr(x), _ptr(out), x.numel() // c, c, _stream()), "lavb_split_bf16")
+    _COUNT[0] += 1
+    return out

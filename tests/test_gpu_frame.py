@@ -141,3 +141,46 @@ def test_frame_pipeline_bf16_close_to_oracle(cuda):
     sc = float(want["plan"][1].abs().max()) + 1
     assert float((out["ego_plan_locs"][0].float().cpu() - want["plan"][1]).abs().max()) < 5e-2 * sc
     assert abs(float(out["pred_bra"][0]) - float(want["bra"][0])) < 2e-2
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_static_pipeline_matches_dynamic(cuda, graphs):
+    """The fixed-shape / CUDA-graph pipeline (batched paint, table-driven stack, ring-buffer FIFO) must reproduce the
+    dynamic FramePipeline tick by tick, including ticks where older sweeps do not exist yet."""
+    from lav_b200.agent import FramePipeline, SweepHistory, StaticFramePipeline
+    from lav_b200.heads import RGBBrakePredictionModel
+    lm, _ = util.lidar_model()
+    sm, _ = util.seg_model()
+    up, _ = uniplanner()
+    bra = RGBBrakePredictionModel([4, 6, 7, 10]).eval()
+    bra.load_state_dict(synth.fill_state_dict_(bra.state_dict()))
+    dyn = FramePipeline(sm, lm, up, bra, device=cuda, precision="fp32")
+    B, N = 2, 5000
+    st = StaticFramePipeline(sm, lm, up, bra, B, N, device=cuda, precision="fp32", use_graphs=graphs)
+    hist = [SweepHistory() for _ in range(B)]
+    nxps = torch.tensor([[0.0, -20.0], [3.0, -15.0]])
+    for tick in range(12):
+        rgbs = torch.stack([synth.rgb_frames(tag=f"s{tick}{b}", smooth=True) for b in range(B)])
+        tels = torch.stack([synth.rgb_frames(tag=f"st{tick}{b}", smooth=True, n_cam=1, h=192, w=480)[0] for b in range(B)])
+        lidars = [synth.lidar_sweep(N - 100 * b, tag=f"sl{tick}{b}") for b in range(B)]       # agent 1 has a shorter sweep
+        poses = [(np.array([0.3 * tick, 0.1 * b]), 0.02 * tick) for b in range(B)]
+        heavy = tick in (0, 4, 5, 10, 11)     # compare on the ticks where the set of stacked sweeps changes
+        o_s = st.step(rgbs.to(cuda), tels.to(cuda), [l.to(cuda) for l in lidars], nxps, [3, 1], poses=poses, fixed_dets=DETS)
+        if not heavy:
+            for b in range(B):   # keep the dynamic FIFO in step without running its networks
+                hist[b].push(st.cur[b, :lidars[b].shape[0]].clone(), poses[b][0], poses[b][1])
+            continue
+        im = dyn.infer_model
+        orig = im.det_inference_batch
+        im.det_inference_batch = lambda *a, **k: [[d[0], list(DETS)] for d in orig(*a, **k)]
+        o_d = dyn.step(rgbs.to(cuda), tels.to(cuda), [l.to(cuda) for l in lidars], hist, nxps.to(cuda), [3, 1], poses=poses)
+        im.det_inference_batch = orig
+        for b in range(B):
+            n = lidars[b].shape[0]
+            assert torch.equal(st.cur[b, :n].cpu(), hist[b].lidars[-1].cpu()), tick
+            assert util.rel_err(o_s["pred_bev"][b], o_d["pred_bev"][b]) < 1e-4, tick
+            sc = float(o_d["ego_plan_locs"][b].abs().max()) + 1
+            assert float((o_s["ego_plan_locs"][b] - o_d["ego_plan_locs"][b]).abs().max()) < 1e-3 * sc, tick
+            assert float((o_s["other_cast_locs"][b] - o_d["other_cast_locs"][b]).abs().max()) < 1e-3 * sc, tick
+            assert abs(float(o_s["pred_bra"][b]) - float(o_d["pred_bra"][b])) < 1e-4
+            assert [[d[:2] for d in c] for c in o_s["det"][b]] == [[d[:2] for d in c] for c in o_d["det"][b]]

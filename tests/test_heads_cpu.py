@@ -65,7 +65,7 @@ def test_det_decode_matches_reference_golden(golden_dir):
     sizem = torch.rand(2, 320, 320, generator=gb) * 3
     orim = torch.randn(2, 320, 320, generator=gb)
     stub = type("S", (), {"pixels_per_meter": 4})()
-    dets = InferModel.det_inference_batch(stub, torch.sigmoid(heat)[None], sizem[None], orim[None])[0]
+    dets = InferModel.decode_packed(stub, InferModel.pack_peaks(torch.sigmoid(heat)[None], sizem[None], orim[None]))[0]
     want = O.det_inference(torch.sigmoid(heat), sizem, orim)
     assert dets == want
     np.testing.assert_allclose(np.array(dets[0]).reshape(-1, 6), gold["det0"], rtol=0, atol=0)
