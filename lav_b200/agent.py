@@ -153,28 +153,38 @@ class StaticFramePipeline(FramePipeline):
 
     # ---- host-side state ------------------------------------------------------------------------------------
     def _fill_jobs(self, poses):
-        jobs = self.jobs_host.numpy().view(ops.STACK_JOB_DTYPE)
-        B, T, N = self.B, self.T, self.N
-        s0 = self.tick % self.KEEP
+        """rewrite the (agent, sweep) job table for this tick — vectorised numpy, then one small H2D copy."""
+        B, T, N, KEEP = self.B, self.T, self.N, self.KEEP
+        jobs = self.jobs_host.numpy().view(ops.STACK_JOB_DTYPE).reshape(B, T)
+        s0 = self.tick % KEEP
+        if poses is not None:
+            self.ring_pose[:, s0, :2] = np.asarray([p[0] for p in poses], dtype=np.float64)
+            self.ring_pose[:, s0, 2] = np.asarray([p[1] for p in poses], dtype=np.float64)
+        else:
+            self.ring_pose[:, s0] = 0
+        self.ring_valid[:, s0] = True
+        ticks = self.tick - np.arange(T) * GAP                                   # (T,)
+        slots = ticks % KEEP
+        pose = self.ring_pose[:, slots]                                           # (B,T,3)
+        valid = (ticks >= 0)[None] & self.ring_valid[:, slots]
+        loc0, ori0 = pose[:, :1, :2], pose[:, :1, 2]
+        d = pose[..., 2] - ori0                                                   # (B,T)
+        c0, si0 = np.cos(ori0), np.sin(ori0)
+        dl = pose[..., :2] - loc0
+        R = np.zeros((B, T, 9), dtype=np.float32)
+        R[..., 0], R[..., 1], R[..., 3], R[..., 4], R[..., 8] = np.cos(d), np.sin(d), -np.sin(d), np.cos(d), 1.0
+        jobs["R"] = R
+        jobs["dx"] = dl[..., 0] * c0 + dl[..., 1] * si0                           # dloc @ [[c,-s],[s,c]]
+        jobs["dy"] = -dl[..., 0] * si0 + dl[..., 1] * c0
+        jobs["n"] = np.where(valid, N, 0)
+        jobs["time_idx"] = np.arange(T)[None]
         row_bytes = 4 * (8 + T)
-        for b in range(B):
-            loc0, ori0 = (np.asarray(poses[b][0], dtype=np.float64), float(poses[b][1])) if poses is not None else (np.zeros(2), 0.0)
-            self.ring_pose[b, s0] = (loc0[0], loc0[1], ori0)
-            self.ring_valid[b, s0] = True
-            c0, si0 = math.cos(ori0), math.sin(ori0)
-            for i in range(T):
-                slot = (self.tick - i * GAP) % self.KEEP
-                j = jobs[b * T + i]
-                valid = self.tick - i * GAP >= 0 and self.ring_valid[b, slot]
-                j["src"] = self.cur[b].data_ptr() if i == 0 else self.ring[b, slot].data_ptr()
-                j["dst"] = self.stacked[b].data_ptr() + i * N * row_bytes
-                j["n"] = N if valid else 0
-                j["time_idx"] = i
-                lx, ly, ori = self.ring_pose[b, slot]
-                d = ori - ori0
-                j["R"] = np.array([math.cos(d), math.sin(d), 0, -math.sin(d), math.cos(d), 0, 0, 0, 1], dtype=np.float32)
-                dl = (np.array([lx, ly]) - loc0) @ np.array([[c0, -si0], [si0, c0]])
-                j["dx"], j["dy"] = dl[0], dl[1]
+        ring_b, ring_s = self.ring.stride(0) * 4, self.ring.stride(1) * 4
+        src = self.ring.data_ptr() + np.arange(B, dtype=np.uint64)[:, None] * np.uint64(ring_b) + slots.astype(np.uint64)[None] * np.uint64(ring_s)
+        src[:, 0] = self.cur.data_ptr() + np.arange(B, dtype=np.uint64) * np.uint64(self.cur.stride(0) * 4)
+        jobs["src"] = src
+        jobs["dst"] = (self.stacked.data_ptr() + np.arange(B, dtype=np.uint64)[:, None] * np.uint64(self.stacked.stride(0) * 4)
+                       + np.arange(T, dtype=np.uint64)[None] * np.uint64(N * row_bytes))
         self.jobs_dev.copy_(self.jobs_host, non_blocking=True)
 
     def preload_history(self, b, sweeps):

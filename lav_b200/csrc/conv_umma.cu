@@ -8,10 +8,11 @@
 // (128 rows x 128 B).  Strided convs use the tensor map's element strides; a transposed conv is issued per output
 // phase with its own tap list (same host packing as conv_taps.cu).
 //
-// Warp roles (192 threads, 1 CTA/SM, persistent over tiles):
+// Warp roles (320 threads, 1 CTA/SM, persistent over tiles):
 //   warp 0   : TMA producer (one lane)      — smem ring of `stages` {A 16 KB, B cout*128 B}
 //   warp 1   : TMEM allocator + MMA issuer  — 4 x tcgen05.mma (M128,N=cout,K16) per K-block, commit -> empty barrier
-//   warps 2-5: epilogue                     — tcgen05.ld 32x32b.x32, bias/ReLU/BN-affine/residual, 16 B global stores
+//   warps 2-9: epilogue (2 per TMEM lane quarter, alternating 32-column chunks) — tcgen05.ld 32x32b.x32,
+//              max/FMA with (scale,shift) pairs broadcast from smem, residual, 16 B global stores; flag-free inner loop
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -98,9 +99,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                                                           const __grid_constant__ CUtensorMap tmap_b,
-                                                           const __grid_constant__ UmmaArgs p) {
+// kEpiWarps = 8: two warps per TMEM lane quarter (they split the column chunks), one CTA per SM — wide layers (cout > 128).
+// kEpiWarps = 4: one warp per quarter and TWO co-resident CTAs per SM (half the smem ring each): two independent tile
+//                pipelines hide the per-tile serial chain (commit -> epilogue -> tmem_empty) of the narrow layers.
+template <bool kOutF32, bool kRes, bool kSigmoid, bool kPreBias, int kEpiWarps>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : 1) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                const __grid_constant__ CUtensorMap tmap_b,
+                                                                const __grid_constant__ UmmaArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B operands need 1024 B alignment
   const int b_bytes = p.cout * kBlockK * 2;
@@ -110,9 +115,8 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
                  tempty_bar = tfull_bar + 16, tmem_slot = tempty_bar + 16;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
-  float* ep_bias = reinterpret_cast<float*>(gen + (tmem_slot - base) + 16);
-  float* ep_scale = ep_bias + 256;
-  float* ep_shift = ep_scale + 256;
+  float* ep_bias = reinterpret_cast<float*>(gen + (tmem_slot - base) + 16);   // only read when kPreBias
+  float* ep_st = ep_bias + 256;                                               // interleaved (scale, shift) per channel
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -128,9 +132,13 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int c = threadIdx.x; c < p.cout; c += blockDim.x) {
-    ep_bias[c] = p.bias ? __ldg(p.bias + c) : 0.f;
-    ep_scale[c] = p.scale ? __ldg(p.scale + c) : 1.f;
-    ep_shift[c] = p.shift ? __ldg(p.shift + c) : 0.f;
+    // epi(a) = max(a + b, lo) * s + t.  Without the pre-ReLU the bias folds into the shift: (a + b) s + t = a s + (b s + t)
+    const float b = p.bias ? __ldg(p.bias + c) : 0.f;
+    const float sc = p.scale ? __ldg(p.scale + c) : 1.f;
+    const float sh = p.shift ? __ldg(p.shift + c) : 0.f;
+    ep_bias[c] = b;
+    ep_st[2 * c] = sc;
+    ep_st[2 * c + 1] = kPreBias ? sh : fmaf(b, sc, sh);
   }
   tc_fence_before();
   __syncthreads();
@@ -183,9 +191,12 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
       }
     }
   } else {
-    const int q = warp & 3;                        // TMEM lane quarter this warp may read
+    const int q = warp & 3;                        // TMEM lane quarter this warp may read (warp id % 4)
+    const int half = (warp - 2) >> 2;              // with 8 warps the two warps of a quarter take alternate 32-column chunks
+    constexpr int kChunkStride = 32 * (kEpiWarps / 4);
     const int row = q * 32 + lane;
     const int py = row / kTileW, px = row % kTileW;
+    const float lo_pre = p.pre_relu ? 0.f : -INFINITY, lo_post = p.post_relu ? 0.f : -INFINITY;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
@@ -195,18 +206,21 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
       const long long pix = ((long long)img * p.hout + oy) * p.wout + ox;
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
-      for (int c0 = 0; c0 < p.cout; c0 += 32) {
+      for (int c0 = half * 32; c0 < p.cout; c0 += kChunkStride) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.cout + c0), v);
-        if (valid) {
-          float f[32];
+        float f[32];
+        const float4* st4 = reinterpret_cast<const float4*>(ep_st + 2 * c0);   // (s0,t0,s1,t1): broadcast LDS.128
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) + ep_bias[c0 + j];
-            if (p.pre_relu) x = fmaxf(x, 0.f);
-            f[j] = fmaf(x, ep_scale[c0 + j], ep_shift[c0 + j]);
-          }
-          if (p.res) {
+        for (int j = 0; j < 16; ++j) {
+          const float4 st = st4[j];
+          float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
+          if (kPreBias) { x0 += ep_bias[c0 + 2 * j]; x1 += ep_bias[c0 + 2 * j + 1]; }
+          f[2 * j] = fmaf(fmaxf(x0, lo_pre), st.x, st.y);
+          f[2 * j + 1] = fmaf(fmaxf(x1, lo_pre), st.z, st.w);
+        }
+        if (valid) {
+          if (kRes) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_cstride + p.res_coff + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -221,10 +235,10 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            if (p.post_relu) f[j] = fmaxf(f[j], 0.f);
-            if (p.sigmoid) f[j] = 1.f / (1.f + expf(-f[j]));
+            f[j] = fmaxf(f[j], lo_post);
+            if (kSigmoid) f[j] = 1.f / (1.f + expf(-f[j]));
           }
-          if (p.out_is_f32) {
+          if (kOutF32) {
             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_cstride + p.out_coff + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
@@ -316,7 +330,8 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   a.num_tiles = a.n * a.tiles_x * a.tiles_y;
   a.hout = d->hout; a.wout = d->wout; a.cin = d->cin; a.cout = d->cout; a.kchunks = d->cin / kBlockK; a.ntaps = d->ntaps;
   const int stage_bytes = kABytes + d->cout * kBlockK * 2;
-  a.stages = min(kMaxStages, (196 * 1024) / stage_bytes);
+  const bool two_per_sm = d->cout <= 128;            // narrow layers: 2 CTAs / SM, each with half the smem ring
+  a.stages = two_per_sm ? min(kMaxStages, (100 * 1024) / stage_bytes) : min(kMaxStages, (196 * 1024) / stage_bytes);
   int cols = 32;
   while (cols < 2 * d->cout) cols <<= 1;
   a.tmem_cols = cols;
@@ -329,15 +344,31 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   a.bias = d->bias; a.scale = d->scale; a.shift = d->shift;
   if (a.num_tiles == 0) return 0;
   const size_t smem = (size_t)a.stages * stage_bytes + 1024 /*align*/ + 16 * kMaxStages + 64 + 3 * 256 * sizeof(float);
-  {  // once per process (never during a later stream capture): opt in to the full 227 KB of dynamic shared memory
-    static bool configured = false;
-    if (!configured) {
-      LAVB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      configured = true;
-    }
+  const int grid = min(a.num_tiles, two_per_sm ? 2 * kNumSMs : kNumSMs);
+  const bool f32 = a.out_is_f32, res = a.res != nullptr, sig = a.sigmoid != 0, pb = a.pre_relu && a.bias != nullptr;
+  // epilogue variants are compiled separately so the inner loop carries no runtime flag tests
+#define LAVB_UMMA_LAUNCH(F, R, S, B, EW)                                                                                \
+  {                                                                                                                     \
+    static bool configured = false; /* once per process and variant, never during a later stream capture */            \
+    if (!configured) {                                                                                                  \
+      LAVB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<F, R, S, B, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        EW == 4 ? 112 * 1024 : 227 * 1024));                                            \
+      configured = true;                                                                                                \
+    }                                                                                                                   \
+    conv_umma_kernel<F, R, S, B, EW><<<grid, 64 + 32 * EW, smem, (cudaStream_t)stream>>>(tmap_a, tmap_b, a);            \
+    LAVB_LAUNCH_OK();                                                                                                   \
+    return 0;                                                                                                           \
   }
-  const int grid = min(a.num_tiles, kNumSMs);
-  conv_umma_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmap_a, tmap_b, a);
-  LAVB_LAUNCH_OK();
-  return 0;
+#define LAVB_UMMA_CASE(F, R, S, B)                                                                                      \
+  if (f32 == F && res == R && sig == S && pb == B) {                                                                    \
+    if (two_per_sm) LAVB_UMMA_LAUNCH(F, R, S, B, 4) else LAVB_UMMA_LAUNCH(F, R, S, B, 8)                                \
+  }
+  LAVB_UMMA_CASE(false, false, false, false) LAVB_UMMA_CASE(false, true, false, false)
+  LAVB_UMMA_CASE(true, false, false, false)  LAVB_UMMA_CASE(true, true, false, false)
+  LAVB_UMMA_CASE(false, false, true, false)  LAVB_UMMA_CASE(true, false, true, false)
+  LAVB_UMMA_CASE(false, false, false, true)  LAVB_UMMA_CASE(false, true, false, true)
+  LAVB_UMMA_CASE(true, false, false, true)   LAVB_UMMA_CASE(true, true, false, true)
+#undef LAVB_UMMA_CASE
+#undef LAVB_UMMA_LAUNCH
+  LAVB_CHECK_ARG(false, "conv_umma: this epilogue combination (sigmoid with residual / pre-ReLU bias) is not compiled");
 }

@@ -57,8 +57,59 @@ class ResNet18(nn.Module):
         self.fc = nn.Linear(512, num_classes)             # keys exist in the checkpoints, unused (resnet.py:235-247)
 
     def forward(self, x):
+        if not self.training and x.is_cuda and not torch.is_grad_enabled():
+            return self._forward_folded(x)
         x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
         return self.layer4(self.layer3(self.layer2(self.layer1(x))))
+
+    # ---- eval fast path: BatchNorm folded into the conv weights, conv+bias+ReLU and conv+bias+add+ReLU as single cuDNN
+    # fused ops (no separate BN / ReLU / add passes over the activations).  Folded weights are cached per (dtype, device).
+    def _folded(self, dtype, device):
+        key = (dtype, str(device))
+        cache = self.__dict__.setdefault("_fold_cache", {})
+        if key not in cache:
+            def fold(conv, bn):
+                s = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
+                w = (conv.weight.double() * s[:, None, None, None]).to(dtype).contiguous(memory_format=torch.channels_last)
+                b = (bn.bias.double() - bn.running_mean.double() * s).to(dtype)
+                return w, b
+            f = {"stem": fold(self.conv1, self.bn1)}
+            for li in range(1, 5):
+                for bi, blk in enumerate(getattr(self, f"layer{li}")):
+                    f[(li, bi, 1)] = fold(blk.conv1, blk.bn1)
+                    f[(li, bi, 2)] = fold(blk.conv2, blk.bn2)
+                    if blk.downsample is not None:
+                        f[(li, bi, "d")] = fold(blk.downsample[0], blk.downsample[1])
+            cache[key] = f
+        return cache[key]
+
+    def _forward_folded(self, x):
+        dt = self.conv1.weight.dtype
+        x = x.to(dt).contiguous(memory_format=torch.channels_last)
+        f = self._folded(dt, x.device)
+        w, b = f["stem"]
+        x = torch.cudnn_convolution_relu(x, w, b, (2, 2), (3, 3), (1, 1), 1)
+        x = self.maxpool(x)
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(self, f"layer{li}")):
+                st = blk.conv1.stride
+                w1, b1 = f[(li, bi, 1)]
+                w2, b2 = f[(li, bi, 2)]
+                idt = x
+                if blk.downsample is not None:
+                    wd, bd = f[(li, bi, "d")]
+                    idt = F.conv2d(x, wd, bd, blk.downsample[0].stride)
+                y = torch.cudnn_convolution_relu(x, w1, b1, st, (1, 1), (1, 1), 1)
+                x = torch.cudnn_convolution_add_relu(y, w2, idt, 1.0, b2, (1, 1), (1, 1), (1, 1), 1)
+        return x
+
+    def _apply(self, fn, *a, **k):
+        self.__dict__["_fold_cache"] = {}
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self.__dict__["_fold_cache"] = {}
+        return super().load_state_dict(*a, **k)
 
 
 def resnet18(pretrained=False, num_channels=3, **kw):

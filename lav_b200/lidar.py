@@ -90,6 +90,11 @@ class ConvBackbone(PlanMixin, nn.Module):
         return out
 
     def forward(self, x):
+        if self.training:    # autograd path: the module tree's own layers (cuDNN) — see lav_b200/train.py
+            x1 = self.conv1(x)
+            x2 = self.conv2(x1)
+            x3 = self.conv3(x2)
+            return torch.cat([self.upconv1(x1), self.upconv2(x2), self.upconv3(x3)], dim=1)
         return self.forward_nhwc(_nhwc(x)).permute(0, 3, 1, 2)
 
 
@@ -125,6 +130,9 @@ class Head(PlanMixin, nn.Module):
         return up(conv(x, out_dtype=_DT[self.precision]), out_dtype=torch.float32)
 
     def forward(self, x):
+        if self.training:
+            y = self.net(x)
+            return self.output_activation(y) if self.output_activation else y
         return self.forward_nhwc(_nhwc(x)).permute(0, 3, 1, 2)
 
 

@@ -69,29 +69,27 @@ class InferModel(nn.Module):
         return self.decode_packed(self.pack_peaks(heatmaps, sizemaps, orimaps), heatmaps.shape[1], min_score)
 
     def decode_packed(self, packed, ncls=2, min_score=0.2):
-        packed = packed.cpu().numpy().astype(np.float64)                  # the ONE device->host copy of the decode
+        """host part of det_inference (model_inference.py:98-121), vectorised over the batch: score threshold, the
+        class-1 size filter, the ego-distance window; survivors keep the reference's order (descending score)."""
+        packed = packed.cpu().numpy()                                     # the ONE device->host copy of the decode
         B = packed.shape[0]
-        W = int(packed[0, 6, 0]) if B else 0
+        if B == 0:
+            return []
+        W = int(packed[0, 6, 0])
         nd = packed.shape[2] // ncls
+        score, loc = packed[:, 0].astype(np.float64), packed[:, 1].astype(np.int64)
+        x, y = loc % W, loc // W
+        w, h = packed[:, 2], packed[:, 3]
+        cls = np.arange(packed.shape[2]) // nd
+        dist = np.sqrt(((x - 160) ** 2 + (y - 280) ** 2).astype(np.float64))     # TODO hard-code of the reference kept
+        keep = (score > min_score) & ~((cls[None] == 1) & (np.maximum(w, h) < 0.1 * self.pixels_per_meter))
+        keep &= ~((dist <= 2) | (dist >= 30 * self.pixels_per_meter))
         out = []
         for b in range(B):
-            dets = []
-            for i in range(ncls):
-                det = []
-                for j in range(i * nd, (i + 1) * nd):
-                    s = packed[b, 0, j]
-                    if not s > min_score:
-                        continue
-                    l = int(packed[b, 1, j])
-                    x, y = l % W, l // W
-                    w, h, cos, sin = (float(np.float32(packed[b, k, j])) for k in (2, 3, 4, 5))
-                    if i == 1 and max(w, h) < 0.1 * self.pixels_per_meter:
-                        continue
-                    dist = np.linalg.norm([x - 160, y - 280])            # TODO hard-code of the reference kept
-                    if dist <= 2 or dist >= 30 * self.pixels_per_meter:
-                        continue
-                    det.append((x, y, w, h, cos, sin))
-                dets.append(det)
+            dets = [[] for _ in range(ncls)]
+            for j in np.nonzero(keep[b])[0]:
+                dets[int(cls[j])].append((int(x[b, j]), int(y[b, j]), float(packed[b, 2, j]), float(packed[b, 3, j]),
+                                          float(packed[b, 4, j]), float(packed[b, 5, j])))
             out.append(dets)
         return out
 

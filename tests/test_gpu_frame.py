@@ -183,4 +183,4 @@ def test_static_pipeline_matches_dynamic(cuda, graphs):
             assert float((o_s["ego_plan_locs"][b] - o_d["ego_plan_locs"][b]).abs().max()) < 1e-3 * sc, tick
             assert float((o_s["other_cast_locs"][b] - o_d["other_cast_locs"][b]).abs().max()) < 1e-3 * sc, tick
             assert abs(float(o_s["pred_bra"][b]) - float(o_d["pred_bra"][b])) < 1e-4
-            assert [[d[:2] for d in c] for c in o_s["det"][b]] == [[d[:2] for d in c] for c in o_d["det"][b]]
+            assert [d[:2] for d in o_s["det"][b][0]] == [d[:2] for d in o_d["det"][b][0]]     # class 1 was overridden with DETS
