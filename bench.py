@@ -146,10 +146,10 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def workload_config(B, precision):
+def workload_config(B, precision, P=1):
     return {"workload": "LAV agent frame forward: 3xRGB 288x256 -> ERFNet -> paint 40k-pt sweep -> stack 3 sweeps (120k pts) -> "
                         "PointPillars -> BEV backbone + 4 heads -> det decode -> UniPlanner (ego + 3 vehicles) -> brake model",
-            "frames_per_step_per_gpu": B, "precision": precision, "weights": "seeded random init (released .th files are LFS pointers)",
+            "frames_per_step_per_gpu": B, "agent_groups_per_gpu": P, "precision": precision, "weights": "seeded random init (released .th files are LFS pointers)",
             "planner_detections": "decode runs on the predicted maps; planner is fed a fixed K=3 list (SURVEY 8d)",
             "l2": "per-step working set (B x 26 MB canvas + B x 39 MB features + ...) exceeds the 126 MB L2; inputs rotate over 2 sets",
             "parallelism": "replicas (one process per GPU, no data-path collective)",
@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--pipelines", type=int, default=2, help="agent groups per GPU that overlap host decode with GPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="run the static pipeline eagerly (debug / ncu launch lists)")
     args = ap.parse_args()
@@ -198,26 +199,39 @@ def main():
     B = args.batch
     N = synth.SWEEP_POINTS
     (seg, lid, uni, bra), sds = build_models()
-    pipe = StaticFramePipeline(seg, lid, uni, bra, B, N, device=dev, precision=args.precision, use_graphs=not args.no_graphs)
+    P = max(1, min(args.pipelines, B))
+    assert B % P == 0, "--batch must be a multiple of --pipelines"
+    Bp = B // P
+    pipes = [StaticFramePipeline(seg, lid, uni, bra, Bp, N, device=dev, precision=args.precision, use_graphs=not args.no_graphs)
+             for _ in range(P)]
+    pipe = pipes[0]
     rgbs, tels, lidars, prev, poses = synth_frames(B, rank)
     lid_t = torch.stack(lidars)
     h_rgbs, h_tels, h_lidar = rgbs.pin_memory(), tels.pin_memory(), lid_t.pin_memory()
     d_sets = [(rgbs.to(dev), tels.to(dev), lid_t.to(dev)) for _ in range(2)]
     nxps = torch.tensor([[0.0, -20.0]] * B).pin_memory()
     cmds = torch.tensor([3] * B).pin_memory()
-    pipe.tick = 10
-    for b in range(B):     # ticks t-1..t-10 of the FIFO: slots t-5 / t-10 hold painted sweeps
-        loc, ori = poses[b]
-        pipe.preload_history(b, [(prev[b][k % 2].to(dev), loc[1 + (k % 2)], ori[1 + (k % 2)]) for k in range(10)])
+    for pi, pp in enumerate(pipes):
+        pp.tick = 10
+        for b in range(Bp):     # ticks t-1..t-10 of the FIFO: slots t-5 / t-10 hold painted sweeps
+            loc, ori = poses[pi * Bp + b]
+            pp.preload_history(b, [(prev[pi * Bp + b][k % 2].to(dev), loc[1 + (k % 2)], ori[1 + (k % 2)]) for k in range(10)])
     step_poses = [(poses[b][0][0], poses[b][1][0]) for b in range(B)]
+    sl = [slice(pi * Bp, (pi + 1) * Bp) for pi in range(P)]
+
+    def run(r, t, l):
+        # software pipeline over the P agent groups: all G1 graphs are queued first, then each group's detections are
+        # decoded on the host while the other groups' GPU work is still running
+        for pi, pp in enumerate(pipes):
+            pp.begin(r[sl[pi]], t[sl[pi]], l[sl[pi]], nxps[sl[pi]], cmds[sl[pi]], poses=step_poses[sl[pi]])
+        return [pp.finish(fixed_dets=FIXED_DETS) for pp in pipes]
 
     def step_resident(i):
-        r, t, l = d_sets[i % 2]
-        return pipe.step(r, t, l, nxps, cmds, poses=step_poses, fixed_dets=FIXED_DETS)
+        return run(*d_sets[i % 2])
 
     def step_e2e(i):
-        o = pipe.step(h_rgbs, h_tels, h_lidar, nxps, cmds, poses=step_poses, fixed_dets=FIXED_DETS)
-        return o["ego_plan_locs"].float().cpu(), o["pred_bra"].float().cpu()
+        outs = run(h_rgbs, h_tels, h_lidar)
+        return [(o["ego_plan_locs"].float().cpu(), o["pred_bra"].float().cpu()) for o in outs]
 
     def timed(fn, steps, warmup):
         for i in range(warmup):
@@ -249,7 +263,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     ms, t0, t1 = timed(step_resident, args.steps, args.warmup)
     # lav_b200 kernels per step = those recorded in the two graphs (replays do not pass through ops.py) + the FIFO copy
-    launches = args.steps * sum(pipe._launches[:2])
+    launches = args.steps * sum(sum(pp._launches[:2]) for pp in pipes)
     _dbg(f"timed resident loop done: {ms / args.steps:.2f} ms/step")
     clocks = sampler.stop(t0, t1) if sampler else None
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
@@ -283,7 +297,7 @@ def main():
         frames = world * B * args.steps
         line = {"metric": "agent_frames_per_s", "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": args.precision, "data": "synthetic", "config": workload_config(B, args.precision),
+                "dtype": args.precision, "data": "synthetic", "config": workload_config(B, args.precision, P),
                 "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s",
                         "h2d_bytes_per_step": int(h_rgbs.numel() + h_tels.numel() + h_lidar.numel() * 4),
                         "d2h_bytes_per_step": int(B * 20 * 2 * 4 + B * 4)},

@@ -87,6 +87,18 @@ int lavb_pillar_forward(const float* d_pts, int pt_stride, int d,
                         const float* d_w2, const float* d_s2, const float* d_t2, int h2,
                         void* d_canvas, int canvas_dtype, void* d_workspace, void* stream);
 
+/* Sorted, atomic-free variant for the tensor-core pipeline: counting sort of the points by canvas cell, layer 1 in
+ * fp32, layer 2 on the tensor cores (bf16 operands, fp32 accumulate), one canvas row written per pillar and the rows
+ * of empty cells zero-filled by the scan pass.  out_mode 0: fp32 canvas [B][ny][nx][h2]; 1: bf16 canvas
+ * [B][ny][nx][hi(h2) | lo(h2)] (the error-free split lavb_split_bf16 produces).  Same semantics otherwise. */
+size_t lavb_pillar_sorted_workspace_bytes(int batch, int nx, int ny, long long total_points);
+int lavb_pillar_forward_sorted(const float* d_pts, int pt_stride, int d,
+                               const long long* h_cloud_start, const int* h_cloud_count, int batch,
+                               float min_x, float max_x, float min_y, float max_y, float ppm, int nx, int ny,
+                               const float* d_w1, const float* d_s1, const float* d_t1, int h1,
+                               const float* d_w2, const float* d_s2, const float* d_t2, int h2,
+                               void* d_canvas, int out_mode, void* d_workspace, void* stream);
+
 /* training-mode pieces (BatchNorm1d batch statistics over all in-window points, arg-routed backward).
  * stage 0: voxelise + decorate -> d_feat [M][d+5] (M = number of in-window points, returned in *h_m),
  *          d_cell [M] int32 canvas cell id (b*ny*nx + row*nx + col), -1 never appears.

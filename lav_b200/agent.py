@@ -146,6 +146,7 @@ class StaticFramePipeline(FramePipeline):
         self.nxps = torch.zeros((B, 2), device=dev)
         self.cmds = torch.zeros((B,), dtype=torch.long, device=dev)
         self.tick = 0
+        self.stream = torch.cuda.Stream(device=dev)
         self._g1 = None
         self._g2 = {}
         self._launches = []      # lav_b200 kernel launches per captured graph (G1 first)
@@ -219,12 +220,8 @@ class StaticFramePipeline(FramePipeline):
         return self.infer_model.uniplanner.infer_device(self._o1["features"].permute(0, 3, 1, 2), locs, oris, fidx, K, self.nxps, self.cmds)
 
     def _capture(self, fn):
-        side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                out = fn()                                   # warm-up: cuDNN plans, workspaces, plan caches
-        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(2):
+            out = fn()                                       # warm-up: cuDNN plans, workspaces, plan caches
         torch.cuda.synchronize()
         c0 = ops.launches()
         if not self.use_graphs:
@@ -240,7 +237,27 @@ class StaticFramePipeline(FramePipeline):
     @torch.no_grad()
     def step(self, rgbs_u8, tel_u8, lidars, nxps, cmds, poses=None, fixed_dets=None):
         """rgbs_u8 (B,3,288,256,3) u8 / tel_u8 (B,192,480,3) u8 on host (pinned) or device; lidars: (B,n,4) tensor or list of
-        (n_b,4) (n_b <= N); nxps (B,2); cmds (B,) ints.  Returns the dict of FramePipeline.step."""
+        (n_b,4) (n_b <= N); nxps (B,2); cmds (B,) ints.  Returns the dict of FramePipeline.step.
+        = begin() + finish(); call them separately to overlap the host-side decode of one pipeline with the GPU work of
+        another (each StaticFramePipeline owns a stream)."""
+        self.begin(rgbs_u8, tel_u8, lidars, nxps, cmds, poses)
+        return self.finish(fixed_dets)
+
+    @torch.no_grad()
+    def begin(self, rgbs_u8, tel_u8, lidars, nxps, cmds, poses=None):
+        """stage inputs and launch G1 (asynchronous)."""
+        with torch.cuda.stream(self.stream):
+            self._begin(rgbs_u8, tel_u8, lidars, nxps, cmds, poses)
+
+    @torch.no_grad()
+    def finish(self, fixed_dets=None):
+        """decode detections on the host, launch G2, return the outputs (device tensors, valid on self.stream)."""
+        with torch.cuda.stream(self.stream):
+            out = self._finish(fixed_dets)
+        torch.cuda.current_stream().wait_stream(self.stream)
+        return out
+
+    def _begin(self, rgbs_u8, tel_u8, lidars, nxps, cmds, poses):
         B, N = self.B, self.N
         self.rgbs.copy_(rgbs_u8, non_blocking=True)
         if tel_u8 is not None:
@@ -261,9 +278,12 @@ class StaticFramePipeline(FramePipeline):
             self._g1.replay()
         else:
             self._o1 = self._g1_body()
-        o1 = self._o1
         self.ring[:, self.tick % self.KEEP].copy_(self.cur)                   # FIFO push (lav_agent_fast.py:267)
         self.tick += 1
+
+    def _finish(self, fixed_dets):
+        B = self.B
+        o1 = self._o1
         dets = self.infer_model.decode_packed(o1["packed"])
         veh = [list(fixed_dets) for _ in range(B)] if fixed_dets is not None else [d[1] for d in dets]
         up = self.infer_model.uniplanner
@@ -281,9 +301,8 @@ class StaticFramePipeline(FramePipeline):
             self._g2[K] = (g, out, st)
         g, out, st = self._g2[K]
         if K > 0:
-            st["locs"][:K].copy_(torch.tensor(locs, dtype=torch.float32), non_blocking=False)
-            st["oris"][:K].copy_(torch.tensor(oris, dtype=torch.float32), non_blocking=False)
-            st["fidx"][:K].copy_(torch.tensor(fidx, dtype=torch.int32), non_blocking=False)
+            pk = torch.tensor([l + [o, float(f)] for l, o, f in zip(locs, oris, fidx)], dtype=torch.float32).to(self.device, non_blocking=True)
+            st["locs"][:K].copy_(pk[:, :2]); st["oris"][:K].copy_(pk[:, 2]); st["fidx"][:K].copy_(pk[:, 3])
         if g is not None:
             g.replay()
         else:

@@ -278,6 +278,296 @@ static int fill_clouds(Clouds& c, const long long* start, const int* count, int 
 
 static size_t stats_bytes(int batch, int nx, int ny) { return (size_t)batch * (nx + 1) * (ny + 1) * sizeof(float4); }
 
+// =====================================================================================================================
+// Sorted (atomic-free canvas) pillar encoder for the tensor-core pipeline.
+//   K1 count   : per point -> centroid sums (one vector RED) + per-canvas-cell point count
+//   K2 offsets : exclusive scan of the counts (block sums -> single-block scan -> per-cell offsets); the same pass
+//                zero-fills the canvas rows of EMPTY cells (so every canvas byte is written exactly once overall)
+//                and records for every 128-slot window the first segment head at/after it (tile_start)
+//   K3 fill    : counting-sort scatter of point indices into cell order
+//   K4 encode  : block i owns the whole pillars whose first point lies in slots [128 i, 128 (i+1)); per 128-row chunk:
+//                decorate + layer 1 (fp32 FFMA) -> bf16 hidden tile in swizzled smem -> layer 2 on the tensor cores
+//                (mma.sync m16n8k16 bf16, fp32 accumulate; the 64x64 weight fragments live in registers) ->
+//                BN affine + ReLU -> fp32 tile in smem -> 64 channel-threads walk the rows and emit one canvas row per
+//                pillar (running max), as fp32 or as the [hi | lo] bf16 split conv1 consumes.
+// The first layer stays fp32 because its inputs are raw metric coordinates (bf16 would quantise x to 0.25 m).
+// =====================================================================================================================
+constexpr int kCellsPerBlock = 1024;
+constexpr int kRows = 128;            // slots per encode chunk
+constexpr int kOsPitch = 68;          // fp32 output tile pitch (floats): conflict-free fragment stores
+
+__global__ void __launch_bounds__(256) pillar_count_kernel(const float* __restrict__ pts, int pt_stride,
+                                                           const __grid_constant__ Clouds clouds,
+                                                           const __grid_constant__ Grid g, float4* __restrict__ stats,
+                                                           int* __restrict__ count) {
+  const int total = clouds.cum[clouds.batch];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = find_cloud(clouds, i);
+    const float* p = pts + (clouds.start[b] + (i - clouds.cum[b])) * pt_stride;
+    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    int xi, yi;
+    if (!locate(g, x, y, xi, yi)) continue;
+    atomicAdd(&stats[pillar_key(g, b, xi, yi)], make_float4(x, y, z, 1.f));
+    atomicAdd(&count[canvas_cell(g, b, xi, yi)], 1);
+  }
+}
+
+__global__ void __launch_bounds__(kCellsPerBlock) cell_block_sum_kernel(const int* __restrict__ count, long long ncells,
+                                                                        int* __restrict__ block_sum) {
+  const long long c = (long long)blockIdx.x * kCellsPerBlock + threadIdx.x;
+  int v = c < ncells ? count[c] : 0;
+  __shared__ int ws[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = ws[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (threadIdx.x == 0) block_sum[blockIdx.x] = w;
+  }
+}
+
+// per-cell exclusive offsets + zero-fill of empty canvas rows + tile_start table
+__global__ void __launch_bounds__(kCellsPerBlock) cell_offsets_kernel(const int* __restrict__ count, long long ncells,
+                                                                      const int* __restrict__ block_off,
+                                                                      int* __restrict__ offsets, int* __restrict__ tile_start,
+                                                                      const int* __restrict__ total_kept,
+                                                                      uint4* __restrict__ canvas16, int row_vec16) {
+  __shared__ int ws[32];
+  const long long c = (long long)blockIdx.x * kCellsPerBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cnt = c < ncells ? count[c] : 0;
+  int x = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) ws[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    int w = ws[lane], s = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+    ws[lane] = s - w;
+  }
+  __syncthreads();
+  const int off = block_off[blockIdx.x] + ws[warp] + x - cnt;
+  if (c < ncells) offsets[c] = off;
+  if (c == ncells - 1) { offsets[ncells] = off + cnt; }
+  if (cnt > 0) {   // window boundaries 128*i inside [off, off+cnt): first head at/after the boundary
+    for (int i = (off + kRows - 1) / kRows; i * kRows < off + cnt; ++i) tile_start[i] = (i * kRows == off) ? off : off + cnt;
+  }
+  if (c == 0) { const int tk = *total_kept; tile_start[(tk + kRows - 1) / kRows] = tk; }
+  // zero-fill: the warp's 32 cells are one contiguous canvas span; lanes sweep it 16 B at a time, skipping occupied rows
+  const unsigned occ = __ballot_sync(0xffffffffu, cnt > 0 || c >= ncells);
+  const long long c0 = c - lane;
+  const int per_iter = 32 / row_vec16 > 0 ? 32 / row_vec16 : 1;      // rows covered per sweep step (row_vec16 = 16 B pieces / row)
+  for (int r0 = 0; r0 < 32; r0 += per_iter) {
+    if (row_vec16 <= 32) {
+      const int r = r0 + lane / row_vec16, v = lane % row_vec16;
+      if (r < 32 && !((occ >> r) & 1u)) canvas16[(c0 + r) * row_vec16 + v] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      if (!((occ >> r0) & 1u))
+        for (int v = lane; v < row_vec16; v += 32) canvas16[(c0 + r0) * row_vec16 + v] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pillar_fill_kernel(const float* __restrict__ pts, int pt_stride,
+                                                          const __grid_constant__ Clouds clouds, const __grid_constant__ Grid g,
+                                                          const int* __restrict__ offsets, int* __restrict__ cursor,
+                                                          int* __restrict__ order, int* __restrict__ ocell) {
+  const int total = clouds.cum[clouds.batch];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = find_cloud(clouds, i);
+    const float* p = pts + (clouds.start[b] + (i - clouds.cum[b])) * pt_stride;
+    int xi, yi;
+    if (!locate(g, __ldg(p), __ldg(p + 1), xi, yi)) continue;
+    const int cell = (int)canvas_cell(g, b, xi, yi);
+    const int slot = __ldg(offsets + cell) + atomicAdd(cursor + cell, 1);
+    order[slot] = i;
+    ocell[slot] = cell;
+  }
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int D, bool kSplitOut>
+__global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
+    const float* __restrict__ pts, int pt_stride, const __grid_constant__ Clouds clouds, const __grid_constant__ Grid g,
+    const float4* __restrict__ stats, const int* __restrict__ order, const int* __restrict__ ocell,
+    const int* __restrict__ tile_start, const int* __restrict__ total_kept, const float* __restrict__ w1,
+    const float* __restrict__ s1, const float* __restrict__ t1, const float* __restrict__ w2, const float* __restrict__ s2,
+    const float* __restrict__ t2, void* __restrict__ canvas) {
+  constexpr int F = D + 5, H = 64;
+  extern __shared__ __align__(128) uint8_t sm[];
+  __nv_bfloat16* Hs = reinterpret_cast<__nv_bfloat16*>(sm);                       // [128][64] bf16, 16 B chunks XOR (row & 7)
+  float* Os = reinterpret_cast<float*>(sm + kRows * H * 2);                        // [128][kOsPitch]
+  float* w1s = Os + kRows * kOsPitch;                                              // [F][64]
+  __nv_bfloat16* w2s = reinterpret_cast<__nv_bfloat16*>(w1s + F * H);              // [64 n][64 k]
+  float* aff = reinterpret_cast<float*>(w2s + H * H);                              // s1 | t1 | s2 | t2
+  int* cells = reinterpret_cast<int*>(aff + 4 * H);                                // [128]
+
+  const int nt = (*total_kept + kRows - 1) / kRows;
+  if ((int)blockIdx.x >= nt) return;
+  const int row_begin = tile_start[blockIdx.x], row_end = tile_start[blockIdx.x + 1];
+  if (row_begin >= row_end) return;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < F * H; i += kRows) w1s[(i % F) * H + i / F] = __ldg(w1 + i);                 // w1 is [64][F]
+  for (int i = tid; i < H * H; i += kRows) w2s[i] = __float2bfloat16_rn(__ldg(w2 + i));             // w2 is [64 n][64 k]
+  for (int i = tid; i < H; i += kRows) { aff[i] = __ldg(s1 + i); aff[H + i] = __ldg(t1 + i); aff[2 * H + i] = __ldg(s2 + i); aff[3 * H + i] = __ldg(t2 + i); }
+  __syncthreads();
+  // layer-2 weight fragments (B operand, "col" layout = rows of w2): b0 (k = 16kk + 2t.., n = 8nn + g), b1 (k + 8)
+  uint32_t bfrag[4][8][2];
+  {
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int nn = 0; nn < 8; ++nn) {
+        const __nv_bfloat16* wp = w2s + (nn * 8 + gq) * H + kk * 16 + tq * 2;
+        bfrag[kk][nn][0] = *reinterpret_cast<const uint32_t*>(wp);
+        bfrag[kk][nn][1] = *reinterpret_cast<const uint32_t*>(wp + 8);
+      }
+  }
+  float run_max = 0.f;      // channel-thread state of the row walk (threads 0..63)
+  int run_cell = -1;
+
+  for (int base = row_begin; base < row_end; base += kRows) {
+    const int rows = min(kRows, row_end - base);
+    // ---- (1) gather + decorate + layer 1 (one thread per row)
+    {
+      float h[H];
+#pragma unroll
+      for (int j = 0; j < H; ++j) h[j] = 0.f;
+      int cell = -1;
+      if (tid < rows) {
+        const int i = __ldg(order + base + tid);
+        cell = __ldg(ocell + base + tid);
+        const int b = find_cloud(clouds, i);
+        const float* p = pts + (clouds.start[b] + (i - clouds.cum[b])) * pt_stride;
+        int xi, yi;
+        locate(g, __ldg(p), __ldg(p + 1), xi, yi);
+        float f[F];
+        decorate<D>(g, p, xi, yi, __ldg(&stats[pillar_key(g, b, xi, yi)]), f);
+#pragma unroll
+        for (int k = 0; k < F; ++k) {
+#pragma unroll
+          for (int j = 0; j < H; j += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(&w1s[k * H + j]);
+            h[j] = fmaf(f[k], w.x, h[j]); h[j + 1] = fmaf(f[k], w.y, h[j + 1]);
+            h[j + 2] = fmaf(f[k], w.z, h[j + 2]); h[j + 3] = fmaf(f[k], w.w, h[j + 3]);
+          }
+        }
+      }
+      cells[tid] = cell;
+      // relu(affine) -> bf16, 8 channels (16 B) per store, chunk index XOR (row & 7)
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = c8 * 8 + e * 2;
+          const float v0 = fmaxf(fmaf(h[j], aff[j], aff[H + j]), 0.f), v1 = fmaxf(fmaf(h[j + 1], aff[j + 1], aff[H + j + 1]), 0.f);
+          const __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+          pk[e] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(Hs) + tid * 128 + ((c8 ^ (tid & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+    __syncthreads();
+    // ---- (2) layer 2 on the tensor cores: warp w -> rows [32w, 32w+32) as two m16 tiles
+    {
+      const uint32_t hs_base = (uint32_t)__cvta_generic_to_shared(Hs);
+      const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int row0 = warp * 32 + mt * 16;
+        float acc[8][4];
+#pragma unroll
+        for (int nn = 0; nn < 8; ++nn) { acc[nn][0] = acc[nn][1] = acc[nn][2] = acc[nn][3] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int r = row0 + (lane & 15), chunk = kk * 2 + (lane >> 4);
+          uint32_t a0, a1, a2, a3;
+          ldmatrix_x4(hs_base + r * 128 + ((chunk ^ (r & 7)) << 4), a0, a1, a2, a3);
+#pragma unroll
+          for (int nn = 0; nn < 8; ++nn) mma_bf16_16816(acc[nn], a0, a1, a2, a3, bfrag[kk][nn][0], bfrag[kk][nn][1]);
+        }
+#pragma unroll
+        for (int nn = 0; nn < 8; ++nn) {
+          const int col = nn * 8 + tq * 2;
+          const float sc0 = aff[2 * H + col], sc1 = aff[2 * H + col + 1], sh0 = aff[3 * H + col], sh1 = aff[3 * H + col + 1];
+          *reinterpret_cast<float2*>(&Os[(row0 + gq) * kOsPitch + col]) =
+              make_float2(fmaxf(fmaf(acc[nn][0], sc0, sh0), 0.f), fmaxf(fmaf(acc[nn][1], sc1, sh1), 0.f));
+          *reinterpret_cast<float2*>(&Os[(row0 + gq + 8) * kOsPitch + col]) =
+              make_float2(fmaxf(fmaf(acc[nn][2], sc0, sh0), 0.f), fmaxf(fmaf(acc[nn][3], sc1, sh1), 0.f));
+        }
+      }
+    }
+    __syncthreads();
+    // ---- (3) row walk: thread c < 64 keeps the running max of channel c and emits a canvas row when the pillar ends
+    if (tid < H) {
+      for (int r = 0; r < rows; ++r) {
+        const int cell = cells[r];
+        if (cell != run_cell) {
+          if (run_cell >= 0) {
+            if (kSplitOut) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(canvas) + (long long)run_cell * 2 * H;
+              const __nv_bfloat16 hi = __float2bfloat16_rn(run_max);
+              o[tid] = hi; o[H + tid] = __float2bfloat16_rn(run_max - __bfloat162float(hi));
+            } else {
+              reinterpret_cast<float*>(canvas)[(long long)run_cell * H + tid] = run_max;
+            }
+          }
+          run_cell = cell; run_max = 0.f;
+        }
+        run_max = fmaxf(run_max, Os[r * kOsPitch + tid]);
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < H && run_cell >= 0) {
+    if (kSplitOut) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(canvas) + (long long)run_cell * 2 * H;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(run_max);
+      o[tid] = hi; o[H + tid] = __float2bfloat16_rn(run_max - __bfloat162float(hi));
+    } else {
+      reinterpret_cast<float*>(canvas)[(long long)run_cell * H + tid] = run_max;
+    }
+  }
+}
+
+struct SortedWs {
+  float4* stats; int* count; int* offsets; int* cursor; int* block_sum; int* total; int* tile_start; int* order; int* ocell;
+  size_t bytes;
+};
+static SortedWs carve_sorted(void* base, int batch, int nx, int ny, long long total_pts) {
+  SortedWs w;
+  const long long ncells = (long long)batch * nx * ny;
+  const long long nblk = (ncells + kCellsPerBlock - 1) / kCellsPerBlock;
+  char* p = reinterpret_cast<char*>(base);
+  auto take = [&](size_t n) { char* r = p; p += (n + 255) / 256 * 256; return r; };
+  w.stats = reinterpret_cast<float4*>(take(stats_bytes(batch, nx, ny)));
+  w.count = reinterpret_cast<int*>(take(ncells * 4));
+  w.cursor = reinterpret_cast<int*>(take(ncells * 4));
+  w.offsets = reinterpret_cast<int*>(take((ncells + 1) * 4));
+  w.block_sum = reinterpret_cast<int*>(take((nblk + 1) * 4));
+  w.total = reinterpret_cast<int*>(take(256));
+  w.tile_start = reinterpret_cast<int*>(take((total_pts / kRows + 2) * 4));
+  w.order = reinterpret_cast<int*>(take((size_t)total_pts * 4));
+  w.ocell = reinterpret_cast<int*>(take((size_t)total_pts * 4));
+  w.bytes = (size_t)(p - reinterpret_cast<char*>(base));
+  return w;
+}
+
 }  // namespace lavb
 
 using namespace lavb;
@@ -368,6 +658,64 @@ extern "C" int lavb_pillar_scatter_max_bwd(const float* d_gcanvas, const int* d_
   const long long mc = (long long)m * c;
   if (mc == 0) return 0;
   scatter_bwd_kernel<<<ceil_div(mc, 256), 256, 0, (cudaStream_t)stream>>>(d_gcanvas, d_argmax, d_cell, mc, c, d_gh);
+  LAVB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" size_t lavb_pillar_sorted_workspace_bytes(int batch, int nx, int ny, long long total_points) {
+  return carve_sorted(nullptr, batch, nx, ny, total_points).bytes;
+}
+
+extern "C" int lavb_pillar_forward_sorted(const float* d_pts, int pt_stride, int d, const long long* h_cloud_start,
+                                          const int* h_cloud_count, int batch, float min_x, float max_x, float min_y,
+                                          float max_y, float ppm, int nx, int ny, const float* d_w1, const float* d_s1,
+                                          const float* d_t1, int h1, const float* d_w2, const float* d_s2, const float* d_t2,
+                                          int h2, void* d_canvas, int out_mode, void* d_workspace, void* stream) {
+  Clouds clouds;
+  if (fill_clouds(clouds, h_cloud_start, h_cloud_count, batch)) return 1;
+  LAVB_CHECK_ARG(d == 11 && h1 == 64 && h2 == 64, "pillar_forward_sorted: only the v2 configuration (D=11, features [64,64]) is built");
+  LAVB_CHECK_ARG(out_mode == 0 || out_mode == 1, "pillar_forward_sorted: out_mode 0 (fp32) or 1 (bf16 hi|lo split)");
+  LAVB_CHECK_ARG(pt_stride >= d, "pillar_forward_sorted: pt_stride < d");
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g{min_x, max_x, min_y, max_y, ppm, nx, ny};
+  const int total = clouds.cum[batch];
+  const long long ncells = (long long)batch * nx * ny;
+  LAVB_CHECK_ARG(ncells < (1LL << 31), "pillar_forward_sorted: too many cells");
+  const SortedWs w = carve_sorted(d_workspace, batch, nx, ny, total);
+  const int row_bytes = h2 * (out_mode == 1 ? 4 : 4);        // fp32: 64*4; split: 128*2
+  LAVB_CUDA_OK(cudaMemsetAsync(w.stats, 0, stats_bytes(batch, nx, ny), st));
+  LAVB_CUDA_OK(cudaMemsetAsync(w.count, 0, (size_t)ncells * 8 + 512, st));       // count + cursor (adjacent, 256 B padded)
+  LAVB_CUDA_OK(cudaMemsetAsync(w.tile_start, 0, ((size_t)total / kRows + 2) * 4, st));
+  if (total > 0) {
+    pillar_count_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, st>>>(d_pts, pt_stride, clouds, g, w.stats, w.count);
+    LAVB_LAUNCH_OK();
+  }
+  const int nblk = ceil_div(ncells, kCellsPerBlock);
+  cell_block_sum_kernel<<<nblk, kCellsPerBlock, 0, st>>>(w.count, ncells, w.block_sum);
+  LAVB_LAUNCH_OK();
+  scan_blocks_kernel<<<1, 1024, 0, st>>>(w.block_sum, nblk, w.total);
+  LAVB_LAUNCH_OK();
+  cell_offsets_kernel<<<nblk, kCellsPerBlock, 0, st>>>(w.count, ncells, w.block_sum, w.offsets, w.tile_start, w.total,
+                                                       reinterpret_cast<uint4*>(d_canvas), row_bytes / 16);
+  LAVB_LAUNCH_OK();
+  if (total == 0) return 0;
+  pillar_fill_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, st>>>(d_pts, pt_stride, clouds, g, w.offsets, w.cursor,
+                                                                             w.order, w.ocell);
+  LAVB_LAUNCH_OK();
+  const size_t smem = (size_t)kRows * 64 * 2 + (size_t)kRows * kOsPitch * 4 + 16 * 64 * 4 + 64 * 64 * 2 + 4 * 64 * 4 + kRows * 4;
+  static bool configured = false;
+  if (!configured) {
+    LAVB_CUDA_OK(cudaFuncSetAttribute(pillar_encode_sorted_kernel<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    LAVB_CUDA_OK(cudaFuncSetAttribute(pillar_encode_sorted_kernel<11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    configured = true;
+  }
+  const int ntiles = ceil_div(total, kRows);
+  if (out_mode == 0)
+    pillar_encode_sorted_kernel<11, false><<<ntiles, kRows, smem, st>>>(d_pts, pt_stride, clouds, g, w.stats, w.order, w.ocell,
+                                                                        w.tile_start, w.total, d_w1, d_s1, d_t1, d_w2, d_s2, d_t2, d_canvas);
+  else
+    pillar_encode_sorted_kernel<11, true><<<ntiles, kRows, smem, st>>>(d_pts, pt_stride, clouds, g, w.stats, w.order, w.ocell,
+                                                                       w.tile_start, w.total, d_w1, d_s1, d_t1, d_w2, d_s2, d_t2, d_canvas);
   LAVB_LAUNCH_OK();
   return 0;
 }

@@ -75,6 +75,8 @@ class ConvBackbone(PlanMixin, nn.Module):
         if dt == torch.bfloat16 and x.dtype == torch.float32:
             from . import ops
             first = plan["conv1_split"](ops.split_bf16(x), out_dtype=dt)
+        elif dt == torch.bfloat16 and x.shape[-1] == 2 * self.conv1[0].in_channels:
+            first = plan["conv1_split"](x, out_dtype=dt)       # canvas already arrives as the [hi | lo] bf16 split
         xs = []
         for name in ("conv1", "conv2", "conv3"):
             for li, layer in enumerate(plan[name]):
@@ -194,8 +196,8 @@ class LiDARModel(PlanMixin, nn.Module):
         return ops.deconv3x3s2_small(hid, 4, nh, wd, bd, n_outs, sig)
 
     def forward_nhwc(self, lidars, num_points):
-        canvas = self.point_pillar_net(lidars, num_points).permute(0, 2, 3, 1)   # NHWC view of the canvas
-        feats = self.backbone.forward_nhwc(canvas.contiguous())
+        canvas = self.point_pillar_net.forward_nhwc(lidars, num_points, split_out=(self.precision == "bf16"))
+        feats = self.backbone.forward_nhwc(canvas)
         return (feats, *self.heads_nhwc(feats))
 
     def forward(self, lidars, num_points):

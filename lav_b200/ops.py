@@ -316,3 +316,24 @@ def split_bf16(x):
     check(lib().lavb_split_bf16(_ptr(x), _ptr(out), x.numel() // c, c, _stream()), "lavb_split_bf16")
     _COUNT[0] += 1
     return out
+
+
+def pillar_forward_sorted(pts, starts, counts, grid, w1, s1, t1, w2, s2, t2, split_out=False):
+    """sorted / tensor-core pillar encoder (lavb_pillar_forward_sorted).  Returns the NHWC canvas: fp32 (B,ny,nx,H2) or,
+    with split_out, bf16 (B,ny,nx,2*H2) = [hi | lo]."""
+    _need_cuda(pts, w1, w2)
+    assert pts.dtype == torch.float32 and pts.dim() == 2 and pts.stride(1) == 1
+    min_x, max_x, min_y, max_y, ppm, nx, ny = grid
+    d = w1.shape[1] - 5
+    b, st, ct = _clouds(starts, counts)
+    total = int(sum(int(c) for c in counts))
+    h2 = w2.shape[0]
+    canvas = torch.empty((b, ny, nx, 2 * h2 if split_out else h2), dtype=torch.bfloat16 if split_out else torch.float32, device=pts.device)
+    ws = _workspace(pts.device, lib().lavb_pillar_sorted_workspace_bytes(b, nx, ny, total))
+    e0 = _prof_begin()
+    check(lib().lavb_pillar_forward_sorted(_ptr(pts), pts.stride(0), d, st, ct, b, min_x, max_x, min_y, max_y, ppm, nx, ny,
+                                           _ptr(w1), _ptr(s1), _ptr(t1), w1.shape[0], _ptr(w2), _ptr(s2), _ptr(t2), h2,
+                                           _ptr(canvas), int(split_out), _ptr(ws), _stream()), "lavb_pillar_forward_sorted")
+    _prof_end("pillar", float(total) * d * 4 + float(b) * ny * nx * h2 * 4, e0)
+    _COUNT[0] += 6
+    return canvas

@@ -54,6 +54,7 @@ class PointPillarNet(PlanMixin, nn.Module):
         self.min_x, self.min_y, self.max_x, self.max_y = min_x, min_y, max_x, max_y
         self.pixels_per_meter = pixels_per_meter
         self.num_point_dims = num_input - 5
+        self.precision = "fp32"      # 'bf16' selects the sorted / tensor-core encoder (set by LiDARModel.set_precision)
 
     def _grid(self):
         return (float(self.min_x), float(self.max_x), float(self.min_y), float(self.max_y), float(self.pixels_per_meter),
@@ -107,6 +108,16 @@ class PointPillarNet(PlanMixin, nn.Module):
             h = self.point_net.net(feat)
             canvas = _PillarScatterMax.apply(h, cell, B * self.ny * self.nx)
             return canvas.view(B, self.ny, self.nx, -1).permute(0, 3, 1, 2)
+        return self.forward_nhwc(lidar_list, num_points, _buf=(buf, starts, counts)).permute(0, 3, 1, 2)
+
+    def forward_nhwc(self, lidar_list, num_points, split_out=False, _buf=None):
+        """eval forward returning the raw NHWC canvas buffer.  fp32 precision: exact kernel (fp32 FFMA + atomicMax).
+        bf16 precision: sorted / tensor-core kernel; with split_out the canvas comes as bf16 [hi | lo] (B,ny,nx,2C),
+        which is what ConvBackbone's first tensor-core conv consumes."""
+        buf, starts, counts = _buf if _buf is not None else self._as_buffer(lidar_list, num_points)
+        if not buf.is_cuda:
+            raise LavbError("lav_b200.PointPillarNet needs CUDA tensors (no CPU fallback)")
         w1, s1, t1, w2, s2, t2 = self._plan_get(buf.device, self._build)
-        canvas = ops.pillar_forward(buf, starts, counts, self._grid(), w1, s1, t1, w2, s2, t2)
-        return canvas.permute(0, 3, 1, 2)
+        if self.precision == "bf16":
+            return ops.pillar_forward_sorted(buf, starts, counts, self._grid(), w1, s1, t1, w2, s2, t2, split_out=split_out)
+        return ops.pillar_forward(buf, starts, counts, self._grid(), w1, s1, t1, w2, s2, t2)

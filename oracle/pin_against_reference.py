@@ -140,6 +140,11 @@ def main():
     assert worst < 5e-3
     sel = ["point_pillar_net.point_net.net.0.weight", "point_pillar_net.point_net.net.3.weight",
            "backbone.conv1.0.weight", "backbone.upconv3.0.weight", "center_head.net.3.bias", "backbone.conv2.2.weight"]
+    digest = {}
+    for k, g_ in ref_grads.items():      # compact fingerprint of EVERY parameter gradient: l2 norm, sum, projection on a seeded vector
+        r = torch.randn(g_.shape, generator=synth._gen(13, "dg:" + k))
+        digest[k] = [float(g_.norm()), float(g_.sum()), float((g_ * r).sum()), float(g_.abs().max())]
+    json.dump(digest, open(os.path.join(GOLD, "lidar_model_train_grad_digest.json"), "w"), indent=0)
     np.savez_compressed(os.path.join(GOLD, "lidar_model_train.npz"), loss=float(loss),
                         **{"grad:" + k: ref_grads[k].numpy() for k in sel},
                         **{"out_" + n: o.detach()[:, :, ::8, ::8].numpy() for n, o in zip(names, outs)})

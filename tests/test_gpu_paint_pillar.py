@@ -155,3 +155,35 @@ def test_pillar_full_size_properties(cuda):
         can_p = m.point_pillar_net(batch[:1, perm], [40000])
         assert util.rel_err(can_p[0], can[0]) < 1e-5                                        # point order irrelevant
         assert float(can.min()) >= 0.0
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("mode", ["carla", "uniform", "adversarial", "batch", "empty"])
+def test_pillar_sorted_kernel_matches_oracle(cuda, mode, split):
+    """sorted / tensor-core encoder (bf16 pipeline): same occupancy as the oracle, values within bf16 layer-2 rounding."""
+    m, sd = util.lidar_model(cuda)
+    m.set_precision("bf16")
+    if mode == "batch":
+        clouds = util.pillar_clouds()
+    elif mode == "empty":
+        clouds = [torch.zeros((0, 11))]
+    elif mode == "carla":
+        clouds = [synth.stacked_lidar(20000, tag="sorted")]
+    else:
+        xyz = synth.lidar_sweep(9000, tag=mode, mode=mode)
+        clouds = [torch.cat([xyz, torch.rand(9000, 7, generator=synth._gen(3, mode))], 1)]
+    npts = [len(c) for c in clouds]
+    with torch.no_grad():
+        got = m.point_pillar_net.forward_nhwc([c.to(cuda) for c in clouds], npts, split_out=split).float().cpu()
+    if split:
+        got = got[..., :64] + got[..., 64:]
+    if mode == "empty":
+        assert float(got.abs().max()) == 0.0
+        return
+    with torch.no_grad():
+        want = O.pillar_net(sd, clouds, npts, **util.GRID).permute(0, 2, 3, 1)
+    assert got.shape == want.shape
+    assert torch.equal((got != 0).any(-1), (want != 0).any(-1)), "occupied cells differ"
+    assert util.rel_err(got, want) < 6e-3
+    rms = float(((got - want) ** 2).mean().sqrt() / (want ** 2).mean().sqrt())
+    assert rms < 3e-3, rms
