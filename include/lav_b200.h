@@ -132,6 +132,11 @@ typedef struct {
   const float* w; const float* bias; const float* scale; const float* shift;
   const void* res; int res_dtype; int res_cstride, res_coff;
   int pre_relu, post_relu, sigmoid;
+  /* lavb_conv_umma only: depth-to-space epilogue.  d2s_nout > 0 means the (<= 32) GEMM columns are 4 output positions
+   * x d2s_nout channels: column j = pos*d2s_nout + k goes to pixel (2*gy + pos/2, 2*gx + pos%2), channel k of an fp32
+   * NHWC tensor [n][hout][wout][d2s_nout] (out_s must be 2).  This is how a ConvTranspose2d(k3,s2,p1,op1) with a few
+   * output channels runs as a 2x2-tap GEMM (the four detection heads' last layer). */
+  int d2s_nout;
 } lavb_conv_desc;
 int lavb_conv_taps(const lavb_conv_desc* h_desc, void* stream);
 

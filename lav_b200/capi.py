@@ -27,7 +27,7 @@ class ConvDesc(C.Structure):
         ("ntaps", C.c_int), ("dy", C.c_int * 16), ("dx", C.c_int * 16),
         ("w", C.c_void_p), ("bias", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
         ("res", C.c_void_p), ("res_dtype", C.c_int), ("res_cstride", C.c_int), ("res_coff", C.c_int),
-        ("pre_relu", C.c_int), ("post_relu", C.c_int), ("sigmoid", C.c_int),
+        ("pre_relu", C.c_int), ("post_relu", C.c_int), ("sigmoid", C.c_int), ("d2s_nout", C.c_int),
     ]
 
 

@@ -30,7 +30,7 @@ struct UmmaArgs {
   int hout, wout, cin, cout, kchunks, ntaps, stages, tmem_cols;
   int in_sy, in_sx, out_sy, out_sx, out_oy, out_ox;
   int out_cstride, out_coff, out_is_f32, res_cstride, res_coff;
-  int pre_relu, post_relu, sigmoid;
+  int pre_relu, post_relu, sigmoid, d2s_nout;
   int dy[kMaxTaps], dx[kMaxTaps];
   void* out; const __nv_bfloat16* res;
   const float* bias; const float* scale; const float* shift;
@@ -102,7 +102,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // kEpiWarps = 8: two warps per TMEM lane quarter (they split the column chunks), one CTA per SM — wide layers (cout > 128).
 // kEpiWarps = 4: one warp per quarter and TWO co-resident CTAs per SM (half the smem ring each): two independent tile
 //                pipelines hide the per-tile serial chain (commit -> epilogue -> tmem_empty) of the narrow layers.
-template <bool kOutF32, bool kRes, bool kSigmoid, bool kPreBias, int kEpiWarps>
+template <bool kOutF32, bool kRes, bool kSigmoid, bool kPreBias, int kEpiWarps, bool kD2S = false>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : 1) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                 const __grid_constant__ CUtensorMap tmap_b,
                                                                 const __grid_constant__ UmmaArgs p) {
@@ -238,7 +238,17 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : 1) c
             f[j] = fmaxf(f[j], lo_post);
             if (kSigmoid) f[j] = 1.f / (1.f + expf(-f[j]));
           }
-          if (kOutF32) {
+          if (kD2S) {   // depth-to-space: column j = pos*nout + k -> pixel (oy + pos/2, ox + pos%2), channel k
+            float* ob = reinterpret_cast<float*>(p.out);
+            const int no = p.d2s_nout;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < 4 * no) {
+                const int pos = j / no, k = j - pos * no;
+                ob[(pix + (long long)(pos >> 1) * p.wout + (pos & 1)) * no + k] = f[j];
+              }
+            }
+          } else if (kOutF32) {
             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_cstride + p.out_coff + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
@@ -338,13 +348,33 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   a.in_sy = d->in_sy; a.in_sx = d->in_sx; a.out_sy = d->out_sy; a.out_sx = d->out_sx; a.out_oy = d->out_oy; a.out_ox = d->out_ox;
   a.out_cstride = d->out_cstride; a.out_coff = d->out_coff; a.out_is_f32 = d->out_dtype == LAVB_F32;
   a.res_cstride = d->res_cstride; a.res_coff = d->res_coff;
-  a.pre_relu = d->pre_relu; a.post_relu = d->post_relu; a.sigmoid = d->sigmoid;
+  a.pre_relu = d->pre_relu; a.post_relu = d->post_relu; a.sigmoid = d->sigmoid; a.d2s_nout = d->d2s_nout;
+  if (d->d2s_nout) {
+    LAVB_CHECK_ARG(d->cout == 32 && d->d2s_nout >= 1 && 4 * d->d2s_nout <= 32 && d->out_dtype == LAVB_F32 && d->out_sy == 2 &&
+                   d->out_sx == 2 && d->res == nullptr, "conv_umma: depth-to-space epilogue needs cout=32, fp32 out, out_s=2, no residual");
+  }
   for (int t = 0; t < d->ntaps; ++t) { a.dy[t] = d->dy[t]; a.dx[t] = d->dx[t]; }
   a.out = d->out; a.res = reinterpret_cast<const __nv_bfloat16*>(d->res);
   a.bias = d->bias; a.scale = d->scale; a.shift = d->shift;
   if (a.num_tiles == 0) return 0;
   const size_t smem = (size_t)a.stages * stage_bytes + 1024 /*align*/ + 16 * kMaxStages + 64 + 3 * 256 * sizeof(float);
   const int grid = min(a.num_tiles, two_per_sm ? 2 * kNumSMs : kNumSMs);
+  if (a.d2s_nout) {
+#define LAVB_D2S(S)                                                                                                     \
+    {                                                                                                                   \
+      static bool configured = false;                                                                                   \
+      if (!configured) {                                                                                                \
+        LAVB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<true, false, S, false, 4, true>,                            \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));                    \
+        configured = true;                                                                                              \
+      }                                                                                                                 \
+      conv_umma_kernel<true, false, S, false, 4, true><<<grid, 64 + 32 * 4, smem, (cudaStream_t)stream>>>(tmap_a, tmap_b, a); \
+      LAVB_LAUNCH_OK();                                                                                                 \
+      return 0;                                                                                                         \
+    }
+    if (a.sigmoid) LAVB_D2S(true) else LAVB_D2S(false)
+#undef LAVB_D2S
+  }
   const bool f32 = a.out_is_f32, res = a.res != nullptr, sig = a.sigmoid != 0, pb = a.pre_relu && a.bias != nullptr;
   // epilogue variants are compiled separately so the inner loop carries no runtime flag tests
 #define LAVB_UMMA_LAUNCH(F, R, S, B, EW)                                                                                \

@@ -175,11 +175,11 @@ class LiDARModel(PlanMixin, nn.Module):
             ss.append(s)
             ts.append(t)
         conv = TapConv(torch.cat(ws, 0), False, 1, 1, pre_relu=True, scale=torch.cat(ss), shift=torch.cat(ts))
-        # the four ConvTranspose2d(64 -> 2/2/2/3, k3 s2 p1 op1) output layers as ONE grouped kernel (deconv_small.cu)
+        # the four ConvTranspose2d(64 -> 2/2/2/3, k3 s2 p1 op1) output layers
         nh = self.center_head.net[0].out_channels
         wd = torch.zeros((4, nh, 9, 4), dtype=torch.float32, device=device)
         bd = torch.zeros((4, 4), dtype=torch.float32, device=device)
-        n_outs = []
+        n_outs, d2s = [], []
         for g, h in enumerate(self._heads()):
             ct = h.net[3]
             assert ct.kernel_size == (3, 3) and ct.stride == (2, 2) and ct.padding == (1, 1) and ct.output_padding == (1, 1)
@@ -187,12 +187,36 @@ class LiDARModel(PlanMixin, nn.Module):
             wd[g, :, :, :no] = ct.weight.detach().float().permute(0, 2, 3, 1).reshape(nh, 9, no)   # (cin,cout,ky,kx)->(cin,tap,cout)
             bd[g, :no] = ct.bias.detach().float()
             n_outs.append(no)
-        return conv, (wd.contiguous(), bd.contiguous(), n_outs, [h._is_sigmoid() for h in self._heads()], nh)
+            # tensor-core form (bf16 path): a 2x2-tap GEMM over the input grid with 4*no (<=32) columns and a
+            # depth-to-space epilogue.  out(2y+a, 2x+b) gathers input pixel (y+dy, x+dx) through kernel tap (ky,kx):
+            #   a=0 -> (dy=0,ky=1);  a=1 -> (dy=0,ky=2) and (dy=1,ky=0)      (same for b / dx / kx)
+            w = ct.weight.detach().float()                                      # (cin, cout, ky, kx)
+            wu = torch.zeros((4, 32, nh), dtype=torch.float32, device=device)   # [tap=(dy,dx)][col=pos*no+k][cin]
+            opts = {0: [(0, 1)], 1: [(0, 2), (1, 0)]}
+            for pa in (0, 1):
+                for pb in (0, 1):
+                    for dy, ky in opts[pa]:
+                        for dx, kx in opts[pb]:
+                            wu[dy * 2 + dx, (pa * 2 + pb) * no:(pa * 2 + pb) * no + no] = w[:, :, ky, kx].t()
+            bias32 = torch.zeros(32, dtype=torch.float32, device=device)
+            bias32[:4 * no] = ct.bias.detach().float().repeat(4)
+            d2s.append((wu.to(torch.bfloat16).contiguous(), bias32))
+        return conv, (wd.contiguous(), bd.contiguous(), n_outs, [h._is_sigmoid() for h in self._heads()], nh, d2s)
 
     def heads_nhwc(self, feats):
         from . import ops
-        conv, (wd, bd, n_outs, sig, nh) = self._plan_get(feats.device, self._build)
-        hid = conv(feats, out_dtype=torch.float32)      # fp32 hidden map: one bf16 rounding less before the output layer
+        conv, (wd, bd, n_outs, sig, nh, d2s) = self._plan_get(feats.device, self._build)
+        if self.precision == "bf16":
+            hid = conv(feats, out_dtype=torch.bfloat16)
+            n, h, w, _ = hid.shape
+            outs = []
+            for g, (wu, b32) in enumerate(d2s):
+                out = torch.empty((n, 2 * h, 2 * w, n_outs[g]), dtype=torch.float32, device=hid.device)
+                ops.conv_taps(hid, nh, g * nh, out, 32, 0, h, w, (1, 1), (2, 2), (0, 0), [(0, 0), (0, 1), (1, 0), (1, 1)], wu,
+                              bias=b32, sigmoid=sig[g], umma=True, d2s_nout=n_outs[g])
+                outs.append(out)
+            return outs
+        hid = conv(feats, out_dtype=torch.float32)
         return ops.deconv3x3s2_small(hid, 4, nh, wd, bd, n_outs, sig)
 
     def forward_nhwc(self, lidars, num_points):

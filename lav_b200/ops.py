@@ -89,16 +89,11 @@ def stack_sweep(src, R, dx, dy, time_idx, n_time, dst, roof_filter=False):
 
 
 # ----------------------------------------------------------------------------- pillars
-_WS = {}
-
-
 def _workspace(device, nbytes):
-    key = (device, torch.cuda.current_stream().cuda_stream)
-    ws = _WS.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        _WS[key] = ws
-    return ws
+    """scratch for one call.  Deliberately NOT cached globally: under CUDA-graph capture the buffer must belong to the
+    capturing graph's private pool (two pipelines replaying on different streams must never share scratch); the
+    caching allocator makes the eager-mode cost negligible."""
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
 
 
 def _clouds(starts, counts):
@@ -168,7 +163,7 @@ def pillar_scatter_max_bwd(gcanvas, arg, cell, m):
 
 # ----------------------------------------------------------------------------- convolution
 def conv_taps(x, cin, in_coff, out, cout, out_coff, hog, wog, in_s, out_s, out_o, taps, w, bias=None, scale=None, shift=None,
-              res=None, res_coff=0, pre_relu=False, post_relu=False, sigmoid=False, umma=False):
+              res=None, res_coff=0, pre_relu=False, post_relu=False, sigmoid=False, umma=False, d2s_nout=0):
     """x, out, res: contiguous NHWC buffers (N,H,W,Ctot).  taps: list of (dy,dx).
     umma=False: CUDA-core kernel, w (ntaps,cin,cout_pad16) fp32.
     umma=True : tcgen05 kernel, x bf16, w (ntaps,cout,cin) bf16."""
@@ -182,6 +177,10 @@ def conv_taps(x, cin, in_coff, out, cout, out_coff, hog, wog, in_s, out_s, out_o
     assert out.shape[0] == x.shape[0]
     _, d.hout, d.wout, d.out_cstride = out.shape
     d.cout, d.out_coff = cout, out_coff
+    d.d2s_nout = d2s_nout
+    if d2s_nout:
+        assert umma and out.dtype == torch.float32 and out.shape[3] == d2s_nout and cout == 32 and 4 * d2s_nout <= 32
+        d.out_cstride, d.out_coff = 32, 0        # (validated as a 32-column GEMM; addressing is done by the d2s epilogue)
     d.hog, d.wog = hog, wog
     d.in_sy, d.in_sx = in_s
     d.out_sy, d.out_sx = out_s
