@@ -8,6 +8,7 @@
 // pipeline and a fused epilogue (bias, ReLU, BN affine, residual, ReLU, sigmoid).
 // This is the exact-fp32 workhorse (parity path and all HBM-bound layers); the tensor-core
 // layers of the bf16 path live in conv_umma.cu.
+#include <type_traits>
 #include "common.cuh"
 
 namespace lavb {
@@ -305,9 +306,114 @@ __global__ void __launch_bounds__(256) conv_small_kernel(const __grid_constant__
   }
 }
 
+// ---- 16-input-channel layers on the tensor cores (bf16 path): one tap = one K16 step of mma.sync m16n8k16.
+// ERFNet's 16-channel decoder blocks, the 16->48 downsampler conv and the 16->5 output ConvT (erfnet.py:71,121-124) are
+// FFMA-bound in conv_small_kernel (768 FMA per pixel); here a warp owns 32 output pixels, the A fragment of a tap is
+// loaded straight from global memory (a pixel's 16 channels are 32 contiguous bytes = exactly one fragment row), the
+// weights of a 16-wide output chunk live in registers as B fragments, and the epilogue is the usual fused one.
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <typename TOut, int NTAPS>
+__global__ void __launch_bounds__(128) conv_c16_mma_kernel(const __grid_constant__ ConvArgs a) {
+  const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+  const int co0 = blockIdx.y * 16;
+  // B fragments of this 16-column chunk: b0 = W[tap][k = 2tq, 2tq+1][n = 8nn + gq], b1 = same with k + 8
+  uint32_t bf[NTAPS][2][2];
+#pragma unroll
+  for (int t = 0; t < NTAPS; ++t)
+#pragma unroll
+    for (int nn = 0; nn < 2; ++nn)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float* wp = a.w + ((long long)t * 16 + (2 * tq + 8 * h)) * a.cout_pad + co0 + nn * 8 + gq;
+        const __nv_bfloat162 b2 = __floats2bfloat162_rn(t < a.ntaps ? __ldg(wp) : 0.f, t < a.ntaps ? __ldg(wp + a.cout_pad) : 0.f);
+        bf[t][nn][h] = *reinterpret_cast<const uint32_t*>(&b2);
+      }
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(a.in);
+  const long long M = (long long)a.n * a.hog * a.wog;
+  const int hw = a.hog * a.wog;
+  const long long warp0 = ((long long)blockIdx.x * 4 + (threadIdx.x >> 5)) * 32;
+  for (long long m0 = warp0; m0 < M; m0 += (long long)gridDim.x * 128) {
+    float acc[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) acc[mt][nn][0] = acc[mt][nn][1] = acc[mt][nn][2] = acc[mt][nn][3] = 0.f;
+    // the 4 pixels this lane touches: rows gq, gq+8 of both m-tiles
+    int pn[4], py[4], px[4]; bool pv[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const long long m = m0 + (r >> 1) * 16 + (r & 1) * 8 + gq;
+      pv[r] = m < M;
+      const long long mm = pv[r] ? m : 0;
+      pn[r] = (int)(mm / hw);
+      const int rr = (int)(mm - (long long)pn[r] * hw);
+      py[r] = rr / a.wog; px[r] = rr % a.wog;
+    }
+#pragma unroll
+    for (int t = 0; t < NTAPS; ++t) {
+      if (t < a.ntaps) {
+        uint32_t af[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int iy = py[r] * a.in_sy + a.dy[t], ix = px[r] * a.in_sx + a.dx[t];
+          const bool ok = pv[r] && iy >= 0 && iy < a.hin && ix >= 0 && ix < a.win;
+          const uint32_t* p = reinterpret_cast<const uint32_t*>(in + (((long long)pn[r] * a.hin + iy) * a.win + ix) * a.in_cstride + a.in_coff) + tq;
+          af[r][0] = ok ? __ldg(p) : 0u;        // channels 2tq, 2tq+1
+          af[r][1] = ok ? __ldg(p + 4) : 0u;    // channels 2tq+8, 2tq+9
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nn = 0; nn < 2; ++nn)
+            mma_16816(acc[mt][nn], af[mt * 2][0], af[mt * 2 + 1][0], af[mt * 2][1], af[mt * 2 + 1][1], bf[t][nn][0], bf[t][nn][1]);
+      }
+    }
+    // epilogue: C fragment = (row gq | gq+8, cols 8nn + 2tq, +1)
+    TOut* out = reinterpret_cast<TOut*>(a.out);
+    const TOut* res = reinterpret_cast<const TOut*>(a.res);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (!pv[r]) continue;
+      const int oy = py[r] * a.out_sy + a.out_oy, ox = px[r] * a.out_sx + a.out_ox;
+      if (oy >= a.hout || ox >= a.wout) continue;
+      const long long pix = ((long long)pn[r] * a.hout + oy) * a.wout + ox;
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = co0 + nn * 8 + 2 * tq + e;
+          if (c >= a.cout) continue;
+          float x = acc[r >> 1][nn][(r & 1) * 2 + e];
+          if (a.bias) x += __ldg(a.bias + c);
+          if (a.pre_relu) x = fmaxf(x, 0.f);
+          if (a.scale) x = fmaf(x, __ldg(a.scale + c), __ldg(a.shift + c));
+          if (res) x += to_f32<TOut>(res[pix * a.res_cstride + a.res_coff + c]);
+          if (a.post_relu) x = fmaxf(x, 0.f);
+          if (a.sigmoid) x = 1.f / (1.f + expf(-x));
+          out[pix * a.out_cstride + a.out_coff + c] = from_f32<TOut>(x);
+        }
+      }
+    }
+  }
+}
+
 template <typename TIn, typename TOut>
 static int launch_conv(const ConvArgs& a, cudaStream_t st) {
   const long long M = (long long)a.n * a.hog * a.wog;
+  if constexpr (std::is_same<TIn, __nv_bfloat16>::value) {
+    if (a.cin == 16 && a.ntaps <= 9 && a.in_coff % 2 == 0 && a.in_cstride % 2 == 0) {   // tensor-core path for 16-channel layers
+      dim3 grid(min(ceil_div(M, 128), kNumSMs * 16), a.cout_pad / 16);
+      if (a.ntaps <= 3) conv_c16_mma_kernel<TOut, 3><<<grid, 128, 0, st>>>(a);
+      else if (a.ntaps <= 4) conv_c16_mma_kernel<TOut, 4><<<grid, 128, 0, st>>>(a);
+      else conv_c16_mma_kernel<TOut, 9><<<grid, 128, 0, st>>>(a);
+      LAVB_LAUNCH_OK();
+      return 0;
+    }
+  }
   if (a.cin <= 16) {
     dim3 grid(ceil_div(M, 256), a.cout_pad / 16);
     const size_t smem = (size_t)a.ntaps * 16 * 16 * sizeof(float);

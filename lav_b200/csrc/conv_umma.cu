@@ -30,7 +30,7 @@ struct UmmaArgs {
   int hout, wout, cin, cout, kchunks, ntaps, stages, tmem_cols;
   int in_sy, in_sx, out_sy, out_sx, out_oy, out_ox;
   int out_cstride, out_coff, out_is_f32, res_cstride, res_coff;
-  int pre_relu, post_relu, sigmoid, d2s_nout;
+  int pre_relu, post_relu, sigmoid, d2s_nout, cout_store;
   int dy[kMaxTaps], dx[kMaxTaps];
   void* out; const __nv_bfloat16* res;
   const float* bias; const float* scale; const float* shift;
@@ -133,9 +133,10 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : 1) c
   }
   for (int c = threadIdx.x; c < p.cout; c += blockDim.x) {
     // epi(a) = max(a + b, lo) * s + t.  Without the pre-ReLU the bias folds into the shift: (a + b) s + t = a s + (b s + t)
-    const float b = p.bias ? __ldg(p.bias + c) : 0.f;
-    const float sc = p.scale ? __ldg(p.scale + c) : 1.f;
-    const float sh = p.shift ? __ldg(p.shift + c) : 0.f;
+    const bool real = c < p.cout_store;      // columns past cout_store are MMA padding (never stored)
+    const float b = (p.bias && real) ? __ldg(p.bias + c) : 0.f;
+    const float sc = (p.scale && real) ? __ldg(p.scale + c) : 1.f;
+    const float sh = (p.shift && real) ? __ldg(p.shift + c) : 0.f;
     ep_bias[c] = b;
     ep_st[2 * c] = sc;
     ep_st[2 * c + 1] = kPreBias ? sh : fmaf(b, sc, sh);
@@ -251,7 +252,8 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : 1) c
           } else if (kOutF32) {
             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_cstride + p.out_coff + c0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)
+              if (c0 + 4 * j < p.cout_store) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           } else {
             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cstride + p.out_coff + c0);
 #pragma unroll
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : 1) c
                 const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
                 w[e] = *reinterpret_cast<const uint32_t*>(&b2);
               }
-              op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+              if (c0 + 8 * j < p.cout_store) op[j] = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
         }
@@ -301,7 +303,9 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   LAVB_CHECK_ARG(d->out_dtype == LAVB_BF16 || d->out_dtype == LAVB_F32, "conv_umma: bad output dtype");
   LAVB_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= kMaxTaps, "conv_umma: ntaps must be 1..16");
   LAVB_CHECK_ARG(d->cin % 64 == 0 && d->cin > 0, "conv_umma: cin must be a multiple of 64 (got %d)", d->cin);
-  LAVB_CHECK_ARG(d->cout % 32 == 0 && d->cout >= 32 && d->cout <= 256, "conv_umma: cout must be 32..256, multiple of 32 (got %d)", d->cout);
+  LAVB_CHECK_ARG(d->cout % 8 == 0 && d->cout >= 8 && d->cout <= 256, "conv_umma: cout must be 8..256, multiple of 8 (got %d)", d->cout);
+  const int cout_mma = (d->cout + 31) / 32 * 32;      // MMA width; d->w holds cout_mma rows per tap (zero rows past cout)
+  LAVB_CHECK_ARG(d->res == nullptr || cout_mma == d->cout, "conv_umma: residual needs cout %% 32 == 0");
   LAVB_CHECK_ARG(d->in_cstride % 8 == 0 && d->in_coff % 8 == 0 && d->in_coff + d->cin <= d->in_cstride, "conv_umma: input slice misaligned");
   LAVB_CHECK_ARG(d->out_cstride % 8 == 0 && d->out_coff % 8 == 0 && d->out_coff + d->cout <= d->out_cstride, "conv_umma: output slice misaligned");
   LAVB_CHECK_ARG(d->res == nullptr || (d->res_dtype == LAVB_BF16 && d->res_cstride % 8 == 0 && d->res_coff % 8 == 0), "conv_umma: residual must be bf16, 16 B aligned");
@@ -324,9 +328,9 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
     LAVB_CHECK_ARG(r == CUDA_SUCCESS, "conv_umma: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)d->cin, (cuuint64_t)d->ntaps * d->cout};
+    cuuint64_t dims[2] = {(cuuint64_t)d->cin, (cuuint64_t)d->ntaps * cout_mma};
     cuuint64_t strides[1] = {(cuuint64_t)d->cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)d->cout};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)cout_mma};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<float*>(d->w), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -338,12 +342,13 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   a.n = d->n; a.hog = d->hog; a.wog = d->wog;
   a.tiles_x = ceil_div(d->wog, kTileW); a.tiles_y = ceil_div(d->hog, kTileH);
   a.num_tiles = a.n * a.tiles_x * a.tiles_y;
-  a.hout = d->hout; a.wout = d->wout; a.cin = d->cin; a.cout = d->cout; a.kchunks = d->cin / kBlockK; a.ntaps = d->ntaps;
-  const int stage_bytes = kABytes + d->cout * kBlockK * 2;
-  const bool two_per_sm = d->cout <= 128;            // narrow layers: 2 CTAs / SM, each with half the smem ring
+  a.hout = d->hout; a.wout = d->wout; a.cin = d->cin; a.cout = cout_mma; a.cout_store = d->cout; a.kchunks = d->cin / kBlockK;
+  a.ntaps = d->ntaps;
+  const int stage_bytes = kABytes + cout_mma * kBlockK * 2;
+  const bool two_per_sm = cout_mma <= 128;            // narrow layers: 2 CTAs / SM, each with half the smem ring
   a.stages = two_per_sm ? min(kMaxStages, (100 * 1024) / stage_bytes) : min(kMaxStages, (196 * 1024) / stage_bytes);
   int cols = 32;
-  while (cols < 2 * d->cout) cols <<= 1;
+  while (cols < 2 * cout_mma) cols <<= 1;
   a.tmem_cols = cols;
   a.in_sy = d->in_sy; a.in_sx = d->in_sx; a.out_sy = d->out_sy; a.out_sx = d->out_sx; a.out_oy = d->out_oy; a.out_ox = d->out_ox;
   a.out_cstride = d->out_cstride; a.out_coff = d->out_coff; a.out_is_f32 = d->out_dtype == LAVB_F32;

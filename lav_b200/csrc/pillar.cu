@@ -416,9 +416,6 @@ __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
 
   const int nt = (*total_kept + kRows - 1) / kRows;
   if ((int)blockIdx.x >= nt) return;
-  const int row_begin = tile_start[blockIdx.x], row_end = tile_start[blockIdx.x + 1];
-  if (row_begin >= row_end) return;
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < F * H; i += kRows) w1s[(i % F) * H + i / F] = __ldg(w1 + i);                 // w1 is [64][F]
   for (int i = tid; i < H * H; i += kRows) w2s[i] = __float2bfloat16_rn(__ldg(w2 + i));             // w2 is [64 n][64 k]
@@ -437,6 +434,10 @@ __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
         bfrag[kk][nn][1] = *reinterpret_cast<const uint32_t*>(wp + 8);
       }
   }
+  // persistent: the block walks windows blockIdx.x, +gridDim.x, ... so the weights above are staged once per block
+  for (int win = blockIdx.x; win < nt; win += gridDim.x) {
+  const int row_begin = tile_start[win], row_end = tile_start[win + 1];
+  if (row_begin >= row_end) continue;
   float run_max = 0.f;      // channel-thread state of the row walk (threads 0..63)
   int run_cell = -1;
 
@@ -543,6 +544,7 @@ __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
       reinterpret_cast<float*>(canvas)[(long long)run_cell * H + tid] = run_max;
     }
   }
+  }   // window loop
 }
 
 struct SortedWs {
@@ -709,7 +711,7 @@ extern "C" int lavb_pillar_forward_sorted(const float* d_pts, int pt_stride, int
     LAVB_CUDA_OK(cudaFuncSetAttribute(pillar_encode_sorted_kernel<11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     configured = true;
   }
-  const int ntiles = ceil_div(total, kRows);
+  const int ntiles = min(ceil_div(total, kRows), kNumSMs * 3);     // persistent: 3 resident blocks per SM
   if (out_mode == 0)
     pillar_encode_sorted_kernel<11, false><<<ntiles, kRows, smem, st>>>(d_pts, pt_stride, clouds, g, w.stats, w.order, w.ocell,
                                                                         w.tile_start, w.total, d_w1, d_s1, d_t1, d_w2, d_s2, d_t2, d_canvas);

@@ -77,10 +77,14 @@ class TapConv:
         for ph in self.phases:
             assert len(ph["taps"]) <= 16, "tap list longer than the kernel's table"
         # tcgen05 path (bf16 activations): weights [ntaps][cout][cin] bf16, K contiguous
-        self.umma_ok = USE_UMMA and self.cin_k % 64 == 0 and self.cout % 32 == 0 and self.cout <= 256
+        # (cout that is a multiple of 8 but not of 32 is zero-padded to the MMA width; only the real channels are stored)
+        self.umma_ok = USE_UMMA and self.cin_k % 64 == 0 and self.cout % 8 == 0 and self.cout <= 256
         if self.umma_ok:
+            cm = (self.cout + 31) // 32 * 32
             for ph in self.phases:
-                ph["w_umma"] = ph["w"][:, :, :self.cout].permute(0, 2, 1).contiguous().to(torch.bfloat16)
+                wu = torch.zeros((len(ph["taps"]), cm, self.cin_k), dtype=torch.bfloat16, device=ph["w"].device)
+                wu[:, :self.cout] = ph["w"][:, :, :self.cout].permute(0, 2, 1).to(torch.bfloat16)
+                ph["w_umma"] = wu.contiguous()
 
     def _block(self, w_ci_co):
         if self.cin_k == self.cin:
@@ -106,7 +110,7 @@ class TapConv:
             osy, osx = ph["out_s"]
             ooy, oox = ph["out_o"]
             hog, wog = (hout - ooy + osy - 1) // osy, (wout - oox + osx - 1) // osx
-            umma = (self.umma_ok and x.dtype == torch.bfloat16 and (res is None or res.dtype == torch.bfloat16)
+            umma = (self.umma_ok and x.dtype == torch.bfloat16 and (res is None or (res.dtype == torch.bfloat16 and self.cout % 32 == 0))
                     and (UMMA_STRIDED or ph["in_s"] == (1, 1)))
             ops.conv_taps(x, self.cin_k, in_coff, out, self.cout, out_coff, hog, wog, ph["in_s"], ph["out_s"], ph["out_o"],
                           ph["taps"], ph["w_umma"] if umma else ph["w"], self.bias, self.scale, self.shift, res, res_coff,

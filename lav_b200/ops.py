@@ -187,7 +187,7 @@ def conv_taps(x, cin, in_coff, out, cout, out_coff, hog, wog, in_s, out_s, out_o
     d.out_oy, d.out_ox = out_o
     d.ntaps = len(taps)
     if umma:
-        assert w.dtype == torch.bfloat16 and tuple(w.shape) == (len(taps), cout, cin) and x.dtype == torch.bfloat16
+        assert w.dtype == torch.bfloat16 and tuple(w.shape) == (len(taps), (cout + 31) // 32 * 32, cin) and x.dtype == torch.bfloat16
     else:
         assert w.dtype == torch.float32 and tuple(w.shape) == (len(taps), cin, (cout + 15) // 16 * 16)
     for i, (dy, dx) in enumerate(taps):

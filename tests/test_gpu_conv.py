@@ -126,6 +126,7 @@ def test_erfnet_matches_oracle(cuda, weights, golden_dir):
     dict(cin=128, cout=128, k=(4, 4), p=(1, 1), d=(1, 1), hw=(20, 24), t=True, s=2, op=0),
     dict(cin=128, cout=128, k=(4, 4), p=(1, 1), d=(1, 1), hw=(10, 10), t=True, s=4, op=2),
     dict(cin=64, cout=128, k=(1, 1), p=(0, 0), d=(1, 1), hw=(24, 32), t=True, s=1, op=0),
+    dict(cin=64, cout=16, k=(3, 3), p=(1, 1), d=(1, 1), hw=(20, 24), t=True, s=2, op=1, nores=True),   # cout padded to the MMA width
     dict(cin=64, cout=64, k=(3, 3), p=(1, 1), d=(1, 1), hw=(32, 64), cs=2),           # strided conv: TMA element strides
     dict(cin=64, cout=128, k=(3, 3), p=(1, 1), d=(1, 1), hw=(40, 36), cs=2),
 ])
@@ -147,19 +148,21 @@ def test_umma_conv_vs_torch(cuda, cfg):
         s = cfg.get("cs", 1)
         y = F.conv2d(x, w, b, s, cfg["p"], cfg["d"])
     res = torch.randn(y.shape, generator=g).bfloat16().float()
+    if cfg.get("nores"):
+        res = torch.zeros_like(res)
     want = F.relu(F.relu(y) * sc[None, :, None, None] + sh[None, :, None, None] + res)
     assert layers.USE_UMMA
     layer = TapConv(w.to(cuda), t, s, cfg["p"], cfg["d"], cfg.get("op", 0), bias=b.to(cuda), pre_relu=True,
                     scale=sc.to(cuda), shift=sh.to(cuda), post_relu=True)
     assert layer.umma_ok
     xin = x.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16()
-    rin = res.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16()
+    rin = None if cfg.get("nores") else res.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16()
     got32 = layer(xin, res=rin, out_dtype=torch.float32).cpu().permute(0, 3, 1, 2)
     assert util.rel_err(got32, want) < 2e-5          # fp32 output: only accumulation-order noise
     got16 = layer(xin, res=rin).float().cpu().permute(0, 3, 1, 2)
     assert util.rel_err(got16, want) < 6e-3          # bf16 output rounding
     # linearity in the input batch: concatenating images must not mix them (tile scheduler / TMA image coordinate)
-    one = layer(xin[1:2].contiguous(), res=rin[1:2].contiguous(), out_dtype=torch.float32).cpu()
+    one = layer(xin[1:2].contiguous(), res=None if rin is None else rin[1:2].contiguous(), out_dtype=torch.float32).cpu()
     assert torch.equal(one, layer(xin, res=rin, out_dtype=torch.float32).cpu()[1:2])
 
 

@@ -37,7 +37,7 @@ def test_train_forward_backward_matches_reference_golden(cuda, golden_dir):
         if n0 < 1e-3:        # e.g. the Linear bias in front of a batch-stat BatchNorm: its true gradient is 0, the rest is noise
             continue
         r = torch.randn(g.shape, generator=synth._gen(13, "dg:" + k))
-        shallow = ".net.2." in k or ".net.3." in k
+        shallow = "_head.net.2." in k or "_head.net.3." in k
         assert abs(float(g.norm()) / n0 - 1) < (1e-4 if shallow else 1e-2), (k, float(g.norm()), n0)
         assert abs(float((g * r).sum()) - p0) / n0 < (2e-4 if shallow else 3e-2), (k, float((g * r).sum()), p0, n0)
     grads = dict(m.named_parameters())
