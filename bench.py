@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=32, help="agent frames per step per GPU")
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--pipelines", type=int, default=2, help="agent groups per GPU that overlap host decode with GPU work")

@@ -15,6 +15,8 @@ import torch
 from . import ops
 from .model_inference import InferModel
 
+UMMA_TRUNKS = False   # ResNet-18 trunks (brake / planner embedder) on the tcgen05 conv kernel: correct (tested) but measured 5-20%
+                      # slower than the BN-folded cuDNN path on these small maps (B200, B=32), so cuDNN stays the default
 NUM_REPEAT = 4
 GAP = NUM_REPEAT + 1          # lav_agent_fast.py:31-32
 NUM_FRAME_STACK = 2           # team_code_v2/config.yaml: num_frame_stack
@@ -76,9 +78,11 @@ class FramePipeline:
         dt = torch.bfloat16 if precision == "bf16" else torch.float32
         emb = self.infer_model.uniplanner.lidar_conv_emb
         emb.to(dt).to(memory_format=torch.channels_last)
+        emb[0].use_umma_trunk = (precision == "bf16") and UMMA_TRUNKS
         if self.bra_model is not None:
             self.bra_model.conv_backbone.to(dt).to(memory_format=torch.channels_last)
             self.bra_model.attn1.to(dt); self.bra_model.attn2.to(dt)
+            self.bra_model.conv_backbone.use_umma_trunk = (precision == "bf16") and UMMA_TRUNKS
         return self
 
     @torch.no_grad()

@@ -73,4 +73,18 @@ template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16*
   *reinterpret_cast<uint2*>(p) = r;
 }
 
+// 2 consecutive elements (pointer 8 B aligned for float, 4 B for bf16)
+template <typename T> __device__ __forceinline__ float2 load2(const T* p);
+template <> __device__ __forceinline__ float2 load2<float>(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+template <> __device__ __forceinline__ float2 load2<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(p));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r));
+}
+template <typename T> __device__ __forceinline__ void store2(T* p, float a, float b);
+template <> __device__ __forceinline__ void store2<float>(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+template <> __device__ __forceinline__ void store2<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<const uint32_t*>(&v);
+}
+
 }  // namespace lavb

@@ -332,6 +332,20 @@ __global__ void __launch_bounds__(128) conv_c16_mma_kernel(const __grid_constant
         const __nv_bfloat162 b2 = __floats2bfloat162_rn(t < a.ntaps ? __ldg(wp) : 0.f, t < a.ntaps ? __ldg(wp + a.cout_pad) : 0.f);
         bf[t][nn][h] = *reinterpret_cast<const uint32_t*>(&b2);
       }
+  float e_bias[2][2], e_scale[2][2], e_shift[2][2];
+#pragma unroll
+  for (int nn = 0; nn < 2; ++nn)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = co0 + nn * 8 + 2 * tq + e;
+      const bool in_range = c < a.cout;
+      e_bias[nn][e] = (a.bias && in_range) ? __ldg(a.bias + c) : 0.f;
+      e_scale[nn][e] = (a.scale && in_range) ? __ldg(a.scale + c) : 1.f;
+      e_shift[nn][e] = (a.shift && in_range) ? __ldg(a.shift + c) : 0.f;
+    }
+  const float lo_pre = a.pre_relu ? 0.f : -INFINITY, lo_post = a.post_relu ? 0.f : -INFINITY;
+  // 2-element vector access needs even channel offsets / strides
+  const bool pair_ok = (a.out_coff % 2 == 0) && (a.out_cstride % 2 == 0) && (a.res == nullptr || (a.res_coff % 2 == 0 && a.res_cstride % 2 == 0));
   const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(a.in);
   const long long M = (long long)a.n * a.hog * a.wog;
   const int hw = a.hog * a.wog;
@@ -372,7 +386,7 @@ __global__ void __launch_bounds__(128) conv_c16_mma_kernel(const __grid_constant
             mma_16816(acc[mt][nn], af[mt * 2][0], af[mt * 2 + 1][0], af[mt * 2][1], af[mt * 2 + 1][1], bf[t][nn][0], bf[t][nn][1]);
       }
     }
-    // epilogue: C fragment = (row gq | gq+8, cols 8nn + 2tq, +1)
+    // epilogue: C fragment = (row gq | gq+8, cols 8nn + 2tq, +1); the lane's 4 columns' parameters sit in registers
     TOut* out = reinterpret_cast<TOut*>(a.out);
     const TOut* res = reinterpret_cast<const TOut*>(a.res);
 #pragma unroll
@@ -381,21 +395,24 @@ __global__ void __launch_bounds__(128) conv_c16_mma_kernel(const __grid_constant
       const int oy = py[r] * a.out_sy + a.out_oy, ox = px[r] * a.out_sx + a.out_ox;
       if (oy >= a.hout || ox >= a.wout) continue;
       const long long pix = ((long long)pn[r] * a.hout + oy) * a.wout + ox;
+      TOut* op = out + pix * a.out_cstride + a.out_coff;
+      const TOut* rp = res ? res + pix * a.res_cstride + a.res_coff : nullptr;
 #pragma unroll
       for (int nn = 0; nn < 2; ++nn) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int c = co0 + nn * 8 + 2 * tq + e;
-          if (c >= a.cout) continue;
-          float x = acc[r >> 1][nn][(r & 1) * 2 + e];
-          if (a.bias) x += __ldg(a.bias + c);
-          if (a.pre_relu) x = fmaxf(x, 0.f);
-          if (a.scale) x = fmaf(x, __ldg(a.scale + c), __ldg(a.shift + c));
-          if (res) x += to_f32<TOut>(res[pix * a.res_cstride + a.res_coff + c]);
-          if (a.post_relu) x = fmaxf(x, 0.f);
-          if (a.sigmoid) x = 1.f / (1.f + expf(-x));
-          out[pix * a.out_cstride + a.out_coff + c] = from_f32<TOut>(x);
+        const int c = co0 + nn * 8 + 2 * tq;
+        if (c >= a.cout) continue;
+        float x0 = acc[r >> 1][nn][(r & 1) * 2] + e_bias[nn][0], x1 = acc[r >> 1][nn][(r & 1) * 2 + 1] + e_bias[nn][1];
+        x0 = fmaf(fmaxf(x0, lo_pre), e_scale[nn][0], e_shift[nn][0]);
+        x1 = fmaf(fmaxf(x1, lo_pre), e_scale[nn][1], e_shift[nn][1]);
+        const bool pair = pair_ok && (c + 1 < a.cout);
+        if (rp) {
+          if (pair) { const float2 rr = load2<TOut>(rp + c); x0 += rr.x; x1 += rr.y; }
+          else { x0 += to_f32<TOut>(rp[c]); if (c + 1 < a.cout) x1 += to_f32<TOut>(rp[c + 1]); }
         }
+        x0 = fmaxf(x0, lo_post); x1 = fmaxf(x1, lo_post);
+        if (a.sigmoid) { x0 = 1.f / (1.f + expf(-x0)); x1 = 1.f / (1.f + expf(-x1)); }
+        if (pair) store2<TOut>(op + c, x0, x1);
+        else { op[c] = from_f32<TOut>(x0); if (c + 1 < a.cout) op[c + 1] = from_f32<TOut>(x1); }
       }
     }
   }

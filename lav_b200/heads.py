@@ -90,6 +90,14 @@ class ResNet18(nn.Module):
         w, b = f["stem"]
         x = torch.cudnn_convolution_relu(x, w, b, (2, 2), (3, 3), (1, 1), 1)
         x = self.maxpool(x)
+        if getattr(self, "use_umma_trunk", False) and dt == torch.bfloat16:
+            # layer1..4 on the lav_b200 tcgen05 conv kernel (BN / residual / ReLU fused in its epilogue)
+            key = ("umma", str(x.device))
+            cache = self.__dict__.setdefault("_fold_cache", {})
+            if key not in cache:
+                from .resnet_umma import ResNetTrunkUMMA
+                cache[key] = ResNetTrunkUMMA(self)
+            return cache[key](x.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2)
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(self, f"layer{li}")):
                 st = blk.conv1.stride
