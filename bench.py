@@ -277,22 +277,36 @@ def main():
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     roof = {}
-    for kind, bound, unit, peak_key in (("umma", "tensor", "TFLOP/s", "bf16_tflops_sustained"), ("pillar", "hbm", "GB/s", "hbm_gbs")):
-        rows = [(w, a.elapsed_time(b)) for k, w, a, b in prof if k == kind]
-        if not rows:
-            continue
-        work, tms = sum(r[0] for r in rows), sum(r[1] for r in rows)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        peak = peaks.get(peak_key, 1590.0 if kind == "umma" else 6650.0)
-        ach = work / (tms * 1e-3) / (1e12 if kind == "umma" else 1e9)
-        roof[kind] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
-                      "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "launches": len(rows),
-                      "avg_launch_us": 1e3 * tms / len(rows)}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
 
+    def entry(rows, bound, unit, peak, scale):
+        work, tms = sum(r[0] for r in rows), sum(r[1] for r in rows)
+        ach = work / (tms * 1e-3) / scale
+        return {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None, "peak_source": src,
+                "launches": len(rows), "avg_launch_us": 1e3 * tms / len(rows)}
+    umma = {}
+    for k, w, a, b in prof:
+        if k.startswith("umma:"):
+            umma.setdefault(k[5:], []).append((w, a.elapsed_time(b)))
+    if umma:
+        tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        dom = max(umma, key=lambda k: sum(r[1] for r in umma[k]))          # launch shape with the largest share of the step
+        roof["umma"] = entry(umma[dom], "tensor", "TFLOP/s", tf_peak, 1e12)
+        roof["umma"]["kernel"] = "conv_umma_kernel " + dom
+        # DRAM bytes of this launch shape from the committed ncu --set full capture (profiles/r01_kernels.md §1:
+        # 225.5 MB for 8 frames), scaled to the frames one launch processes here
+        roof["umma"]["traffic"] = 225.5e6 / 8 * Bp if dom.startswith("384->256") else None
+        roof["umma_all"] = entry([r for v in umma.values() for r in v], "tensor", "TFLOP/s", tf_peak, 1e12)
+    pil = [(w, a.elapsed_time(b)) for k, w, a, b in prof if k == "pillar"]
+    if pil:
+        roof["pillar"] = entry(pil, "hbm", "GB/s", peaks.get("hbm_gbs", 6650.0), 1e9)
+        roof["pillar"]["kernel"] = "pillar encoder (count, scan+zero-fill, fill, encode)"
+        roof["pillar"]["traffic"] = 663e6 / 16 * Bp                          # profiles/r01_kernels.md §3
     if rank == 0:
         frames = world * B * args.steps
         line = {"metric": "agent_frames_per_s", "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -302,7 +316,7 @@ def main():
                         "h2d_bytes_per_step": int(h_rgbs.numel() + h_tels.numel() + h_lidar.numel() * 4),
                         "d2h_bytes_per_step": int(B * 20 * 2 * 4 + B * 4)},
                 "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": roof.get("umma"), "roofline_pillar": roof.get("pillar")}
+                "roofline": roof.get("umma"), "roofline_conv_all": roof.get("umma_all"), "roofline_pillar": roof.get("pillar")}
         if not args.no_cpu_baseline:
             a2 = argparse.Namespace(**vars(args))
             a2.steps, a2.warmup = 3, 1

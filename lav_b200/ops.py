@@ -203,7 +203,7 @@ def conv_taps(x, cin, in_coff, out, cout, out_coff, hog, wog, in_s, out_s, out_o
     if umma:
         e0 = _prof_begin()
         check(lib().lavb_conv_umma(C.byref(d), _stream()), "lavb_conv_umma")
-        _prof_end("umma", 2.0 * x.shape[0] * hog * wog * cout * cin * len(taps), e0)
+        _prof_end(f"umma:{cin}->{cout}x{len(taps)}taps@{hog}x{wog}", 2.0 * x.shape[0] * hog * wog * cout * cin * len(taps), e0)
     else:
         check(lib().lavb_conv_taps(C.byref(d), _stream()), "lavb_conv_taps")
     _COUNT[0] += 1
