@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=32, help="agent frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=64, help="agent frames per step per GPU")
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--pipelines", type=int, default=2, help="agent groups per GPU that overlap host decode with GPU work")
@@ -192,6 +192,7 @@ def main():
     from lav_b200 import capi, ops, synth
     from lav_b200.agent import StaticFramePipeline
     capi.lib()
+    torch.backends.cudnn.benchmark = bool(int(os.environ.get("LAVB_CUDNN_BENCHMARK", "0")))   # cuDNN autotune measured slower here (1863 vs 1987 frames/s): off
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -295,13 +296,17 @@ def main():
             umma.setdefault(k[5:], []).append((w, a.elapsed_time(b)))
     if umma:
         tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        dom = max(umma, key=lambda k: sum(r[1] for r in umma[k]))          # launch shape with the largest share of the step
-        roof["umma"] = entry(umma[dom], "tensor", "TFLOP/s", tf_peak, 1e12)
-        roof["umma"]["kernel"] = "conv_umma_kernel " + dom
-        # DRAM bytes of this launch shape from the committed ncu --set full capture (profiles/r01_kernels.md §1:
-        # 225.5 MB for 8 frames), scaled to the frames one launch processes here
-        roof["umma"]["traffic"] = 225.5e6 / 8 * Bp if dom.startswith("384->256") else None
-        roof["umma_all"] = entry([r for v in umma.values() for r in v], "tensor", "TFLOP/s", tf_peak, 1e12)
+        # headline: conv_umma_kernel over ALL its launches of a tick (ERFNet, backbone, heads: ~110 launches, 9 shapes)
+        roof["umma"] = entry([r for v in umma.values() for r in v], "tensor", "TFLOP/s", tf_peak, 1e12)
+        roof["umma"]["kernel"] = "conv_umma_kernel (all launches of a tick)"
+        # its largest single launch, the fused 4-head conv 384->256: DRAM bytes from the committed ncu --set full
+        # capture (profiles/r01_kernels.md §1: 225.5 MB for 8 frames, tensor pipe 83.7 %), scaled to the frames per launch
+        hk = [k for k in umma if k.startswith("384->256")]
+        if hk:
+            roof["umma_all"] = entry(umma[hk[0]], "tensor", "TFLOP/s", tf_peak, 1e12)
+            roof["umma_all"]["kernel"] = "conv_umma_kernel " + hk[0]
+            roof["umma_all"]["traffic"] = 225.5e6 / 8 * Bp
+            roof["umma_all"]["ncu_tensor_pipe_pct"] = 83.7
     pil = [(w, a.elapsed_time(b)) for k, w, a, b in prof if k == "pillar"]
     if pil:
         roof["pillar"] = entry(pil, "hbm", "GB/s", peaks.get("hbm_gbs", 6650.0), 1e9)
@@ -316,7 +321,7 @@ def main():
                         "h2d_bytes_per_step": int(h_rgbs.numel() + h_tels.numel() + h_lidar.numel() * 4),
                         "d2h_bytes_per_step": int(B * 20 * 2 * 4 + B * 4)},
                 "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": roof.get("umma"), "roofline_conv_all": roof.get("umma_all"), "roofline_pillar": roof.get("pillar")}
+                "roofline": roof.get("umma"), "roofline_heads_conv": roof.get("umma_all"), "roofline_pillar": roof.get("pillar")}
         if not args.no_cpu_baseline:
             a2 = argparse.Namespace(**vars(args))
             a2.steps, a2.warmup = 3, 1

@@ -158,6 +158,16 @@ int lavb_pool2_affine_relu(const void* d_in, int dtype, int n, int hin, int win,
 int lavb_rgb_normalize(const void* d_rgb, int src_is_u8_nhwc, int n, int h, int w, void* d_out, int out_dtype,
                        void* stream);
 
+/* ---------------------------------------------------------------- detection decode (device part)
+ * replaces: extract_peak (team_code_v2/model_inference.py:189-202: sigmoid, 7x7 max-pool NMS, top-k) and the per-peak
+ * map reads of det_inference (:100-112).  d_center: heat-map LOGITS, d_box / d_ori: size / orientation maps, all fp32
+ * NHWC [batch][h][w][2] (ncls = 2 classes in d_center).  Only local maxima with sigmoid > min_score are kept (anything
+ * else is dropped by the reference's host filter anyway); per (frame, class) the max_det best go to
+ * d_packed [batch][7][ncls*max_det] = score | flat index | w | h | cos | sin | W, -1e5 scores padding the rest. */
+size_t lavb_det_peaks_workspace_bytes(int batch, int ncls);
+int lavb_det_peaks(const float* d_center, const float* d_box, const float* d_ori, int batch, int h, int w, int ncls,
+                   float min_score, int max_det, float* d_packed, void* d_workspace, void* stream);
+
 /* ---------------------------------------------------------------- rotated bilinear crop
  * replaces: UniPlanner.crop_feature (team_code_v2/models/uniplanner.py:303-340; model_inference.py:204-238) =
  *           F.affine_grid(theta, align_corners=True) + F.grid_sample(bilinear, zeros padding, align_corners=True).

@@ -15,6 +15,7 @@ import torch
 from . import ops
 from .model_inference import InferModel
 
+FORK_BRAKE = True     # run the brake predictor as a parallel branch of the perception graph
 UMMA_TRUNKS = False   # ResNet-18 trunks (brake / planner embedder) on the tcgen05 conv kernel: correct (tested) but measured 5-20%
                       # slower than the BN-folded cuDNN path on these small maps (B200, B=32), so cuDNN stays the default
 NUM_REPEAT = 4
@@ -206,19 +207,32 @@ class StaticFramePipeline(FramePipeline):
     def _g1_body(self):
         B, N = self.B, self.N
         im = self.infer_model
+        # the brake predictor only needs the camera frames: fork it onto a side stream so its (cuDNN) kernels fill the
+        # tails of the perception kernels; inside a captured graph this becomes a parallel branch
+        bra, side = None, None
+        if self.bra_model is not None and FORK_BRAKE:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                bra = self._brake()
         logits = self.seg_model.forward_nhwc(self.rgbs.view(B * 3, 288, 256, 3))
         logits = logits.view(B, 3, *logits.shape[1:]).permute(0, 1, 4, 2, 3)
         ops.paint_batched(self.lidar, logits, self._cams, 2, 4, self.cur)
         ops.stack_jobs(self.jobs_dev, B * self.T, N, 8, self.T)
         feats, center, box, ori, seg = im.lidar_model.forward_nhwc(self.stacked, [self.T * N] * B)
-        heat = torch.sigmoid(center.permute(0, 3, 1, 2))
-        packed = im.pack_peaks(heat, box.permute(0, 3, 1, 2), ori.permute(0, 3, 1, 2))
-        bra = None
-        if self.bra_model is not None:
-            wide = self.rgbs.permute(0, 2, 1, 3, 4).reshape(B, 288, 768, 3).permute(0, 3, 1, 2).float()
-            tel = self.tels.permute(0, 3, 1, 2).float()
-            bra = self.bra_model(wide.contiguous(memory_format=torch.channels_last), tel.contiguous(memory_format=torch.channels_last))
+        packed = ops.det_peaks(center, box, ori)        # sigmoid + 7x7 NMS + top-15 + map reads in two small kernels
+        heat = None
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        elif self.bra_model is not None:
+            bra = self._brake()
         return dict(features=feats, pred_bev=seg.permute(0, 3, 1, 2), packed=packed, pred_bra=bra, heat=heat)
+
+    def _brake(self):
+        B = self.B
+        wide = self.rgbs.permute(0, 2, 1, 3, 4).reshape(B, 288, 768, 3).permute(0, 3, 1, 2).float()
+        tel = self.tels.permute(0, 3, 1, 2).float()
+        return self.bra_model(wide.contiguous(memory_format=torch.channels_last), tel.contiguous(memory_format=torch.channels_last))
 
     def _g2_body(self, K, locs, oris, fidx):
         return self.infer_model.uniplanner.infer_device(self._o1["features"].permute(0, 3, 1, 2), locs, oris, fidx, K, self.nxps, self.cmds)

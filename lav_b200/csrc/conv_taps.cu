@@ -196,6 +196,32 @@ __global__ void __launch_bounds__((BM / TM) * (BN / (4 * NH))) conv_taps_kernel(
 }
 
 template <typename T>
+__global__ void __launch_bounds__(256) pool2_vec4_kernel(const T* __restrict__ in, int n, int hin, int win, int c, int in_cstride,
+                                                         int in_coff, const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, T* __restrict__ out, int out_cstride,
+                                                         int out_coff) {
+  const int ho = hin / 2, wo = win / 2, c4 = c / 4;
+  const long long total = (long long)n * ho * wo * c4;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = (int)(i % c4) * 4;
+  long long p = i / c4;
+  const int ox = (int)(p % wo); p /= wo;
+  const int oy = (int)(p % ho);
+  const int nn = (int)(p / ho);
+  const T* s = in + (((long long)nn * hin + oy * 2) * win + ox * 2) * in_cstride + in_coff + ch;
+  const float4 a = load4<T>(s), b = load4<T>(s + in_cstride), cc = load4<T>(s + (long long)win * in_cstride),
+               d = load4<T>(s + (long long)(win + 1) * in_cstride);
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + ch)), sh = __ldg(reinterpret_cast<const float4*>(shift + ch));
+  float4 y;
+  y.x = fmaxf(fmaf(fmaxf(fmaxf(a.x, b.x), fmaxf(cc.x, d.x)), sc.x, sh.x), 0.f);
+  y.y = fmaxf(fmaf(fmaxf(fmaxf(a.y, b.y), fmaxf(cc.y, d.y)), sc.y, sh.y), 0.f);
+  y.z = fmaxf(fmaf(fmaxf(fmaxf(a.z, b.z), fmaxf(cc.z, d.z)), sc.z, sh.z), 0.f);
+  y.w = fmaxf(fmaf(fmaxf(fmaxf(a.w, b.w), fmaxf(cc.w, d.w)), sc.w, sh.w), 0.f);
+  store4<T>(out + (((long long)nn * ho + oy) * wo + ox) * out_cstride + out_coff + ch, y);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) pool2_kernel(const T* __restrict__ in, int n, int hin, int win, int c, int in_cstride,
                                                     int in_coff, const float* __restrict__ scale,
                                                     const float* __restrict__ shift, T* __restrict__ out, int out_cstride,
@@ -318,8 +344,12 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
 
 template <typename TOut, int NTAPS>
 __global__ void __launch_bounds__(128) conv_c16_mma_kernel(const __grid_constant__ ConvArgs a) {
+  // grid: x = (image, output-grid row), y = 128-pixel segment of that row, z = 16-column chunk -> no per-pixel div/mod
   const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
-  const int co0 = blockIdx.y * 16;
+  const int co0 = blockIdx.z * 16;
+  const int img = blockIdx.x / a.hog, gy = blockIdx.x - img * a.hog;
+  const int gx0 = blockIdx.y * 128 + (threadIdx.x >> 5) * 32;
+  if (gx0 >= a.wog) return;
   // B fragments of this 16-column chunk: b0 = W[tap][k = 2tq, 2tq+1][n = 8nn + gq], b1 = same with k + 8
   uint32_t bf[NTAPS][2][2];
 #pragma unroll
@@ -344,76 +374,66 @@ __global__ void __launch_bounds__(128) conv_c16_mma_kernel(const __grid_constant
       e_shift[nn][e] = (a.shift && in_range) ? __ldg(a.shift + c) : 0.f;
     }
   const float lo_pre = a.pre_relu ? 0.f : -INFINITY, lo_post = a.post_relu ? 0.f : -INFINITY;
-  // 2-element vector access needs even channel offsets / strides
   const bool pair_ok = (a.out_coff % 2 == 0) && (a.out_cstride % 2 == 0) && (a.res == nullptr || (a.res_coff % 2 == 0 && a.res_cstride % 2 == 0));
-  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(a.in);
-  const long long M = (long long)a.n * a.hog * a.wog;
-  const int hw = a.hog * a.wog;
-  const long long warp0 = ((long long)blockIdx.x * 4 + (threadIdx.x >> 5)) * 32;
-  for (long long m0 = warp0; m0 < M; m0 += (long long)gridDim.x * 128) {
-    float acc[2][2][4];
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(a.in) + (long long)img * a.hin * a.win * a.in_cstride + a.in_coff + 2 * tq;
+  // the 4 pixels this lane touches: rows gq, gq+8 of both m-tiles
+  int gx[4]; bool pv[4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+  for (int r = 0; r < 4; ++r) { gx[r] = gx0 + (r >> 1) * 16 + (r & 1) * 8 + gq; pv[r] = gx[r] < a.wog; }
+  float acc[2][2][4];
 #pragma unroll
-      for (int nn = 0; nn < 2; ++nn) acc[mt][nn][0] = acc[mt][nn][1] = acc[mt][nn][2] = acc[mt][nn][3] = 0.f;
-    // the 4 pixels this lane touches: rows gq, gq+8 of both m-tiles
-    int pn[4], py[4], px[4]; bool pv[4];
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const long long m = m0 + (r >> 1) * 16 + (r & 1) * 8 + gq;
-      pv[r] = m < M;
-      const long long mm = pv[r] ? m : 0;
-      pn[r] = (int)(mm / hw);
-      const int rr = (int)(mm - (long long)pn[r] * hw);
-      py[r] = rr / a.wog; px[r] = rr % a.wog;
-    }
+    for (int nn = 0; nn < 2; ++nn) acc[mt][nn][0] = acc[mt][nn][1] = acc[mt][nn][2] = acc[mt][nn][3] = 0.f;
 #pragma unroll
-    for (int t = 0; t < NTAPS; ++t) {
-      if (t < a.ntaps) {
-        uint32_t af[4][2];
+  for (int t = 0; t < NTAPS; ++t) {
+    if (t < a.ntaps) {
+      const int iy = gy * a.in_sy + a.dy[t];
+      const bool row_ok = iy >= 0 && iy < a.hin;
+      const __nv_bfloat16* rowp = in + (long long)iy * a.win * a.in_cstride;
+      uint32_t af[4][2];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int iy = py[r] * a.in_sy + a.dy[t], ix = px[r] * a.in_sx + a.dx[t];
-          const bool ok = pv[r] && iy >= 0 && iy < a.hin && ix >= 0 && ix < a.win;
-          const uint32_t* p = reinterpret_cast<const uint32_t*>(in + (((long long)pn[r] * a.hin + iy) * a.win + ix) * a.in_cstride + a.in_coff) + tq;
-          af[r][0] = ok ? __ldg(p) : 0u;        // channels 2tq, 2tq+1
-          af[r][1] = ok ? __ldg(p + 4) : 0u;    // channels 2tq+8, 2tq+9
-        }
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-          for (int nn = 0; nn < 2; ++nn)
-            mma_16816(acc[mt][nn], af[mt * 2][0], af[mt * 2 + 1][0], af[mt * 2][1], af[mt * 2 + 1][1], bf[t][nn][0], bf[t][nn][1]);
+      for (int r = 0; r < 4; ++r) {
+        const int ix = gx[r] * a.in_sx + a.dx[t];
+        const bool ok = row_ok && pv[r] && ix >= 0 && ix < a.win;
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(rowp + (long long)ix * a.in_cstride);
+        af[r][0] = ok ? __ldg(p) : 0u;        // channels 2tq, 2tq+1
+        af[r][1] = ok ? __ldg(p + 4) : 0u;    // channels 2tq+8, 2tq+9
       }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn)
+          mma_16816(acc[mt][nn], af[mt * 2][0], af[mt * 2 + 1][0], af[mt * 2][1], af[mt * 2 + 1][1], bf[t][nn][0], bf[t][nn][1]);
     }
-    // epilogue: C fragment = (row gq | gq+8, cols 8nn + 2tq, +1); the lane's 4 columns' parameters sit in registers
-    TOut* out = reinterpret_cast<TOut*>(a.out);
-    const TOut* res = reinterpret_cast<const TOut*>(a.res);
+  }
+  // epilogue: C fragment = (row gq | gq+8, cols 8nn + 2tq, +1); the lane's 4 columns' parameters sit in registers
+  const int oy = gy * a.out_sy + a.out_oy;
+  if (oy >= a.hout) return;
+  TOut* orow = reinterpret_cast<TOut*>(a.out) + ((long long)img * a.hout + oy) * a.wout * a.out_cstride + a.out_coff;
+  const TOut* rrow = a.res ? reinterpret_cast<const TOut*>(a.res) + ((long long)img * a.hout + oy) * a.wout * a.res_cstride + a.res_coff : nullptr;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (!pv[r]) continue;
-      const int oy = py[r] * a.out_sy + a.out_oy, ox = px[r] * a.out_sx + a.out_ox;
-      if (oy >= a.hout || ox >= a.wout) continue;
-      const long long pix = ((long long)pn[r] * a.hout + oy) * a.wout + ox;
-      TOut* op = out + pix * a.out_cstride + a.out_coff;
-      const TOut* rp = res ? res + pix * a.res_cstride + a.res_coff : nullptr;
+  for (int r = 0; r < 4; ++r) {
+    const int ox = gx[r] * a.out_sx + a.out_ox;
+    if (!pv[r] || ox >= a.wout) continue;
+    TOut* op = orow + (long long)ox * a.out_cstride;
+    const TOut* rp = rrow ? rrow + (long long)ox * a.res_cstride : nullptr;
 #pragma unroll
-      for (int nn = 0; nn < 2; ++nn) {
-        const int c = co0 + nn * 8 + 2 * tq;
-        if (c >= a.cout) continue;
-        float x0 = acc[r >> 1][nn][(r & 1) * 2] + e_bias[nn][0], x1 = acc[r >> 1][nn][(r & 1) * 2 + 1] + e_bias[nn][1];
-        x0 = fmaf(fmaxf(x0, lo_pre), e_scale[nn][0], e_shift[nn][0]);
-        x1 = fmaf(fmaxf(x1, lo_pre), e_scale[nn][1], e_shift[nn][1]);
-        const bool pair = pair_ok && (c + 1 < a.cout);
-        if (rp) {
-          if (pair) { const float2 rr = load2<TOut>(rp + c); x0 += rr.x; x1 += rr.y; }
-          else { x0 += to_f32<TOut>(rp[c]); if (c + 1 < a.cout) x1 += to_f32<TOut>(rp[c + 1]); }
-        }
-        x0 = fmaxf(x0, lo_post); x1 = fmaxf(x1, lo_post);
-        if (a.sigmoid) { x0 = 1.f / (1.f + expf(-x0)); x1 = 1.f / (1.f + expf(-x1)); }
-        if (pair) store2<TOut>(op + c, x0, x1);
-        else { op[c] = from_f32<TOut>(x0); if (c + 1 < a.cout) op[c + 1] = from_f32<TOut>(x1); }
+    for (int nn = 0; nn < 2; ++nn) {
+      const int c = co0 + nn * 8 + 2 * tq;
+      if (c >= a.cout) continue;
+      float x0 = acc[r >> 1][nn][(r & 1) * 2] + e_bias[nn][0], x1 = acc[r >> 1][nn][(r & 1) * 2 + 1] + e_bias[nn][1];
+      x0 = fmaf(fmaxf(x0, lo_pre), e_scale[nn][0], e_shift[nn][0]);
+      x1 = fmaf(fmaxf(x1, lo_pre), e_scale[nn][1], e_shift[nn][1]);
+      const bool pair = pair_ok && (c + 1 < a.cout);
+      if (rp) {
+        if (pair) { const float2 rr = load2<TOut>(rp + c); x0 += rr.x; x1 += rr.y; }
+        else { x0 += to_f32<TOut>(rp[c]); if (c + 1 < a.cout) x1 += to_f32<TOut>(rp[c + 1]); }
       }
+      x0 = fmaxf(x0, lo_post); x1 = fmaxf(x1, lo_post);
+      if (a.sigmoid) { x0 = 1.f / (1.f + expf(-x0)); x1 = 1.f / (1.f + expf(-x1)); }
+      if (pair) store2<TOut>(op + c, x0, x1);
+      else { op[c] = from_f32<TOut>(x0); if (c + 1 < a.cout) op[c + 1] = from_f32<TOut>(x1); }
     }
   }
 }
@@ -423,7 +443,7 @@ static int launch_conv(const ConvArgs& a, cudaStream_t st) {
   const long long M = (long long)a.n * a.hog * a.wog;
   if constexpr (std::is_same<TIn, __nv_bfloat16>::value) {
     if (a.cin == 16 && a.ntaps <= 9 && a.in_coff % 2 == 0 && a.in_cstride % 2 == 0) {   // tensor-core path for 16-channel layers
-      dim3 grid(min(ceil_div(M, 128), kNumSMs * 16), a.cout_pad / 16);
+      dim3 grid(a.n * a.hog, ceil_div(a.wog, 128), a.cout_pad / 16);
       if (a.ntaps <= 3) conv_c16_mma_kernel<TOut, 3><<<grid, 128, 0, st>>>(a);
       else if (a.ntaps <= 4) conv_c16_mma_kernel<TOut, 4><<<grid, 128, 0, st>>>(a);
       else conv_c16_mma_kernel<TOut, 9><<<grid, 128, 0, st>>>(a);
@@ -488,7 +508,16 @@ extern "C" int lavb_pool2_affine_relu(const void* d_in, int dtype, int n, int hi
   const long long total = (long long)n * (hin / 2) * (win / 2) * c;
   if (total == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == LAVB_F32)
+  const bool vec = c % 4 == 0 && in_cstride % 4 == 0 && in_coff % 4 == 0 && out_cstride % 4 == 0 && out_coff % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(d_scale) % 16 == 0) && (reinterpret_cast<uintptr_t>(d_shift) % 16 == 0);
+  if (vec && dtype == LAVB_F32) {
+    pool2_vec4_kernel<float><<<ceil_div(total / 4, 256), 256, 0, st>>>((const float*)d_in, n, hin, win, c, in_cstride, in_coff, d_scale,
+                                                                        d_shift, (float*)d_out, out_cstride, out_coff);
+  } else if (vec && dtype == LAVB_BF16) {
+    pool2_vec4_kernel<__nv_bfloat16><<<ceil_div(total / 4, 256), 256, 0, st>>>((const __nv_bfloat16*)d_in, n, hin, win, c, in_cstride,
+                                                                                in_coff, d_scale, d_shift, (__nv_bfloat16*)d_out,
+                                                                                out_cstride, out_coff);
+  } else if (dtype == LAVB_F32)
     pool2_kernel<float><<<ceil_div(total, 256), 256, 0, st>>>((const float*)d_in, n, hin, win, c, in_cstride, in_coff, d_scale,
                                                                d_shift, (float*)d_out, out_cstride, out_coff);
   else if (dtype == LAVB_BF16)

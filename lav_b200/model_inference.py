@@ -108,9 +108,9 @@ class InferModel(nn.Module):
     def forward_batch(self, lidars, num_points, nxps, cmd_values):
         """B independent frames.  lidars: list of (P_b,11) tensors or (B,P,11); nxps (B,2); cmd_values (B,).
         Returns dict of batched outputs; 'det' is the per-frame detection list of the reference."""
+        from . import ops
         feats, center, box, ori, seg = self.lidar_model.forward_nhwc(lidars, num_points)
-        heat = torch.sigmoid(center.permute(0, 3, 1, 2).float())
-        dets = self.det_inference_batch(heat, box.permute(0, 3, 1, 2), ori.permute(0, 3, 1, 2))
+        dets = self.decode_packed(ops.det_peaks(center, box, ori))
         ee, epl, ecl, ocl, occ = self.uniplanner.infer_batch(feats.permute(0, 3, 1, 2), [d[1] for d in dets], cmd_values, nxps)
         return dict(ego_embd=ee, ego_plan_locs=epl, ego_cast_locs=ecl, other_cast_locs=ocl, other_cast_cmds=occ,
                     pred_bev=seg.permute(0, 3, 1, 2), det=dets, features=feats)

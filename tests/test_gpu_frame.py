@@ -201,3 +201,35 @@ def test_resnet_trunk_on_umma_matches_cudnn(cuda):
     assert got.shape == want.shape == (2, 512, 6, 15)
     rms = float(((got - want) ** 2).mean().sqrt() / (want ** 2).mean().sqrt())
     assert rms < 2e-2, rms            # both paths are bf16 with different rounding points (cuDNN keeps BN folded in the weights)
+
+
+@pytest.mark.parametrize("kind", ["blobs", "noise", "flat"])
+def test_det_peaks_kernel_matches_reference_decode(cuda, kind):
+    """CUDA decode (sigmoid + 7x7 NMS + top-15 + map reads) vs the torch restatement of extract_peak / det_inference."""
+    from lav_b200 import ops
+    from lav_b200.model_inference import InferModel
+    g = synth._gen(17, kind)
+    B = 3
+    if kind == "blobs":
+        yy, xx = torch.meshgrid(torch.arange(320.), torch.arange(320.), indexing="ij")
+        logit = torch.full((B, 2, 320, 320), -6.0)
+        for b in range(B):
+            for k in range(25):
+                cx, cy = (torch.rand(2, generator=g) * 320).tolist()
+                amp = 3.0 + float(torch.rand(1, generator=g)) * 8
+                logit[b, k % 2] = torch.maximum(logit[b, k % 2], -6 + amp * torch.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / 8.0))
+    elif kind == "noise":
+        logit = torch.randn(B, 2, 320, 320, generator=g) * 1.5 - 4.0
+    else:
+        logit = torch.full((B, 2, 320, 320), -9.0)          # nothing above the threshold
+    size = torch.rand(B, 2, 320, 320, generator=g) * 3
+    ori = torch.randn(B, 2, 320, 320, generator=g)
+    stub = type("S", (), {"pixels_per_meter": 4})()
+    want = InferModel.decode_packed(stub, InferModel.pack_peaks(torch.sigmoid(logit), size, ori))
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(cuda)
+    got = InferModel.decode_packed(stub, ops.det_peaks(nhwc(logit), nhwc(size), nhwc(ori)))
+    for b in range(B):
+        for c in range(2):
+            assert sorted(got[b][c]) == sorted(want[b][c]), (kind, b, c)
+            if kind == "blobs":
+                assert got[b][c] == want[b][c]            # distinct scores: same (descending) order as torch.topk
