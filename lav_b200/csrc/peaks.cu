@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(256) peak_candidates_kernel(const float* __res
   if (i >= (long long)B * H * W) return;
   const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / ((long long)W * H));
   for (int c = 0; c < ncls; ++c) {
-    const float s = sigmoidf_ref(__ldg(center + i * ncls + c));
+    const float xl = __ldg(center + i * ncls + c);
+    const float s = sigmoidf_ref(xl);
     if (!((double)s > (double)min_score)) continue;
     bool peak = true;
     for (int dy = -3; dy <= 3 && peak; ++dy) {
@@ -28,7 +29,10 @@ __global__ void __launch_bounds__(256) peak_candidates_kernel(const float* __res
       for (int dx = -3; dx <= 3; ++dx) {
         const int xx = x + dx;
         if (xx < 0 || xx >= W) continue;
-        if (sigmoidf_ref(__ldg(center + (((long long)b * H + yy) * W + xx) * ncls + c)) > s) { peak = false; break; }
+        // sigmoid is monotonic: only a neighbour with a larger LOGIT can have a larger sigmoid; the exact fp32 sigmoid
+        // comparison (ties of saturated values count as peaks, like max_pool2d on the sigmoid map) runs only then
+        const float xn = __ldg(center + (((long long)b * H + yy) * W + xx) * ncls + c);
+        if (xn > xl && sigmoidf_ref(xn) > s) { peak = false; break; }
       }
     }
     if (!peak) continue;

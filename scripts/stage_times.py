@@ -42,8 +42,7 @@ with torch.no_grad():
     cv = canvas.permute(0, 2, 3, 1).contiguous()
     feats = t_graph("backbone", lambda: im.lidar_model.backbone.forward_nhwc(cv))
     heads = t_graph("heads", lambda: im.lidar_model.heads_nhwc(feats))
-    heat = torch.sigmoid(heads[0].permute(0, 3, 1, 2))
-    t_graph("peaks", lambda: im.pack_peaks(heat, heads[1].permute(0, 3, 1, 2), heads[2].permute(0, 3, 1, 2)))
+    t_graph("peaks", lambda: ops.det_peaks(heads[0], heads[1], heads[2]))
     wide = pipe.rgbs.permute(0, 2, 1, 3, 4).reshape(B, 288, 768, 3).permute(0, 3, 1, 2).float().contiguous(memory_format=torch.channels_last)
     tel = pipe.tels.permute(0, 3, 1, 2).float().contiguous(memory_format=torch.channels_last)
     t_graph("brake", lambda: pipe.bra_model(wide, tel))

@@ -171,10 +171,10 @@ def test_static_pipeline_matches_dynamic(cuda, graphs):
                 hist[b].push(st.cur[b, :lidars[b].shape[0]].clone(), poses[b][0], poses[b][1])
             continue
         im = dyn.infer_model
-        orig = im.det_inference_batch
-        im.det_inference_batch = lambda *a, **k: [[d[0], list(DETS)] for d in orig(*a, **k)]
+        orig = im.decode_packed
+        im.decode_packed = lambda *a, **k: [[d[0], list(DETS)] for d in orig(*a, **k)]
         o_d = dyn.step(rgbs.to(cuda), tels.to(cuda), [l.to(cuda) for l in lidars], hist, nxps.to(cuda), [3, 1], poses=poses)
-        im.det_inference_batch = orig
+        im.decode_packed = orig
         for b in range(B):
             n = lidars[b].shape[0]
             assert torch.equal(st.cur[b, :n].cpu(), hist[b].lidars[-1].cpu()), tick
