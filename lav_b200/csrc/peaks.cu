@@ -12,47 +12,62 @@ constexpr int kCandCap = 8192;   // candidates kept per (frame, class); heat map
 
 __device__ __forceinline__ float sigmoidf_ref(float x) { return 1.f / (1.f + expf(-x)); }   // torch.sigmoid, fp32
 
+// Tile kernel: a 32x32 pixel tile (+3 halo) of one class is turned into sigmoid values in shared memory, the 7x7
+// window maximum is built separably (7-wide row max, then 7-high column max) and a pixel is a peak when nothing in its
+// window is larger — exactly max_pool2d(heat, 7, 1, 3) followed by `max_cls > heat` (ties of saturated values all count).
+constexpr int kPT = 32, kPH = 3, kPW = kPT + 2 * kPH;      // 38
+
 __global__ void __launch_bounds__(256) peak_candidates_kernel(const float* __restrict__ center, int B, int H, int W, int ncls,
                                                               float min_score, int* __restrict__ counts,
                                                               float2* __restrict__ cand) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)B * H * W) return;
-  const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / ((long long)W * H));
-  for (int c = 0; c < ncls; ++c) {
-    const float xl = __ldg(center + i * ncls + c);
-    const float s = sigmoidf_ref(xl);
+  __shared__ float sv[kPW][kPW + 1];      // sigmoid values, -inf outside the map (max_pool2d pads with -inf)
+  __shared__ float rm[kPW][kPT + 1];      // row-wise 7-max for the 32 centre columns
+  const int tiles_x = (W + kPT - 1) / kPT, tiles_y = (H + kPT - 1) / kPT;
+  int t = blockIdx.x;
+  const int c = t % ncls; t /= ncls;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y; const int b = t / tiles_y;
+  const int x0 = tx * kPT - kPH, y0 = ty * kPT - kPH;
+  for (int i = threadIdx.x; i < kPW * kPW; i += blockDim.x) {
+    const int ly = i / kPW, lx = i - ly * kPW, y = y0 + ly, x = x0 + lx;
+    sv[ly][lx] = (y >= 0 && y < H && x >= 0 && x < W) ? sigmoidf_ref(__ldg(center + (((long long)b * H + y) * W + x) * ncls + c)) : -INFINITY;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kPW * kPT; i += blockDim.x) {
+    const int ly = i / kPT, lx = i - ly * kPT;
+    float m = sv[ly][lx];
+#pragma unroll
+    for (int d = 1; d < 7; ++d) m = fmaxf(m, sv[ly][lx + d]);
+    rm[ly][lx] = m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kPT * kPT; i += blockDim.x) {
+    const int ly = i / kPT, lx = i - ly * kPT, y = y0 + kPH + ly, x = x0 + kPH + lx;
+    if (y >= H || x >= W) continue;
+    const float s = sv[ly + kPH][lx + kPH];
     if (!((double)s > (double)min_score)) continue;
-    bool peak = true;
-    for (int dy = -3; dy <= 3 && peak; ++dy) {
-      const int yy = y + dy;
-      if (yy < 0 || yy >= H) continue;
-      for (int dx = -3; dx <= 3; ++dx) {
-        const int xx = x + dx;
-        if (xx < 0 || xx >= W) continue;
-        // sigmoid is monotonic: only a neighbour with a larger LOGIT can have a larger sigmoid; the exact fp32 sigmoid
-        // comparison (ties of saturated values count as peaks, like max_pool2d on the sigmoid map) runs only then
-        const float xn = __ldg(center + (((long long)b * H + yy) * W + xx) * ncls + c);
-        if (xn > xl && sigmoidf_ref(xn) > s) { peak = false; break; }
-      }
-    }
-    if (!peak) continue;
+    float m = rm[ly][lx];
+#pragma unroll
+    for (int d = 1; d < 7; ++d) m = fmaxf(m, rm[ly + d][lx]);
+    if (m > s) continue;                                     // something in the 7x7 window is larger: not a peak
     const int slot = atomicAdd(&counts[b * ncls + c], 1);
     if (slot < kCandCap) cand[(long long)(b * ncls + c) * kCandCap + slot] = make_float2(s, __int_as_float(y * W + x));
   }
 }
 
-// one warp per (frame, class): max_det rounds of arg-max over the candidate list (ties -> smaller flat index)
-__global__ void __launch_bounds__(32) peak_select_kernel(const float* __restrict__ box, const float* __restrict__ ori, int H, int W,
-                                                         int ncls, int max_det, const int* __restrict__ counts,
-                                                         float2* __restrict__ cand, float* __restrict__ packed) {
-  const int bc = blockIdx.x, b = bc / ncls, c = bc % ncls, lane = threadIdx.x;
+// one block per (frame, class): max_det rounds of arg-max over the candidate list (ties -> smaller flat index)
+__global__ void __launch_bounds__(256) peak_select_kernel(const float* __restrict__ box, const float* __restrict__ ori, int H, int W,
+                                                          int ncls, int max_det, const int* __restrict__ counts,
+                                                          float2* __restrict__ cand, float* __restrict__ packed) {
+  __shared__ float sb[8]; __shared__ int sl[8], si[8];
+  const int bc = blockIdx.x, b = bc / ncls, c = bc % ncls, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = min(counts[bc], kCandCap);
   float2* list = cand + (long long)bc * kCandCap;
   const int cols = ncls * max_det;
   float* out = packed + (long long)b * 7 * cols + c * max_det;
   for (int k = 0; k < max_det; ++k) {
     float best = -INFINITY; int best_loc = 0x7fffffff, best_i = -1;
-    for (int j = lane; j < n; j += 32) {
+    for (int j = tid; j < n; j += 256) {
       const float2 e = list[j];
       const int loc = __float_as_int(e.y);
       if (e.x > best || (e.x == best && loc < best_loc)) { best = e.x; best_loc = loc; best_i = j; }
@@ -63,7 +78,11 @@ __global__ void __launch_bounds__(32) peak_select_kernel(const float* __restrict
       const int ol = __shfl_xor_sync(0xffffffffu, best_loc, o), oi = __shfl_xor_sync(0xffffffffu, best_i, o);
       if (ob > best || (ob == best && ol < best_loc)) { best = ob; best_loc = ol; best_i = oi; }
     }
-    if (lane == 0) {
+    if (lane == 0) { sb[warp] = best; sl[warp] = best_loc; si[warp] = best_i; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (sb[w] > best || (sb[w] == best && sl[w] < best_loc)) { best = sb[w]; best_loc = sl[w]; best_i = si[w]; }
       if (best_i >= 0) {
         list[best_i].x = -INFINITY;                       // consumed
         const long long px = ((long long)b * H * W + best_loc) * 2;
@@ -76,7 +95,7 @@ __global__ void __launch_bounds__(32) peak_select_kernel(const float* __restrict
       }
       out[6 * cols + k] = (float)W;
     }
-    __syncwarp();
+    __syncthreads();
   }
 }
 
@@ -96,9 +115,10 @@ extern "C" int lavb_det_peaks(const float* d_center, const float* d_box, const f
   int* counts = reinterpret_cast<int*>(d_workspace);
   float2* cand = reinterpret_cast<float2*>(reinterpret_cast<char*>(d_workspace) + ((size_t)batch * ncls * sizeof(int) + 255) / 256 * 256);
   LAVB_CUDA_OK(cudaMemsetAsync(counts, 0, (size_t)batch * ncls * sizeof(int), st));
-  peak_candidates_kernel<<<ceil_div((long long)batch * h * w, 256), 256, 0, st>>>(d_center, batch, h, w, ncls, min_score, counts, cand);
+  const int tiles = batch * ceil_div(h, kPT) * ceil_div(w, kPT) * ncls;
+  peak_candidates_kernel<<<tiles, 256, 0, st>>>(d_center, batch, h, w, ncls, min_score, counts, cand);
   LAVB_LAUNCH_OK();
-  peak_select_kernel<<<batch * ncls, 32, 0, st>>>(d_box, d_ori, h, w, ncls, max_det, counts, cand, d_packed);
+  peak_select_kernel<<<batch * ncls, 256, 0, st>>>(d_box, d_ori, h, w, ncls, max_det, counts, cand, d_packed);
   LAVB_LAUNCH_OK();
   return 0;
 }

@@ -160,6 +160,57 @@ class BEVPlanner(nn.Module):
         self.cast_mlps = nn.ModuleList([nn.Linear(64, 2) for _ in range(num_cmds)])
         self.cast_cmd_pred = nn.Sequential(nn.Linear(512, num_cmds), nn.Sigmoid())
 
+    # the frozen teacher of the distillation step (lav/models/bev_planner_v2.py:176-262); PyTorch, no grad needed
+    def crop_feature(self, features, rel_locs, rel_oris, pixels_per_meter=4, crop_size=96):
+        B, C, H, W = features.size()
+        theta = crop_theta(rel_locs, rel_oris, H, W, pixels_per_meter, crop_size, self.offset_x, self.offset_y)
+        grids = F.affine_grid(theta, torch.Size((B, C, crop_size, crop_size)), align_corners=True)
+        return F.grid_sample(features, grids, align_corners=True)
+
+    def cast(self, embd):
+        B = embd.size(0)
+        u = embd.expand(self.num_plan, B, -1).permute(1, 0, 2).contiguous()
+        return torch.stack([torch.cumsum(mlp(gru(u)[0]), dim=1) for gru, mlp in zip(self.cast_grus, self.cast_mlps)], dim=1)
+
+    def plan(self, embd, nxp, cast_locs=None, pixels_per_meter=4, crop_size=96):
+        return _plan_rollout(self.plan_gru, self.plan_mlp, self.num_cmds, self.num_plan, self.num_plan_iter, embd, nxp,
+                             (self.cast(embd) if cast_locs is None else cast_locs).detach(), pixels_per_meter, crop_size)
+
+
+def _plan_rollout(plan_gru, plan_mlp, num_cmds, num_plan, num_plan_iter, embd, nxp, plan_loc, pixels_per_meter, crop_size):
+    """plan/_plan of both planners (uniplanner.py:227-259): the six command branches share the GRU, so one call rolls
+    6*B sequences; repeated num_plan_iter times feeding its own output."""
+    B = embd.size(0)
+    u0 = nxp * pixels_per_meter / crop_size * 2 - 1
+    h0 = embd[:, None].expand(B, num_cmds, -1).reshape(1, B * num_cmds, -1).contiguous()
+    outs = []
+    for _ in range(num_plan_iter):
+        u = torch.cat([u0[:, None, None].expand(B, num_cmds, num_plan, 2), plan_loc], dim=3)
+        out, _ = plan_gru(u.reshape(B * num_cmds, num_plan, 4), h0)
+        plan_loc = torch.cumsum(plan_mlp(out), dim=1).view(B, num_cmds, num_plan, 2) + plan_loc
+        outs.append(plan_loc)
+    return torch.stack(outs, dim=1)
+
+
+def filter_cars(ego_locs, locs, typs):
+    """uniplanner.py:329-333: only vehicles ahead of the ego."""
+    rel_locs = locs[:, :, 0] - ego_locs[:, 0:1]
+    return typs & (rel_locs[..., 1] < 0)
+
+
+def random_sample(binaries, size):
+    """uniplanner.py:336-347: keep at most `size` vehicles per sample (same RNG consumption as the reference)."""
+    cut = torch.zeros_like(binaries)
+    for i in range(binaries.size(0)):
+        if binaries[i].sum() <= size:
+            cut[i] = binaries[i]
+        else:
+            nonzero = torch.nonzero(binaries[i]).squeeze(1)
+            idx = torch.multinomial(torch.ones_like(nonzero).float(), size)
+            nonzero = nonzero[idx]
+            cut[i, nonzero] = binaries[i, nonzero]
+    return cut
+
 
 class UniPlanner(nn.Module):
     def __init__(self, bev_planner, pixels_per_meter=2, crop_size=64, x_offset=0, y_offset=0.75, feature_x_jitter=1,
@@ -189,7 +240,7 @@ class UniPlanner(nn.Module):
         materialising an expanded copy."""
         B, C, H, W = features.size()
         theta = crop_theta(rel_locs, rel_oris, H, W, pixels_per_meter, crop_size, self.offset_x, self.offset_y)
-        if features.is_cuda:
+        if features.is_cuda and not (torch.is_grad_enabled() and features.requires_grad):
             from . import ops
             feats_nhwc = features.permute(0, 2, 3, 1)
             if feats_nhwc.is_contiguous():
@@ -210,23 +261,70 @@ class UniPlanner(nn.Module):
             locs.append(torch.cumsum(mlp(out), dim=1))
         return torch.stack(locs, dim=1)
 
-    def _plan(self, embd, nxp, cast_locs, pixels_per_meter=4, crop_size=96):
-        B = embd.size(0)
-        h0, u0 = embd, nxp * pixels_per_meter / crop_size * 2 - 1
-        # the six command branches share plan_gru/plan_mlp: run them as one batch of 6*B sequences
-        u = torch.cat([u0[:, None, None].expand(B, self.num_cmds, self.num_plan, 2), cast_locs], dim=3)
-        out, _ = self.plan_gru(u.reshape(B * self.num_cmds, self.num_plan, 4),
-                               h0[:, None].expand(B, self.num_cmds, -1).reshape(1, B * self.num_cmds, -1).contiguous())
-        locs = torch.cumsum(self.plan_mlp(out), dim=1).view(B, self.num_cmds, self.num_plan, 2)
-        return locs + cast_locs
-
     def plan(self, embd, nxp, cast_locs=None, pixels_per_meter=4, crop_size=96):
-        plan_loc = (self.cast(embd) if cast_locs is None else cast_locs).detach()
-        plan_locs = []
-        for _ in range(self.num_plan_iter):
-            plan_loc = self._plan(embd, nxp, plan_loc, pixels_per_meter=pixels_per_meter, crop_size=crop_size)
-            plan_locs.append(plan_loc)
-        return torch.stack(plan_locs, dim=1)
+        return _plan_rollout(self.plan_gru, self.plan_mlp, self.num_cmds, self.num_plan, self.num_plan_iter, embd, nxp,
+                             (self.cast(embd) if cast_locs is None else cast_locs).detach(), pixels_per_meter, crop_size)
+
+    def forward(self, features, bev, ego_locs, locs, oris, nxps, typs):
+        """Training forward of the student with its frozen teacher (lav/models/uniplanner.py:56-151).  Random jitter
+        is drawn on the CPU in the reference's order, so a seeded run reproduces the reference exactly."""
+        self.bev_planner.eval()
+        ego_oris = oris[:, :1]
+        locs, oris = locs[:, 1:], oris[:, 1:]
+        typs = (typs[:, 1:] == 1)
+        N = locs.size(1)
+        typs = filter_cars(ego_locs, locs, typs)
+        bp = self.bev_planner
+        if int(typs.float().sum()) > 0:
+            typs = random_sample(typs, size=self.max_num_cars)
+            flat_features = features.expand(N, *features.size()).permute(1, 0, 2, 3, 4)[typs]
+            flat_bev = bev.expand(N, *bev.size()).permute(1, 0, 2, 3, 4)[typs]
+            flat_locs = (locs[:, :, 1:] - locs[:, :, :1])[typs]
+            flat_rel_loc0 = (locs[:, :, 0] - ego_locs[:, None, 0])[typs]
+            flat_rel_ori0 = (oris - ego_oris)[typs]
+            K = flat_locs.size(0)
+            locs_jitter = (torch.rand((K, 2)) * 2 - 1).float().to(locs.device) * self.feature_x_jitter
+            locs_jitter[:, 1] = 0
+            oris_jitter = (torch.rand((K,)) * 2 - 1).float().to(oris.device) * self.feature_angle_jitter
+            cropped_other_features = self.crop_feature(flat_features, flat_rel_loc0 + locs_jitter, flat_rel_ori0 + oris_jitter,
+                                                       pixels_per_meter=self.pixels_per_meter / 2, crop_size=self.crop_size)
+            cropped_other_bev = bp.crop_feature(flat_bev, flat_rel_loc0 + locs_jitter, flat_rel_ori0 + oris_jitter,
+                                                pixels_per_meter=self.pixels_per_meter, crop_size=self.crop_size * 2)
+            other_locs = transform_points(flat_locs - locs_jitter[:, None], -flat_rel_ori0 - oris_jitter)
+            other_embd = self.lidar_conv_emb(cropped_other_features)
+            other_cast_locs = self.cast(other_embd, mode='other')
+            other_cast_cmds = self.cast_cmd_pred(other_embd)
+            with torch.no_grad():
+                other_bev_embd = bp.bev_conv_emb(cropped_other_bev)
+                other_cast_locs_expert = bp.cast(other_bev_embd)
+                other_cast_cmds_expert = bp.cast_cmd_pred(other_bev_embd)
+        else:
+            z = dict(dtype=features.dtype, device=features.device)
+            other_locs = torch.zeros((N, self.num_plan, 2), **z)
+            other_cast_locs = torch.zeros((N, self.num_cmds, self.num_plan, 2), **z)
+            other_cast_cmds = torch.zeros((N, self.num_cmds), **z)
+            other_cast_locs_expert = torch.zeros((N, self.num_cmds, self.num_plan, 2), **z)
+            other_cast_cmds_expert = torch.zeros((N, self.num_cmds), **z)
+        B = features.size(0)
+        locs_jitter = (torch.rand((B, 2)) * 2 - 1).float().to(locs.device) * self.feature_x_jitter
+        locs_jitter[:, 1] = 0
+        oris_jitter = (torch.rand((B,)) * 2 - 1).float().to(oris.device) * self.feature_angle_jitter
+        ego_locs = transform_points(ego_locs[:, 1:] - locs_jitter[:, None], -oris_jitter)
+        nxps = transform_points(nxps[:, None] - locs_jitter[:, None], -oris_jitter)[:, 0]
+        cropped_ego_features = self.crop_feature(features, locs_jitter, oris_jitter, pixels_per_meter=self.pixels_per_meter / 2,
+                                                 crop_size=self.crop_size)
+        cropped_ego_bev = bp.crop_feature(bev, locs_jitter, oris_jitter, pixels_per_meter=self.pixels_per_meter, crop_size=self.crop_size * 2)
+        ego_embd = self.lidar_conv_emb(cropped_ego_features)
+        with torch.no_grad():
+            ego_bev_embd = bp.bev_conv_emb(cropped_ego_bev)
+            ego_cast_locs_expert = bp.cast(ego_bev_embd)
+            ego_plan_locs_expert = bp.plan(ego_bev_embd, nxps, cast_locs=ego_cast_locs_expert, pixels_per_meter=self.pixels_per_meter,
+                                           crop_size=self.crop_size * 2)
+        ego_cast_locs = self.cast(ego_embd, mode='ego')
+        ego_plan_locs = self.plan(ego_embd, nxps, cast_locs=ego_cast_locs, pixels_per_meter=self.pixels_per_meter, crop_size=self.crop_size * 2)
+        ego_cast_cmds = self.cast_cmd_pred(ego_embd)
+        return (other_locs, other_cast_locs, other_cast_cmds, other_cast_locs_expert, other_cast_cmds_expert,
+                ego_locs, ego_plan_locs, ego_cast_locs, ego_cast_cmds, ego_cast_locs_expert, ego_plan_locs_expert)
 
     def det_to_locs(self, det, H, W):
         """detections -> (locs list, oris list) in ego metres (uniplanner.py:195-214)."""

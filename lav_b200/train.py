@@ -10,7 +10,9 @@ What runs where (round 1):
     autograd on channels-last tensors — hand-written dgrad/wgrad kernels are the next step of this row.
   * gradient exchange: ``GradAllReducer`` — bucketed (25 MB) asynchronous all-reduce launched from
     post-accumulate-grad hooks while backward is still running; BN statistics stay per rank (as DataParallel).
-The UniPlanner distillation branch (teacher BEVPlanner, jittered crops) is not built yet.
+The full step (``LAVTrainer.train_lidar``) adds the UniPlanner distillation branch — student crops/GRUs with autograd,
+frozen BEVPlanner teacher under no_grad (lav_b200/heads.py, pinned bit-exact against the reference on CPU) — and the
+motion losses of lav_final_v2.py:190-225.
 """
 import torch
 import torch.distributed as dist
@@ -157,3 +159,114 @@ class PerceptionTrainer:
         self.reducer.finish()
         self.optim.step()
         return loss.detach(), parts
+
+
+class LAVTrainer:
+    """LAV.train_lidar (lav/lav_final_v2.py:140-259) as one process per GPU: LiDAR model + UniPlanner student trained
+    against the frozen BEVPlanner teacher; Adam over the same parameter set (:74-86), gradients averaged across ranks by
+    GradAllReducer.  Config values default to config_v2.yaml / team_code_v2/config.yaml."""
+
+    def __init__(self, lidar_model, uniplanner, lr=3e-4, device=None, box_weight=1.0, ori_weight=1.0, seg_weight=2.0,
+                 perception_weight=4.0, other_weight=0.5, cmd_weight=0.1, branch_weights=(5, 5, 5, 1, 1, 1), distill=True,
+                 cmd_smooth=0.2, perceive_only=False, motion_only=False, bucket_bytes=25 << 20):
+        self.lidar_model, self.uniplanner = lidar_model.train(), uniplanner.train()
+        uniplanner.bev_planner.eval()
+        for p in uniplanner.bev_planner.parameters():
+            p.requires_grad_(False)
+        self.device = device or next(lidar_model.parameters()).device
+        up = uniplanner
+        params = (list(up.plan_gru.parameters()) + list(up.plan_mlp.parameters()) + list(up.cast_grus_ego.parameters()) +
+                  list(up.cast_mlps_ego.parameters()) + list(up.cast_grus_other.parameters()) + list(up.cast_mlps_other.parameters()) +
+                  list(up.cast_cmd_pred.parameters()) + list(up.lidar_conv_emb.parameters()))
+        if not motion_only:
+            params += list(lidar_model.parameters())
+        self.params = params
+        self.optim = torch.optim.Adam(params, lr=lr)
+        self.sched = torch.optim.lr_scheduler.StepLR(self.optim, step_size=4, gamma=0.5)
+        self.reducer = GradAllReducer(params, bucket_bytes)
+        self.seg_mask = build_seg_mask().to(self.device)
+        self.branch_weights = torch.tensor(branch_weights).float().to(self.device)
+        self.w = dict(box=box_weight, ori=ori_weight, seg=seg_weight, perc=perception_weight, other=other_weight, cmd=cmd_weight)
+        self.distill, self.cmd_smooth = distill, cmd_smooth
+        self.perceive_only, self.motion_only = perceive_only, motion_only
+
+    def losses(self, lidars, num_points, heatmaps, sizemaps, orimaps, bev, ego_locs, cmds, nxps, bras, locs, oris, typs):
+        up = self.uniplanner
+        bev = bev.float()
+        seg_bev = bev[:, [0, 1, 2]]
+        cmds = cmds.long()
+        idxs = (1 - bras).bool()
+        outs = self.lidar_model(lidars, num_points)
+        features, ph, ps, po, pb = outs
+        (other_next_locs, other_cast_locs, other_cast_cmds, other_cast_locs_expert, other_cast_cmds_expert, ego_next_locs,
+         ego_plan_locs, ego_cast_locs, ego_cast_cmds, ego_cast_locs_expert, ego_plan_locs_expert) = up(
+            features, bev, ego_locs.float(), locs.float(), oris.float(), nxps.float(), typs)
+        hm, box, ori = DetLoss()(ph, heatmaps, ps, sizemaps, po, orimaps)
+        det_loss = hm + self.w["box"] * box + self.w["ori"] * ori
+        seg_loss = torch.mean(F.binary_cross_entropy(pb, seg_bev, reduction='none') * self.seg_mask) * self.w["seg"]
+        T = up.num_plan
+        gather_idx = cmds.expand(T, 2, 1, -1).permute(3, 2, 0, 1)
+        target = ego_plan_locs_expert[:, -1].gather(1, gather_idx).unsqueeze(1).repeat(1, up.num_plan_iter, up.num_cmds, 1, 1)
+        plan_loss = torch.mean(F.l1_loss(ego_plan_locs, target, reduction='none').mean(dim=[1, 2, 3, 4]) * self.branch_weights[cmds])
+        if self.distill:
+            ego_cast_loss = F.l1_loss(ego_cast_locs, ego_cast_locs_expert)
+            other_cast_loss = F.l1_loss(other_cast_locs, other_cast_locs_expert)
+            cmd_loss = F.binary_cross_entropy(other_cast_cmds, other_cast_cmds_expert)
+        else:
+            ego_cast_loss = F.l1_loss(ego_cast_locs.gather(1, gather_idx).squeeze(1), ego_locs[:, 1:].float(), reduction='none').mean(dim=[1, 2])[idxs].mean()
+            other_cast_loss = F.l1_loss(other_cast_locs, other_next_locs.unsqueeze(1).repeat(1, up.num_cmds, 1, 1), reduction='none').mean(dim=[2, 3]).min(1)[0].mean()
+            cmd_loss = F.binary_cross_entropy(ego_cast_cmds, (1. - self.cmd_smooth) * F.one_hot(cmds, up.num_cmds) + self.cmd_smooth / up.num_cmds)
+        mot_loss = plan_loss + ego_cast_loss + other_cast_loss * self.w["other"] + cmd_loss * self.w["cmd"]
+        if self.perceive_only:
+            loss = det_loss + seg_loss
+        elif self.motion_only:
+            loss = mot_loss
+        else:
+            loss = mot_loss + (det_loss + seg_loss) * self.w["perc"]
+        parts = dict(hm_loss=hm, box_loss=box, ori_loss=ori, seg_loss=seg_loss, plan_loss=plan_loss, ego_cast_loss=ego_cast_loss,
+                     other_cast_loss=other_cast_loss, cmd_loss=cmd_loss)
+        return loss, {k: v.detach() for k, v in parts.items()}
+
+    def train_lidar(self, *batch):
+        """batch = the 14-tuple of TemporalLiDARPaintedDataset (temporal_lidar_painted_dataset.py:172-179) minus num_objs:
+        lidars, num_points, heatmaps, sizemaps, orimaps, bev, ego_locs, cmds, nxps, bras, locs, oris, typs"""
+        loss, parts = self.losses(*batch[:13])
+        self.optim.zero_grad(set_to_none=True)
+        loss.backward()
+        self.reducer.finish()
+        self.optim.step()
+        return loss.detach(), parts
+
+
+def synthetic_train_batch(B, device, seed=2021, n_points=(60000, 120000), n_obj=6):
+    """seeded batch with the shapes of SURVEY 8(a) a18: lidar (B,120000,11), maps (B,2,320,320), bev (B,9,320,320) ..."""
+    from . import synth
+    g = synth._gen(seed, f"train{B}")
+    P = 120000
+    lid = torch.zeros(B, P, 11)
+    npts = []
+    for b in range(B):
+        n = int(torch.randint(n_points[0], n_points[1] + 1, (1,), generator=g))
+        pts = synth.stacked_lidar(40000, seed=seed, tag=f"tb{b}")[:n]
+        lid[b, :len(pts)] = pts
+        npts.append(len(pts))
+    yy, xx = torch.meshgrid(torch.arange(320.), torch.arange(320.), indexing="ij")
+    heat = torch.zeros(B, 2, 320, 320)
+    for b in range(B):
+        for k in range(6):
+            cx, cy = (torch.rand(2, generator=g) * 320).tolist()
+            heat[b, k % 2] = torch.maximum(heat[b, k % 2], torch.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / 18.0))
+    size = torch.rand(B, 2, 320, 320, generator=g) * 3
+    ori = torch.randn(B, 2, 320, 320, generator=g)
+    bev = (torch.rand(B, 9, 320, 320, generator=g) > 0.7).to(torch.uint8)
+    ego_locs = torch.cumsum(torch.rand(B, 21, 2, generator=g) * torch.tensor([0.2, -1.0]), dim=1)
+    locs = torch.randn(B, n_obj, 21, 2, generator=g) * 6 + torch.tensor([0.0, -8.0])
+    locs[:, 0] = ego_locs
+    oris = torch.rand(B, n_obj, generator=g) * 0.6 - 0.3
+    typs = (torch.rand(B, n_obj, generator=g) > 0.3).long()
+    cmds = torch.randint(0, 6, (B,), generator=g)
+    nxps = torch.tensor([[0.0, -20.0]]).repeat(B, 1) + torch.randn(B, 2, generator=g)
+    bras = (torch.rand(B, generator=g) > 0.8).long()
+    to = lambda t: t.to(device)
+    return (to(lid), torch.tensor(npts), to(heat), to(size), to(ori), to(bev), to(ego_locs), to(cmds), to(nxps), to(bras), to(locs),
+            to(oris), to(typs))

@@ -224,6 +224,43 @@ def main():
                         ego_cast=r_ecl.numpy(), other_cast=r_ocl.numpy(), other_cmds=r_occ.numpy(),
                         det0=np.array(ref_dets[0]).reshape(-1, 6), det1=np.array(ref_dets[1]).reshape(-1, 6))
 
+    # ---- UniPlanner training forward with its frozen teacher (a17) -----------------------------------------------
+    print("[uniplanner train]")
+    import importlib
+    pkg = types.ModuleType("lavm")                      # lav/models as a package WITHOUT running its __init__ (it imports an absent unet)
+    pkg.__path__ = [os.path.join(REF, "lav", "models")]
+    sys.modules["lavm"] = pkg
+    UP2 = importlib.import_module("lavm.uniplanner").UniPlanner
+    BP2 = importlib.import_module("lavm.bev_planner_v2").BEVPlanner
+    from lav_b200.heads import UniPlanner as MyUP, BEVPlanner as MyBP
+    ref_up = UP2(BP2(num_frame_stack=2, **kw), num_input_feature=384, **kw).train()
+    assert list(ref_up.state_dict().keys()) == list(sd_up.keys())
+    ref_up.load_state_dict(sd_up)
+    my_up = MyUP(MyBP(num_frame_stack=2, **kw), num_input_feature=384, **kw).train()
+    my_up.load_state_dict(sd_up)
+    gt = synth._gen(23, "uptrain")
+    Bt, No = 2, 5
+    feats_t = (ref_out[0][:Bt] * 0.5).clone()                                  # (2,384,160,160)
+    bev_t = (torch.rand(Bt, 9, 320, 320, generator=gt) > 0.7).float()
+    ego_locs_t = torch.cumsum(torch.rand(Bt, 21, 2, generator=gt) * torch.tensor([0.2, -1.0]), dim=1)
+    locs_t = torch.randn(Bt, No + 1, 21, 2, generator=gt) * 6 + torch.tensor([0.0, -8.0])
+    locs_t[:, 0] = ego_locs_t
+    oris_t = torch.rand(Bt, No + 1, generator=gt) * 0.6 - 0.3
+    typs_t = torch.tensor([[1, 1, 1, 0, 1, 1], [1, 1, 0, 1, 1, 0]])
+    nxps_t = torch.tensor([[0.0, -20.0], [3.0, -15.0]])
+    torch.set_grad_enabled(True)
+    torch.manual_seed(1234)
+    r_out = ref_up(feats_t, bev_t, ego_locs_t, locs_t, oris_t, nxps_t, typs_t)
+    torch.manual_seed(1234)
+    m_out = my_up(feats_t, bev_t, ego_locs_t, locs_t, oris_t, nxps_t, typs_t)
+    names_t = ["other_locs", "other_cast_locs", "other_cast_cmds", "other_cast_locs_expert", "other_cast_cmds_expert", "ego_locs",
+               "ego_plan_locs", "ego_cast_locs", "ego_cast_cmds", "ego_cast_locs_expert", "ego_plan_locs_expert"]
+    assert len(r_out) == len(m_out) == 11
+    for n, a_, b_ in zip(names_t, r_out, m_out):
+        check("train " + n, a_.detach(), b_.detach(), 2e-4 * (float(a_.abs().max()) + 1))
+    torch.set_grad_enabled(False)
+    np.savez_compressed(os.path.join(GOLD, "uniplanner_train.npz"), **{n: a_.detach().numpy() for n, a_ in zip(names_t, r_out)})
+
     # ---- brake model (a19) -------------------------------------------------------------------------
     print("[brake]")
     bra = RGBBrakePredictionModel([4, 6, 7, 10], pretrained=False).eval()

@@ -58,3 +58,23 @@ def test_perception_trainer_step_decreases_loss(cuda):
     bev = (torch.rand(2, 9, 320, 320, generator=g) > 0.5).float().to(cuda)
     losses = [float(tr.train_step(clouds, [len(c) for c in clouds], heat, size, ori, bev)[0]) for _ in range(6)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_full_train_lidar_step(cuda):
+    """LAVTrainer.train_lidar: LiDAR model + UniPlanner student vs frozen teacher, all 8 losses finite, parameters move,
+    the teacher stays frozen."""
+    from lav_b200.train import LAVTrainer, synthetic_train_batch
+    from tests.test_heads_cpu import uniplanner
+    m, _ = util.lidar_model(cuda)
+    up, _ = uniplanner()
+    up = up.to(cuda)
+    tr = LAVTrainer(m, up, lr=1e-4, device=cuda)
+    batch = synthetic_train_batch(2, cuda, n_points=(20000, 30000))
+    teacher0 = [p.detach().clone() for p in up.bev_planner.parameters()]
+    w0 = up.plan_mlp.weight.detach().clone()
+    l0, parts = tr.train_lidar(*batch)
+    l1, _ = tr.train_lidar(*batch)
+    assert all(torch.isfinite(v) for v in parts.values()) and torch.isfinite(l0) and torch.isfinite(l1)
+    assert set(parts) == {"hm_loss", "box_loss", "ori_loss", "seg_loss", "plan_loss", "ego_cast_loss", "other_cast_loss", "cmd_loss"}
+    assert not torch.equal(w0, up.plan_mlp.weight)
+    assert all(torch.equal(a, b) for a, b in zip(teacher0, up.bev_planner.parameters()))

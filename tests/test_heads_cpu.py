@@ -70,3 +70,30 @@ def test_det_decode_matches_reference_golden(golden_dir):
     assert dets == want
     np.testing.assert_allclose(np.array(dets[0]).reshape(-1, 6), gold["det0"], rtol=0, atol=0)
     np.testing.assert_allclose(np.array(dets[1]).reshape(-1, 6), gold["det1"], rtol=0, atol=0)
+
+
+def test_uniplanner_train_forward_matches_reference_golden(golden_dir):
+    """student + frozen teacher training forward (lav/models/uniplanner.py:56-151), seeded jitter, vs the reference run."""
+    gold = np.load(os.path.join(golden_dir, "uniplanner_train.npz"))
+    up, _ = uniplanner()
+    up.train()
+    _, lsd = util.lidar_model()
+    clouds = util.pillar_clouds()
+    with torch.no_grad():
+        feats = O.lidar_model(lsd, clouds, [len(c) for c in clouds], **util.GRID)[0][:2] * 0.5
+    gt = synth._gen(23, "uptrain")
+    bev = (torch.rand(2, 9, 320, 320, generator=gt) > 0.7).float()
+    ego_locs = torch.cumsum(torch.rand(2, 21, 2, generator=gt) * torch.tensor([0.2, -1.0]), dim=1)
+    locs = torch.randn(2, 6, 21, 2, generator=gt) * 6 + torch.tensor([0.0, -8.0])
+    locs[:, 0] = ego_locs
+    oris = torch.rand(2, 6, generator=gt) * 0.6 - 0.3
+    typs = torch.tensor([[1, 1, 1, 0, 1, 1], [1, 1, 0, 1, 1, 0]])
+    nxps = torch.tensor([[0.0, -20.0], [3.0, -15.0]])
+    torch.manual_seed(1234)
+    out = up(feats, bev, ego_locs, locs, oris, nxps, typs)
+    names = ["other_locs", "other_cast_locs", "other_cast_cmds", "other_cast_locs_expert", "other_cast_cmds_expert", "ego_locs",
+             "ego_plan_locs", "ego_cast_locs", "ego_cast_cmds", "ego_cast_locs_expert", "ego_plan_locs_expert"]
+    assert len(out) == 11
+    for n, o in zip(names, out):
+        np.testing.assert_allclose(o.detach().numpy(), gold[n], atol=5e-4 * (np.abs(gold[n]).max() + 1), err_msg=n)
+    assert out[6].requires_grad and not out[9].requires_grad          # student carries grad, teacher does not
