@@ -158,6 +158,14 @@ int lavb_pool2_affine_relu(const void* d_in, int dtype, int n, int hin, int win,
 int lavb_rgb_normalize(const void* d_rgb, int src_is_u8_nhwc, int n, int h, int w, void* d_out, int out_dtype,
                        void* stream);
 
+/* ---------------------------------------------------------------- brake-model stem on raw camera bytes
+ * replaces: Normalize + ResNet conv1(7x7,s2,p3,3->64) + bn1 + ReLU of RGBBrakePredictionModel (team_code_v2/models/rgb.py:66-70,
+ * lav/models/resnet.py:178,235-238).  d_img: uint8 (batch, ncam, h, cam_w, 3) — the logical image is the ncam cameras side by
+ * side (h x ncam*cam_w); d_w: BatchNorm-folded weights bf16 [64][160], k = (ky*7+kx)*3+c, zero past 147; d_bias [64];
+ * h_mean/h_std: the 3 ImageNet constants; d_out: bf16 NHWC (batch, h/2, ncam*cam_w/2, 64). */
+int lavb_stem7x7s2_u8(const void* d_img, int batch, int ncam, int h, int cam_w, const void* d_w, const float* d_bias,
+                      const float* h_mean, const float* h_std, void* d_out, void* stream);
+
 /* ---------------------------------------------------------------- detection decode (device part)
  * replaces: extract_peak (team_code_v2/model_inference.py:189-202: sigmoid, 7x7 max-pool NMS, top-k) and the per-peak
  * map reads of det_inference (:100-112).  d_center: heat-map LOGITS, d_box / d_ori: size / orientation maps, all fp32

@@ -16,6 +16,7 @@ from . import ops
 from .model_inference import InferModel
 
 FORK_BRAKE = True     # run the brake predictor as a parallel branch of the perception graph
+STEM_U8 = True        # brake-model stem (7x7 s2 on 3 channels) in the lav_b200 kernel, straight from the camera bytes
 UMMA_TRUNKS = False   # ResNet-18 trunks (brake / planner embedder) on the tcgen05 conv kernel: correct (tested) but measured 5-20%
                       # slower than the BN-folded cuDNN path on these small maps (B200, B=32), so cuDNN stays the default
 NUM_REPEAT = 4
@@ -230,6 +231,8 @@ class StaticFramePipeline(FramePipeline):
 
     def _brake(self):
         B = self.B
+        if STEM_U8 and self.bra_model.conv_backbone.conv1.weight.dtype == torch.bfloat16:
+            return self.bra_model.forward_u8(self.rgbs, self.tels)
         wide = self.rgbs.permute(0, 2, 1, 3, 4).reshape(B, 288, 768, 3).permute(0, 3, 1, 2).float()
         tel = self.tels.permute(0, 3, 1, 2).float()
         return self.bra_model(wide.contiguous(memory_format=torch.channels_last), tel.contiguous(memory_format=torch.channels_last))

@@ -8,6 +8,7 @@
 // pipeline and a fused epilogue (bias, ReLU, BN affine, residual, ReLU, sigmoid).
 // This is the exact-fp32 workhorse (parity path and all HBM-bound layers); the tensor-core
 // layers of the bf16 path live in conv_umma.cu.
+#include <algorithm>
 #include <type_traits>
 #include "common.cuh"
 
@@ -23,6 +24,7 @@ struct ConvArgs {
   int ntaps;
   int dy[16], dx[16];
   int pre_relu, post_relu, sigmoid;
+  int rows_pb;   // conv_c16_mma_kernel: output-grid rows each block walks (amortises its weight/epilogue preamble)
 };
 
 constexpr int BK = 16;
@@ -344,10 +346,13 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
 
 template <typename TOut, int NTAPS>
 __global__ void __launch_bounds__(128) conv_c16_mma_kernel(const __grid_constant__ ConvArgs a) {
-  // grid: x = (image, output-grid row), y = 128-pixel segment of that row, z = 16-column chunk -> no per-pixel div/mod
+  // grid: x = (image, group of rows_pb output-grid rows), y = 128-pixel segment of a row, z = 16-column chunk -> no per-pixel
+  // div/mod; the weight fragments and epilogue constants are built once and reused for every row of the group
   const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
   const int co0 = blockIdx.z * 16;
-  const int img = blockIdx.x / a.hog, gy = blockIdx.x - img * a.hog;
+  const int groups = (a.hog + a.rows_pb - 1) / a.rows_pb;
+  const int img = blockIdx.x / groups, gy_begin = (blockIdx.x - img * groups) * a.rows_pb;
+  const int gy_end = min(gy_begin + a.rows_pb, a.hog);
   const int gx0 = blockIdx.y * 128 + (threadIdx.x >> 5) * 32;
   if (gx0 >= a.wog) return;
   // B fragments of this 16-column chunk: b0 = W[tap][k = 2tq, 2tq+1][n = 8nn + gq], b1 = same with k + 8
@@ -380,6 +385,8 @@ __global__ void __launch_bounds__(128) conv_c16_mma_kernel(const __grid_constant
   int gx[4]; bool pv[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) { gx[r] = gx0 + (r >> 1) * 16 + (r & 1) * 8 + gq; pv[r] = gx[r] < a.wog; }
+#pragma unroll 1
+  for (int gy = gy_begin; gy < gy_end; ++gy) {
   float acc[2][2][4];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -409,7 +416,7 @@ __global__ void __launch_bounds__(128) conv_c16_mma_kernel(const __grid_constant
   }
   // epilogue: C fragment = (row gq | gq+8, cols 8nn + 2tq, +1); the lane's 4 columns' parameters sit in registers
   const int oy = gy * a.out_sy + a.out_oy;
-  if (oy >= a.hout) return;
+  if (oy >= a.hout) continue;
   TOut* orow = reinterpret_cast<TOut*>(a.out) + ((long long)img * a.hout + oy) * a.wout * a.out_cstride + a.out_coff;
   const TOut* rrow = a.res ? reinterpret_cast<const TOut*>(a.res) + ((long long)img * a.hout + oy) * a.wout * a.res_cstride + a.res_coff : nullptr;
 #pragma unroll
@@ -436,14 +443,18 @@ __global__ void __launch_bounds__(128) conv_c16_mma_kernel(const __grid_constant
       else { op[c] = from_f32<TOut>(x0); if (c + 1 < a.cout) op[c + 1] = from_f32<TOut>(x1); }
     }
   }
+  }   // row loop
 }
 
 template <typename TIn, typename TOut>
-static int launch_conv(const ConvArgs& a, cudaStream_t st) {
+static int launch_conv(ConvArgs& a, cudaStream_t st) {
   const long long M = (long long)a.n * a.hog * a.wog;
   if constexpr (std::is_same<TIn, __nv_bfloat16>::value) {
     if (a.cin == 16 && a.ntaps <= 9 && a.in_coff % 2 == 0 && a.in_cstride % 2 == 0) {   // tensor-core path for 16-channel layers
-      dim3 grid(a.n * a.hog, ceil_div(a.wog, 128), a.cout_pad / 16);
+      // rows per block: as many as keeps >= ~16 blocks per SM in flight, at most 8
+      const long long row_blocks = (long long)a.n * a.hog * ceil_div(a.wog, 128) * (a.cout_pad / 16);
+      a.rows_pb = (int)std::max<long long>(1, std::min<long long>(8, row_blocks / (kNumSMs * 16)));
+      dim3 grid(a.n * ceil_div(a.hog, a.rows_pb), ceil_div(a.wog, 128), a.cout_pad / 16);
       if (a.ntaps <= 3) conv_c16_mma_kernel<TOut, 3><<<grid, 128, 0, st>>>(a);
       else if (a.ntaps <= 4) conv_c16_mma_kernel<TOut, 4><<<grid, 128, 0, st>>>(a);
       else conv_c16_mma_kernel<TOut, 9><<<grid, 128, 0, st>>>(a);

@@ -89,7 +89,27 @@ class ResNet18(nn.Module):
         f = self._folded(dt, x.device)
         w, b = f["stem"]
         x = torch.cudnn_convolution_relu(x, w, b, (2, 2), (3, 3), (1, 1), 1)
-        x = self.maxpool(x)
+        return self._trunk_folded(self.maxpool(x), f)
+
+    def forward_u8(self, img_u8, mean, std):
+        """Eval fast path from raw camera bytes: img_u8 (B, ncam, H, cam_w, 3) uint8 (cameras side by side) -> layer4 map.
+        Normalisation + conv1 + bn1 + ReLU run in the lav_b200 tensor-core stem kernel (csrc/stem.cu); 3 input channels
+        are the one shape cuDNN's channels-last kernels handle badly.  bf16 weights only."""
+        from . import ops
+        dt = self.conv1.weight.dtype
+        assert dt == torch.bfloat16 and self.conv1.in_channels == 3, "forward_u8: bf16 3-channel stem only"
+        f = self._folded(dt, img_u8.device)
+        if "stem_u8" not in f:
+            w, b = self._folded(torch.float32, img_u8.device)["stem"]                  # fold in fp32, round once
+            wk = torch.zeros((64, 160), dtype=torch.float32, device=img_u8.device)
+            wk[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147)                       # k = (ky*7 + kx)*3 + c
+            f["stem_u8"] = (wk.to(torch.bfloat16).contiguous(), b.float().contiguous())
+        wk, b = f["stem_u8"]
+        x = ops.stem7x7s2_u8(img_u8, wk, b, mean, std).permute(0, 3, 1, 2)            # NCHW view of channels-last memory
+        return self._trunk_folded(self.maxpool(x), f)
+
+    def _trunk_folded(self, x, f):
+        dt = x.dtype
         if getattr(self, "use_umma_trunk", False) and dt == torch.bfloat16:
             # layer1..4 on the lav_b200 tcgen05 conv kernel (BN / residual / ReLU fused in its epilogue)
             key = ("umma", str(x.device))
@@ -467,3 +487,15 @@ class RGBBrakePredictionModel(nn.Module):
         if mask:
             return (pred_bra[:, 0], F.interpolate(self.seg_head(x1), scale_factor=4), F.interpolate(self.seg_head(x2), scale_factor=4))
         return pred_bra[:, 0]
+
+    @torch.no_grad()
+    def forward_u8(self, rgbs_u8, tel_u8):
+        """Same as forward(wide, tel) (team_code_v2/lav_agent_fast.py:257-262,318-321) from the raw camera bytes:
+        rgbs_u8 (B, 3, 288, 256, 3) — the three cameras, stitched side by side inside the stem kernel — and tel_u8
+        (B, 192, 480, 3).  bf16 eval only; the mean/std constants are read once (host) and cached."""
+        ms = self.__dict__.get("_ms")
+        if ms is None:
+            ms = self.__dict__["_ms"] = (self.normalize.mean.float().tolist(), self.normalize.std.float().tolist())
+        x1 = self.conv_backbone.forward_u8(rgbs_u8, *ms)
+        x2 = self.conv_backbone.forward_u8(tel_u8.unsqueeze(1), *ms)
+        return self.classifier(torch.cat([self.attn1(x1), self.attn2(x2)], dim=1).float())[:, 0]

@@ -349,3 +349,18 @@ def det_peaks(center, box, ori, min_score=0.2, max_det=15):
           "lavb_det_peaks")
     _COUNT[0] += 2
     return packed
+
+
+def stem7x7s2_u8(img_u8, w_bf16, bias, mean, std):
+    """img_u8 (B, ncam, H, cam_w, 3) uint8 contiguous; w_bf16 (64,160); bias (64,) -> bf16 NHWC (B, H/2, ncam*cam_w/2, 64)."""
+    _need_cuda(img_u8, w_bf16, bias)
+    assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous() and img_u8.dim() == 5 and img_u8.shape[4] == 3
+    assert w_bf16.dtype == torch.bfloat16 and tuple(w_bf16.shape) == (64, 160) and w_bf16.is_contiguous()
+    b, ncam, h, cw, _ = img_u8.shape
+    out = torch.empty((b, (h - 1) // 2 + 1, (ncam * cw - 1) // 2 + 1, 64), dtype=torch.bfloat16, device=img_u8.device)
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    sd = (C.c_float * 3)(*[float(v) for v in std])
+    check(lib().lavb_stem7x7s2_u8(_ptr(img_u8), b, ncam, h, cw, _ptr(w_bf16), _ptr(bias), m, sd, _ptr(out), _stream()),
+          "lavb_stem7x7s2_u8")
+    _COUNT[0] += 1
+    return out

@@ -45,7 +45,8 @@ with torch.no_grad():
     t_graph("peaks", lambda: ops.det_peaks(heads[0], heads[1], heads[2]))
     wide = pipe.rgbs.permute(0, 2, 1, 3, 4).reshape(B, 288, 768, 3).permute(0, 3, 1, 2).float().contiguous(memory_format=torch.channels_last)
     tel = pipe.tels.permute(0, 3, 1, 2).float().contiguous(memory_format=torch.channels_last)
-    t_graph("brake", lambda: pipe.bra_model(wide, tel))
+    t_graph("brake_cudnn_stem", lambda: pipe.bra_model(wide, tel))
+    t_graph("brake", lambda: pipe._brake())
     K = 3 * B
     g, o, s2 = pipe._g2[K]
     up = im.uniplanner

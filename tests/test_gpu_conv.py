@@ -190,3 +190,47 @@ def test_grouped_head_deconv_vs_torch(cuda, dtype):
         got = outs[i].cpu().permute(0, 3, 1, 2)
         assert got.shape == want.shape
         assert util.rel_err(got, want) < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 3, 32, 24), (1, 1, 31, 50), (1, 3, 288, 256), (2, 1, 192, 480)])
+def test_stem_u8_vs_torch(cuda, shape):
+    """lavb_stem7x7s2_u8 == Normalize + conv 7x7/s2/p3 (3->64) + bias + ReLU on the side-by-side camera image
+    (team_code_v2/models/rgb.py:66-70, lav/models/resnet.py:235-238); operands rounded to bf16 on both sides, tol 1e-2."""
+    from lav_b200 import ops
+    b, ncam, h, cw = shape
+    g = torch.Generator().manual_seed(5)
+    img = torch.randint(0, 256, (b, ncam, h, cw, 3), generator=g, dtype=torch.uint8)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    bias = torch.randn(64, generator=g) * 0.1
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    wk = torch.zeros(64, 160)
+    wk[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147)
+    out = ops.stem7x7s2_u8(img.cuda(), wk.to(torch.bfloat16).cuda(), bias.cuda(), mean, std).float().cpu()
+    wide = img.permute(0, 2, 1, 3, 4).reshape(b, h, ncam * cw, 3).permute(0, 3, 1, 2).float()
+    x = (wide / 255. - torch.tensor(mean)[None, :, None, None]) / torch.tensor(std)[None, :, None, None]
+    ref = F.relu(F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias, stride=2, padding=3))
+    ref = ref.permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-2, err
+
+
+@pytest.mark.gpu
+def test_brake_forward_u8_matches_forward(cuda):
+    """RGBBrakePredictionModel.forward_u8 (stem kernel on raw bytes) == forward(wide, tel) in bf16."""
+    from lav_b200.heads import RGBBrakePredictionModel
+    torch.manual_seed(3)
+    m = RGBBrakePredictionModel([4, 6, 7, 10]).eval()
+    m.load_state_dict(synth.fill_state_dict_(m.state_dict(), seed=11))
+    m = m.cuda()                                   # as FramePipeline.set_precision('bf16'): trunk + attention in bf16
+    m.conv_backbone.to(torch.bfloat16).to(memory_format=torch.channels_last)
+    m.attn1.to(torch.bfloat16); m.attn2.to(torch.bfloat16)
+    g = torch.Generator().manual_seed(9)
+    rgbs = torch.randint(0, 256, (3, 3, 288, 256, 3), generator=g, dtype=torch.uint8).cuda()
+    tel = torch.randint(0, 256, (3, 192, 480, 3), generator=g, dtype=torch.uint8).cuda()
+    with torch.no_grad():
+        wide = rgbs.permute(0, 2, 1, 3, 4).reshape(3, 288, 768, 3).permute(0, 3, 1, 2).float()
+        a = m(wide, tel.permute(0, 3, 1, 2).float()).float()
+        b = m.forward_u8(rgbs, tel).float()
+    assert (a - b).abs().max().item() < 2e-2, (a, b)
