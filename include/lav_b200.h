@@ -161,10 +161,14 @@ int lavb_rgb_normalize(const void* d_rgb, int src_is_u8_nhwc, int n, int h, int 
 /* ---------------------------------------------------------------- brake-model stem on raw camera bytes
  * replaces: Normalize + ResNet conv1(7x7,s2,p3,3->64) + bn1 + ReLU of RGBBrakePredictionModel (team_code_v2/models/rgb.py:66-70,
  * lav/models/resnet.py:178,235-238).  d_img: uint8 (batch, ncam, h, cam_w, 3) — the logical image is the ncam cameras side by
- * side (h x ncam*cam_w); d_w: BatchNorm-folded weights bf16 [64][160], k = (ky*7+kx)*3+c, zero past 147; d_bias [64];
- * h_mean/h_std: the 3 ImageNet constants; d_out: bf16 NHWC (batch, h/2, ncam*cam_w/2, 64). */
+ * side (h x ncam*cam_w), ncam <= 4, cam_w % 4 == 0; d_w: BatchNorm-folded weights bf16 [64][160] with
+ * k = ky*22 + kx*3 + c (slot 21 of every window row and k >= 154 are zero); d_bias [64]; h_mean/h_std: the 3 ImageNet
+ * constants; d_out: bf16 NHWC (batch, h/2, ncam*cam_w/2, 64). */
 int lavb_stem7x7s2_u8(const void* d_img, int batch, int ncam, int h, int cam_w, const void* d_w, const float* d_bias,
                       const float* h_mean, const float* h_std, void* d_out, void* stream);
+/* replaces: ResNet.maxpool = MaxPool2d(3, 2, 1) (lav/models/resnet.py:181,238) on bf16 NHWC (n, h, w, c), c % 8 == 0
+ * -> (n, (h-1)/2+1, (w-1)/2+1, c). */
+int lavb_maxpool3x3s2_nhwc(const void* d_in, int n, int h, int w, int c, void* d_out, void* stream);
 
 /* ---------------------------------------------------------------- detection decode (device part)
  * replaces: extract_peak (team_code_v2/model_inference.py:189-202: sigmoid, 7x7 max-pool NMS, top-k) and the per-peak

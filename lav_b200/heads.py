@@ -89,24 +89,25 @@ class ResNet18(nn.Module):
         f = self._folded(dt, x.device)
         w, b = f["stem"]
         x = torch.cudnn_convolution_relu(x, w, b, (2, 2), (3, 3), (1, 1), 1)
+        if dt == torch.bfloat16:                        # lav_b200 pool kernel on the channels-last memory (ATen's is ~5x slower)
+            from . import ops
+            return self._trunk_folded(ops.maxpool3x3s2_nhwc(x.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2), f)
         return self._trunk_folded(self.maxpool(x), f)
 
     def forward_u8(self, img_u8, mean, std):
         """Eval fast path from raw camera bytes: img_u8 (B, ncam, H, cam_w, 3) uint8 (cameras side by side) -> layer4 map.
-        Normalisation + conv1 + bn1 + ReLU run in the lav_b200 tensor-core stem kernel (csrc/stem.cu); 3 input channels
-        are the one shape cuDNN's channels-last kernels handle badly.  bf16 weights only."""
+        Normalisation + conv1 + bn1 + ReLU run in the lav_b200 tensor-core stem kernel and the max-pool in its companion
+        (csrc/stem.cu): in cuDNN/ATen these two are 64 % of the brake model's GPU time (3 input channels).  bf16 only."""
         from . import ops
         dt = self.conv1.weight.dtype
         assert dt == torch.bfloat16 and self.conv1.in_channels == 3, "forward_u8: bf16 3-channel stem only"
         f = self._folded(dt, img_u8.device)
         if "stem_u8" not in f:
             w, b = self._folded(torch.float32, img_u8.device)["stem"]                  # fold in fp32, round once
-            wk = torch.zeros((64, 160), dtype=torch.float32, device=img_u8.device)
-            wk[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147)                       # k = (ky*7 + kx)*3 + c
-            f["stem_u8"] = (wk.to(torch.bfloat16).contiguous(), b.float().contiguous())
+            f["stem_u8"] = (ops.pack_stem_weights(w), b.float().contiguous())
         wk, b = f["stem_u8"]
-        x = ops.stem7x7s2_u8(img_u8, wk, b, mean, std).permute(0, 3, 1, 2)            # NCHW view of channels-last memory
-        return self._trunk_folded(self.maxpool(x), f)
+        x = ops.maxpool3x3s2_nhwc(ops.stem7x7s2_u8(img_u8, wk, b, mean, std))
+        return self._trunk_folded(x.permute(0, 3, 1, 2), f)                            # NCHW view of channels-last memory
 
     def _trunk_folded(self, x, f):
         dt = x.dtype

@@ -352,7 +352,8 @@ def det_peaks(center, box, ori, min_score=0.2, max_det=15):
 
 
 def stem7x7s2_u8(img_u8, w_bf16, bias, mean, std):
-    """img_u8 (B, ncam, H, cam_w, 3) uint8 contiguous; w_bf16 (64,160); bias (64,) -> bf16 NHWC (B, H/2, ncam*cam_w/2, 64)."""
+    """img_u8 (B, ncam, H, cam_w, 3) uint8 contiguous; w_bf16 (64,160) packed by pack_stem_weights; bias (64,)
+    -> bf16 NHWC (B, H/2, ncam*cam_w/2, 64)."""
     _need_cuda(img_u8, w_bf16, bias)
     assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous() and img_u8.dim() == 5 and img_u8.shape[4] == 3
     assert w_bf16.dtype == torch.bfloat16 and tuple(w_bf16.shape) == (64, 160) and w_bf16.is_contiguous()
@@ -362,5 +363,25 @@ def stem7x7s2_u8(img_u8, w_bf16, bias, mean, std):
     sd = (C.c_float * 3)(*[float(v) for v in std])
     check(lib().lavb_stem7x7s2_u8(_ptr(img_u8), b, ncam, h, cw, _ptr(w_bf16), _ptr(bias), m, sd, _ptr(out), _stream()),
           "lavb_stem7x7s2_u8")
+    _COUNT[0] += 1
+    return out
+
+
+def pack_stem_weights(w):
+    """(64, 3, 7, 7) conv weights -> (64, 160) bf16 in the stem kernel's K order k = ky*22 + kx*3 + c (zero elsewhere)."""
+    wk = torch.zeros((64, 7, 22), dtype=torch.float32, device=w.device)
+    wk[:, :, :21] = w.float().permute(0, 2, 3, 1).reshape(64, 7, 21)
+    out = torch.zeros((64, 160), dtype=torch.float32, device=w.device)
+    out[:, :154] = wk.reshape(64, 154)
+    return out.to(torch.bfloat16).contiguous()
+
+
+def maxpool3x3s2_nhwc(x):
+    """MaxPool2d(3, 2, 1) on a contiguous bf16 NHWC tensor."""
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4 and x.shape[3] % 8 == 0
+    n, h, w, c = x.shape
+    out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=torch.bfloat16, device=x.device)
+    check(lib().lavb_maxpool3x3s2_nhwc(_ptr(x), n, h, w, c, _ptr(out), _stream()), "lavb_maxpool3x3s2_nhwc")
     _COUNT[0] += 1
     return out

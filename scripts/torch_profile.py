@@ -31,3 +31,5 @@ def table(name, fn):
 
 table("brake", lambda: pipe._brake())
 table("planner graph body", lambda: pipe._g2_body(K, s2["locs"], s2["oris"], s2["fidx"]))
+table("erfnet (3B images)", lambda: pipe.seg_model.forward_nhwc(pipe.rgbs.view(B * 3, 288, 256, 3)))
+table("pillars + backbone + heads", lambda: pipe.infer_model.lidar_model.forward_nhwc(pipe.stacked, [pipe.T * pipe.N] * B))

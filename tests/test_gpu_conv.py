@@ -193,7 +193,7 @@ def test_grouped_head_deconv_vs_torch(cuda, dtype):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(2, 3, 32, 24), (1, 1, 31, 50), (1, 3, 288, 256), (2, 1, 192, 480)])
+@pytest.mark.parametrize("shape", [(2, 3, 32, 24), (1, 1, 31, 52), (1, 3, 9, 88), (1, 3, 288, 256), (2, 1, 192, 480)])
 def test_stem_u8_vs_torch(cuda, shape):
     """lavb_stem7x7s2_u8 == Normalize + conv 7x7/s2/p3 (3->64) + bias + ReLU on the side-by-side camera image
     (team_code_v2/models/rgb.py:66-70, lav/models/resnet.py:235-238); operands rounded to bf16 on both sides, tol 1e-2."""
@@ -204,9 +204,7 @@ def test_stem_u8_vs_torch(cuda, shape):
     w = torch.randn(64, 3, 7, 7, generator=g) * 0.1
     bias = torch.randn(64, generator=g) * 0.1
     mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
-    wk = torch.zeros(64, 160)
-    wk[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147)
-    out = ops.stem7x7s2_u8(img.cuda(), wk.to(torch.bfloat16).cuda(), bias.cuda(), mean, std).float().cpu()
+    out = ops.stem7x7s2_u8(img.cuda(), ops.pack_stem_weights(w.cuda()), bias.cuda(), mean, std).float().cpu()
     wide = img.permute(0, 2, 1, 3, 4).reshape(b, h, ncam * cw, 3).permute(0, 3, 1, 2).float()
     x = (wide / 255. - torch.tensor(mean)[None, :, None, None]) / torch.tensor(std)[None, :, None, None]
     ref = F.relu(F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias, stride=2, padding=3))
@@ -214,6 +212,17 @@ def test_stem_u8_vs_torch(cuda, shape):
     assert out.shape == ref.shape
     err = (out - ref).abs().max().item() / ref.abs().max().item()
     assert err < 1e-2, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 7, 9, 64), (3, 144, 384, 64), (1, 1, 1, 8), (2, 96, 240, 64)])
+def test_maxpool_nhwc_vs_torch(cuda, shape):
+    """lavb_maxpool3x3s2_nhwc == MaxPool2d(3, 2, 1) (lav/models/resnet.py:181), bit-exact (values include negatives)."""
+    from lav_b200 import ops
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16).cuda()
+    out = ops.maxpool3x3s2_nhwc(x)
+    ref = F.max_pool2d(x.permute(0, 3, 1, 2).float(), 3, 2, 1).permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert out.shape == ref.shape and torch.equal(out, ref)
 
 
 @pytest.mark.gpu
