@@ -398,6 +398,68 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+constexpr int kFsPitch = 20;          // fp32 decorated-feature tile pitch (floats)
+constexpr int kW1Pitch = 24;          // bf16 layer-1 weight row pitch: conflict-free B-fragment loads
+
+struct EncSmem {                      // shared-memory plan of pillar_encode_sorted_kernel (bytes from the base)
+  static constexpr int fs = 0;                                             // [128][kFsPitch] fp32
+  static constexpr int os = fs + kRows * kFsPitch * 4;                     // [128][kOsPitch] fp32
+  static constexpr int w1h = os + kRows * kOsPitch * 4;                    // [64][kW1Pitch] bf16 (hi)
+  static constexpr int w1l = w1h + 64 * kW1Pitch * 2;                      // (lo)
+  static constexpr int aff = w1l + 64 * kW1Pitch * 2;                      // s1 | t1 | s2 | t2
+  static constexpr int cells = aff + 4 * 64 * 4;                           // [128] int
+  static constexpr int pmax = cells + kRows * 4;                           // [2 parity][first|last][4 quarters][64] fp32
+  static constexpr int pcell = pmax + 2 * 2 * 4 * 64 * 4;                  // [2 parity][4 quarters][first, last, n, pad] int
+  static constexpr int total = pcell + 2 * 4 * 4 * 4;
+};
+
+template <bool kSplitOut>
+__device__ __forceinline__ void emit_pair(void* canvas, int cell, int c, float m0, float m1) {     // channels c, c+1 (c even)
+  if (kSplitOut) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(canvas) + (long long)cell * 128;
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(m0, m1);
+    const float2 hf = __bfloat1622float2(hi);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(m0 - hf.x, m1 - hf.y);
+    *reinterpret_cast<__nv_bfloat162*>(o + c) = hi;
+    *reinterpret_cast<__nv_bfloat162*>(o + 64 + c) = lo;
+  } else {
+    *reinterpret_cast<float2*>(reinterpret_cast<float*>(canvas) + (long long)cell * 64 + c) = make_float2(m0, m1);
+  }
+}
+template <bool kSplitOut>
+__device__ __forceinline__ void emit_one(void* canvas, int cell, int c, float m) {
+  if (kSplitOut) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(canvas) + (long long)cell * 128;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(m);
+    o[c] = hi; o[64 + c] = __float2bfloat16_rn(m - __bfloat162float(hi));
+  } else {
+    reinterpret_cast<float*>(canvas)[(long long)cell * 64 + c] = m;
+  }
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+// fp32 pair -> bf16 hi pair + bf16 residual pair (error-free split to ~2^-16 relative)
+__device__ __forceinline__ void split_pair(float2 f, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(f.x, f.y);
+  const float2 hf = __bfloat1622float2(h);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = pack_bf16(f.x - hf.x, f.y - hf.y);
+}
+
+// Pillar encoder over the cell-sorted point order (both MLP layers on the tensor cores, no canvas atomics).
+// A block walks "windows" of ~128 sorted rows that begin and end on pillar boundaries (tile_start), 128 rows per batch,
+// warp w owning rows [32w, 32w+32) of the batch end to end — one __syncthreads per batch:
+//   (1) gather + decorate: one thread per row -> 16 fp32 features in shared memory;
+//   (2) layer 1 (16 -> 64) as mma.sync m16n8k16 with the features AND weights split into bf16 hi + lo (3 MMAs per tile:
+//       hi*hi + lo*hi + hi*lo, fp32 accumulate ~ fp32 accuracy); BN affine + ReLU on the accumulator fragments, which are
+//       then re-packed IN REGISTERS as the bf16 A fragments of layer 2 (64 -> 64; C-fragment layout == A-fragment layout);
+//       BN affine + ReLU -> fp32 tile in shared memory;
+//   (3) segmented max: each warp walks its own 32 rows, one lane per channel pair; runs that start and end inside the
+//       quarter go straight to the canvas, the first / last run's partial maxima to a small table;
+//   (4) after the barrier, 64 threads stitch the quarter tables with the run carried from the previous batch.
+// Every canvas row of an occupied cell is written exactly once; empty cells were zero-filled by cell_offsets_kernel.
 template <int D, bool kSplitOut>
 __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
     const float* __restrict__ pts, int pt_stride, const __grid_constant__ Clouds clouds, const __grid_constant__ Grid g,
@@ -406,144 +468,155 @@ __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
     const float* __restrict__ s1, const float* __restrict__ t1, const float* __restrict__ w2, const float* __restrict__ s2,
     const float* __restrict__ t2, void* __restrict__ canvas) {
   constexpr int F = D + 5, H = 64;
+  static_assert(F == 16, "layer 1 is one k16 MMA step");
   extern __shared__ __align__(128) uint8_t sm[];
-  __nv_bfloat16* Hs = reinterpret_cast<__nv_bfloat16*>(sm);                       // [128][64] bf16, 16 B chunks XOR (row & 7)
-  float* Os = reinterpret_cast<float*>(sm + kRows * H * 2);                        // [128][kOsPitch]
-  float* w1s = Os + kRows * kOsPitch;                                              // [F][64]
-  __nv_bfloat16* w2s = reinterpret_cast<__nv_bfloat16*>(w1s + F * H);              // [64 n][64 k]
-  float* aff = reinterpret_cast<float*>(w2s + H * H);                              // s1 | t1 | s2 | t2
-  int* cells = reinterpret_cast<int*>(aff + 4 * H);                                // [128]
+  float* fs = reinterpret_cast<float*>(sm + EncSmem::fs);
+  float* Os = reinterpret_cast<float*>(sm + EncSmem::os);
+  __nv_bfloat16* w1h = reinterpret_cast<__nv_bfloat16*>(sm + EncSmem::w1h);
+  __nv_bfloat16* w1l = reinterpret_cast<__nv_bfloat16*>(sm + EncSmem::w1l);
+  float* aff = reinterpret_cast<float*>(sm + EncSmem::aff);
+  int* cells = reinterpret_cast<int*>(sm + EncSmem::cells);
+  float* pmax = reinterpret_cast<float*>(sm + EncSmem::pmax);
+  int* pcell = reinterpret_cast<int*>(sm + EncSmem::pcell);
 
   const int nt = (*total_kept + kRows - 1) / kRows;
   if ((int)blockIdx.x >= nt) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < F * H; i += kRows) w1s[(i % F) * H + i / F] = __ldg(w1 + i);                 // w1 is [64][F]
-  for (int i = tid; i < H * H; i += kRows) w2s[i] = __float2bfloat16_rn(__ldg(w2 + i));             // w2 is [64 n][64 k]
-  for (int i = tid; i < H; i += kRows) { aff[i] = __ldg(s1 + i); aff[H + i] = __ldg(t1 + i); aff[2 * H + i] = __ldg(s2 + i); aff[3 * H + i] = __ldg(t2 + i); }
-  __syncthreads();
-  // layer-2 weight fragments (B operand, "col" layout = rows of w2): b0 (k = 16kk + 2t.., n = 8nn + g), b1 (k + 8)
-  uint32_t bfrag[4][8][2];
-  {
-    const int gq = lane >> 2, tq = lane & 3;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-      for (int nn = 0; nn < 8; ++nn) {
-        const __nv_bfloat16* wp = w2s + (nn * 8 + gq) * H + kk * 16 + tq * 2;
-        bfrag[kk][nn][0] = *reinterpret_cast<const uint32_t*>(wp);
-        bfrag[kk][nn][1] = *reinterpret_cast<const uint32_t*>(wp + 8);
-      }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
+  for (int i = tid; i < H * F; i += kRows) {                                      // w1 is [64 n][16 k]
+    const float v = __ldg(w1 + i);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    w1h[(i / F) * kW1Pitch + i % F] = hi;
+    w1l[(i / F) * kW1Pitch + i % F] = __float2bfloat16_rn(v - __bfloat162float(hi));
   }
-  // persistent: the block walks windows blockIdx.x, +gridDim.x, ... so the weights above are staged once per block
-  for (int win = blockIdx.x; win < nt; win += gridDim.x) {
-  const int row_begin = tile_start[win], row_end = tile_start[win + 1];
-  if (row_begin >= row_end) continue;
-  float run_max = 0.f;      // channel-thread state of the row walk (threads 0..63)
-  int run_cell = -1;
-
-  for (int base = row_begin; base < row_end; base += kRows) {
-    const int rows = min(kRows, row_end - base);
-    // ---- (1) gather + decorate + layer 1 (one thread per row)
-    {
-      float h[H];
+  for (int i = tid; i < H; i += kRows) { aff[i] = __ldg(s1 + i); aff[H + i] = __ldg(t1 + i); aff[2 * H + i] = __ldg(s2 + i); aff[3 * H + i] = __ldg(t2 + i); }
+  // layer-2 weight fragments (B operand, "col" layout = rows of w2 [64 n][64 k]): b0 (k = 16kk + 2tq.., n = 8nn + gq), b1 (k + 8)
+  uint32_t bfrag[4][8][2];
 #pragma unroll
-      for (int j = 0; j < H; ++j) h[j] = 0.f;
-      int cell = -1;
-      if (tid < rows) {
-        const int i = __ldg(order + base + tid);
-        cell = __ldg(ocell + base + tid);
-        const int b = find_cloud(clouds, i);
-        const float* p = pts + (clouds.start[b] + (i - clouds.cum[b])) * pt_stride;
-        int xi, yi;
-        locate(g, __ldg(p), __ldg(p + 1), xi, yi);
-        float f[F];
-        decorate<D>(g, p, xi, yi, __ldg(&stats[pillar_key(g, b, xi, yi)]), f);
+  for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-        for (int k = 0; k < F; ++k) {
-#pragma unroll
-          for (int j = 0; j < H; j += 4) {
-            const float4 w = *reinterpret_cast<const float4*>(&w1s[k * H + j]);
-            h[j] = fmaf(f[k], w.x, h[j]); h[j + 1] = fmaf(f[k], w.y, h[j + 1]);
-            h[j + 2] = fmaf(f[k], w.z, h[j + 2]); h[j + 3] = fmaf(f[k], w.w, h[j + 3]);
-          }
-        }
-      }
-      cells[tid] = cell;
-      // relu(affine) -> bf16, 8 channels (16 B) per store, chunk index XOR (row & 7)
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = c8 * 8 + e * 2;
-          const float v0 = fmaxf(fmaf(h[j], aff[j], aff[H + j]), 0.f), v1 = fmaxf(fmaf(h[j + 1], aff[j + 1], aff[H + j + 1]), 0.f);
-          const __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
-          pk[e] = *reinterpret_cast<const uint32_t*>(&b2);
-        }
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(Hs) + tid * 128 + ((c8 ^ (tid & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
+    for (int nn = 0; nn < 8; ++nn) {
+      const float* wp = w2 + (nn * 8 + gq) * H + kk * 16 + tq * 2;
+      const float2 lo = __ldg(reinterpret_cast<const float2*>(wp)), hi = __ldg(reinterpret_cast<const float2*>(wp + 8));
+      bfrag[kk][nn][0] = pack_bf16(lo.x, lo.y);
+      bfrag[kk][nn][1] = pack_bf16(hi.x, hi.y);
     }
-    __syncthreads();
-    // ---- (2) layer 2 on the tensor cores: warp w -> rows [32w, 32w+32) as two m16 tiles
-    {
-      const uint32_t hs_base = (uint32_t)__cvta_generic_to_shared(Hs);
-      const int gq = lane >> 2, tq = lane & 3;
+  __syncthreads();
+  int it = 0;               // batch counter: parity of the quarter tables
+  // persistent: the block walks windows blockIdx.x, +gridDim.x, ...
+  for (int win = blockIdx.x; win < nt; win += gridDim.x) {
+    const int row_begin = tile_start[win], row_end = tile_start[win + 1];
+    if (row_begin >= row_end) continue;
+    float run_max = 0.f;      // stitch state of channel `tid` (threads 0..63)
+    int run_cell = -1;
+    for (int base = row_begin; base < row_end; base += kRows, ++it) {
+      const int rows = min(kRows, row_end - base);
+      // ---- (1) gather + decorate (one thread per row; the row belongs to this thread's own warp)
+      {
+        float f[F];
 #pragma unroll
+        for (int k = 0; k < F; ++k) f[k] = 0.f;
+        int cell = -1;
+        if (tid < rows) {
+          const int i = __ldg(order + base + tid);
+          cell = __ldg(ocell + base + tid);
+          const int b = find_cloud(clouds, i);
+          const float* p = pts + (clouds.start[b] + (i - clouds.cum[b])) * pt_stride;
+          int xi, yi;
+          locate(g, __ldg(p), __ldg(p + 1), xi, yi);
+          decorate<D>(g, p, xi, yi, __ldg(&stats[pillar_key(g, b, xi, yi)]), f);
+        }
+        cells[tid] = cell;
+#pragma unroll
+        for (int k = 0; k < F; k += 4) *reinterpret_cast<float4*>(&fs[tid * kFsPitch + k]) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
+      }
+      __syncwarp();
+      // ---- (2) both MLP layers on the tensor cores: warp w -> rows [32w, 32w+32) as two m16 tiles
+#pragma unroll 1
       for (int mt = 0; mt < 2; ++mt) {
         const int row0 = warp * 32 + mt * 16;
-        float acc[8][4];
+        uint32_t ah[4], al[4];
+        split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq) * kFsPitch + 2 * tq]), ah[0], al[0]);
+        split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq + 8) * kFsPitch + 2 * tq]), ah[1], al[1]);
+        split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq) * kFsPitch + 2 * tq + 8]), ah[2], al[2]);
+        split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq + 8) * kFsPitch + 2 * tq + 8]), ah[3], al[3]);
+        uint32_t a2[4][4];        // layer-2 A fragments (bf16 h), one k16 step per pair of layer-1 n-tiles
 #pragma unroll
-        for (int nn = 0; nn < 8; ++nn) { acc[nn][0] = acc[nn][1] = acc[nn][2] = acc[nn][3] = 0.f; }
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int r = row0 + (lane & 15), chunk = kk * 2 + (lane >> 4);
-          uint32_t a0, a1, a2, a3;
-          ldmatrix_x4(hs_base + r * 128 + ((chunk ^ (r & 7)) << 4), a0, a1, a2, a3);
-#pragma unroll
-          for (int nn = 0; nn < 8; ++nn) mma_bf16_16816(acc[nn], a0, a1, a2, a3, bfrag[kk][nn][0], bfrag[kk][nn][1]);
+        for (int nn = 0; nn < 8; ++nn) {
+          const __nv_bfloat16* wh = w1h + (nn * 8 + gq) * kW1Pitch + 2 * tq;
+          const __nv_bfloat16* wl = w1l + (nn * 8 + gq) * kW1Pitch + 2 * tq;
+          const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(wh), bh1 = *reinterpret_cast<const uint32_t*>(wh + 8);
+          const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(wl), bl1 = *reinterpret_cast<const uint32_t*>(wl + 8);
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_bf16_16816(acc, al[0], al[1], al[2], al[3], bh0, bh1);       // small terms first
+          mma_bf16_16816(acc, ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+          mma_bf16_16816(acc, ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+          const int col = nn * 8 + 2 * tq;
+          const float sc0 = aff[col], sc1 = aff[col + 1], sh0 = aff[H + col], sh1 = aff[H + col + 1];
+          a2[nn >> 1][(nn & 1) * 2] = pack_bf16(fmaxf(fmaf(acc[0], sc0, sh0), 0.f), fmaxf(fmaf(acc[1], sc1, sh1), 0.f));       // row gq
+          a2[nn >> 1][(nn & 1) * 2 + 1] = pack_bf16(fmaxf(fmaf(acc[2], sc0, sh0), 0.f), fmaxf(fmaf(acc[3], sc1, sh1), 0.f));   // row gq + 8
         }
 #pragma unroll
         for (int nn = 0; nn < 8; ++nn) {
-          const int col = nn * 8 + tq * 2;
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) mma_bf16_16816(acc, a2[kk][0], a2[kk][1], a2[kk][2], a2[kk][3], bfrag[kk][nn][0], bfrag[kk][nn][1]);
+          const int col = nn * 8 + 2 * tq;
           const float sc0 = aff[2 * H + col], sc1 = aff[2 * H + col + 1], sh0 = aff[3 * H + col], sh1 = aff[3 * H + col + 1];
-          *reinterpret_cast<float2*>(&Os[(row0 + gq) * kOsPitch + col]) =
-              make_float2(fmaxf(fmaf(acc[nn][0], sc0, sh0), 0.f), fmaxf(fmaf(acc[nn][1], sc1, sh1), 0.f));
-          *reinterpret_cast<float2*>(&Os[(row0 + gq + 8) * kOsPitch + col]) =
-              make_float2(fmaxf(fmaf(acc[nn][2], sc0, sh0), 0.f), fmaxf(fmaf(acc[nn][3], sc1, sh1), 0.f));
+          *reinterpret_cast<float2*>(&Os[(row0 + gq) * kOsPitch + col]) = make_float2(fmaxf(fmaf(acc[0], sc0, sh0), 0.f), fmaxf(fmaf(acc[1], sc1, sh1), 0.f));
+          *reinterpret_cast<float2*>(&Os[(row0 + gq + 8) * kOsPitch + col]) = make_float2(fmaxf(fmaf(acc[2], sc0, sh0), 0.f), fmaxf(fmaf(acc[3], sc1, sh1), 0.f));
         }
       }
-    }
-    __syncthreads();
-    // ---- (3) row walk: thread c < 64 keeps the running max of channel c and emits a canvas row when the pillar ends
-    if (tid < H) {
-      for (int r = 0; r < rows; ++r) {
-        const int cell = cells[r];
-        if (cell != run_cell) {
-          if (run_cell >= 0) {
-            if (kSplitOut) {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(canvas) + (long long)run_cell * 2 * H;
-              const __nv_bfloat16 hi = __float2bfloat16_rn(run_max);
-              o[tid] = hi; o[H + tid] = __float2bfloat16_rn(run_max - __bfloat162float(hi));
-            } else {
-              reinterpret_cast<float*>(canvas)[(long long)run_cell * H + tid] = run_max;
+      __syncwarp();
+      // ---- (3) quarter walk: lane = channel pair (2 lane, 2 lane + 1) over the warp's own rows
+      float* pm = pmax + (it & 1) * (2 * 4 * 64);
+      int* pc = pcell + (it & 1) * 16 + warp * 4;
+      {
+        const int n = max(0, min(32, rows - warp * 32));
+        if (n > 0) {
+          const int* cq = cells + warp * 32;
+          const float* oq = Os + warp * 32 * kOsPitch + 2 * lane;
+          const int fc = cq[0];
+          int cur = fc;
+          float m0 = 0.f, m1 = 0.f;
+          bool first = true;
+          for (int r = 0; r < n; ++r) {
+            const int c = cq[r];
+            if (c != cur) {
+              if (first) { *reinterpret_cast<float2*>(pm + warp * 64 + 2 * lane) = make_float2(m0, m1); first = false; }
+              else emit_pair<kSplitOut>(canvas, cur, 2 * lane, m0, m1);
+              cur = c; m0 = 0.f; m1 = 0.f;
             }
+            const float2 v = *reinterpret_cast<const float2*>(oq + r * kOsPitch);
+            m0 = fmaxf(m0, v.x); m1 = fmaxf(m1, v.y);
           }
-          run_cell = cell; run_max = 0.f;
+          *reinterpret_cast<float2*>(pm + (first ? 0 : 4 * 64) + warp * 64 + 2 * lane) = make_float2(m0, m1);
+          if (lane == 0) { pc[0] = fc; pc[1] = cur; }
         }
-        run_max = fmaxf(run_max, Os[r * kOsPitch + tid]);
+        if (lane == 0) pc[2] = n;
+      }
+      __syncthreads();
+      // ---- (4) stitch the four quarters with the carried run (thread = channel)
+      if (tid < H) {
+        const int* pcb = pcell + (it & 1) * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (pcb[q * 4 + 2] == 0) continue;
+          const int fc = pcb[q * 4], lc = pcb[q * 4 + 1];
+          const float fm = pm[q * 64 + tid];
+          if (fc != run_cell) {
+            if (run_cell >= 0) emit_one<kSplitOut>(canvas, run_cell, tid, run_max);
+            run_cell = fc; run_max = fm;
+          } else {
+            run_max = fmaxf(run_max, fm);
+          }
+          if (lc != fc) {
+            emit_one<kSplitOut>(canvas, run_cell, tid, run_max);
+            run_cell = lc; run_max = pm[4 * 64 + q * 64 + tid];
+          }
+        }
       }
     }
-    __syncthreads();
-  }
-  if (tid < H && run_cell >= 0) {
-    if (kSplitOut) {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(canvas) + (long long)run_cell * 2 * H;
-      const __nv_bfloat16 hi = __float2bfloat16_rn(run_max);
-      o[tid] = hi; o[H + tid] = __float2bfloat16_rn(run_max - __bfloat162float(hi));
-    } else {
-      reinterpret_cast<float*>(canvas)[(long long)run_cell * H + tid] = run_max;
-    }
-  }
+    if (tid < H && run_cell >= 0) emit_one<kSplitOut>(canvas, run_cell, tid, run_max);
   }   // window loop
 }
 
@@ -704,7 +777,7 @@ extern "C" int lavb_pillar_forward_sorted(const float* d_pts, int pt_stride, int
   pillar_fill_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, st>>>(d_pts, pt_stride, clouds, g, w.offsets, w.cursor,
                                                                              w.order, w.ocell);
   LAVB_LAUNCH_OK();
-  const size_t smem = (size_t)kRows * 64 * 2 + (size_t)kRows * kOsPitch * 4 + 16 * 64 * 4 + 64 * 64 * 2 + 4 * 64 * 4 + kRows * 4;
+  const size_t smem = EncSmem::total;
   static bool configured = false;
   if (!configured) {
     LAVB_CUDA_OK(cudaFuncSetAttribute(pillar_encode_sorted_kernel<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
