@@ -15,6 +15,7 @@
 //              max/FMA with (scale,shift) pairs broadcast from smem, residual, 16 B global stores; flag-free inner loop
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cudaTypedefs.h>
 #include "common.cuh"
 
@@ -31,6 +32,7 @@ struct UmmaArgs {
   int in_sy, in_sx, out_sy, out_sx, out_oy, out_ox;
   int out_cstride, out_coff, out_is_f32, res_cstride, res_coff;
   int pre_relu, post_relu, sigmoid, d2s_nout, cout_store;
+  int wres;   // weights-stationary: all ntaps*kchunks B blocks are loaded once per CTA and stay in shared memory
   int dy[kMaxTaps], dx[kMaxTaps];
   void* out; const __nv_bfloat16* res;
   const float* bias; const float* scale; const float* shift;
@@ -109,10 +111,12 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : 1) c
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B operands need 1024 B alignment
   const int b_bytes = p.cout * kBlockK * 2;
-  const int stage_bytes = kABytes + b_bytes;
-  const uint32_t ctrl = base + p.stages * stage_bytes;
+  const bool wres = p.wres != 0;
+  const int stage_bytes = wres ? kABytes : kABytes + b_bytes;     // the ring carries A only when the weights are resident
+  const uint32_t bres = base + p.stages * stage_bytes;            // resident weights: [ntaps*kchunks][cout x 64] (wres)
+  const uint32_t ctrl = bres + (wres ? p.ntaps * p.kchunks * b_bytes : 0);
   const uint32_t full_bar = ctrl, empty_bar = ctrl + 8 * kMaxStages, tfull_bar = ctrl + 16 * kMaxStages,
-                 tempty_bar = tfull_bar + 16, tmem_slot = tempty_bar + 16;
+                 tempty_bar = tfull_bar + 16, tmem_slot = tempty_bar + 16, wbar = tmem_slot + 8;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
   float* ep_bias = reinterpret_cast<float*>(gen + (tmem_slot - base) + 16);   // only read when kPreBias
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : 1) c
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar + 8 * a, 1); mbar_init(tempty_bar + 8 * a, 32 * kEpiWarps); }
+    mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -151,6 +156,11 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : 1) c
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      if (wres) {   // narrow layers are bound by L2->SM fill bandwidth: fetch the weights once per CTA, not once per tile
+        mbar_expect_tx(wbar, (uint32_t)(nkb * b_bytes));
+        for (int kb = 0; kb < nkb; ++kb)
+          tma_load_2d(bres + kb * b_bytes, &tmap_b, wbar, (kb % p.kchunks) * kBlockK, (kb / p.kchunks) * p.cout);
+      }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
         const int y0 = (r / p.tiles_x) * kTileH * p.in_sy, x0 = (r % p.tiles_x) * kTileW * p.in_sx;
@@ -160,7 +170,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : 1) c
             const uint32_t sa = base + stage * stage_bytes;
             mbar_expect_tx(full_bar + 8 * stage, stage_bytes);
             tma_load_4d(sa, &tmap_a, full_bar + 8 * stage, kc * kBlockK, x0 + p.dx[t], y0 + p.dy[t], img);
-            tma_load_2d(sa + kABytes, &tmap_b, full_bar + 8 * stage, kc * kBlockK, t * p.cout);
+            if (!wres) tma_load_2d(sa + kABytes, &tmap_b, full_bar + 8 * stage, kc * kBlockK, t * p.cout);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -172,6 +182,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : 1) c
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.cout >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      if (wres) { mbar_wait(wbar, 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
@@ -180,7 +191,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : 1) c
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = base + stage * stage_bytes;
-          const uint64_t a_desc = make_sw128_desc(sa), b_desc = make_sw128_desc(sa + kABytes);
+          const uint64_t a_desc = make_sw128_desc(sa), b_desc = make_sw128_desc(wres ? bres + kb * b_bytes : sa + kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)   // +32 B per K16 step inside the 128 B swizzle atom
             umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
@@ -344,9 +355,21 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   a.num_tiles = a.n * a.tiles_x * a.tiles_y;
   a.hout = d->hout; a.wout = d->wout; a.cin = d->cin; a.cout = cout_mma; a.cout_store = d->cout; a.kchunks = d->cin / kBlockK;
   a.ntaps = d->ntaps;
-  const int stage_bytes = kABytes + cout_mma * kBlockK * 2;
-  const bool two_per_sm = cout_mma <= 128;            // narrow layers: 2 CTAs / SM, each with half the smem ring
-  a.stages = two_per_sm ? min(kMaxStages, (100 * 1024) / stage_bytes) : min(kMaxStages, (196 * 1024) / stage_bytes);
+  int stage_bytes = kABytes + cout_mma * kBlockK * 2;
+  bool two_per_sm = cout_mma <= 128;                  // narrow layers: 2 CTAs / SM, each with half the smem ring
+  // weights-stationary mode (LAVB_WRES: 0 off, 1 = layers whose weights fit beside a 2-CTA/SM ring, 2 = also 1-CTA/SM)
+  static int wres_mode = -1;
+  if (wres_mode < 0) { const char* e = getenv("LAVB_WRES"); wres_mode = e ? atoi(e) : 1; }
+  const int res_bytes = d->ntaps * a.kchunks * cout_mma * kBlockK * 2;
+  if (wres_mode >= 1 && two_per_sm && res_bytes <= 48 * 1024) {
+    a.wres = 1; stage_bytes = kABytes;
+    a.stages = min(kMaxStages, (100 * 1024 - res_bytes) / kABytes);
+  } else if (wres_mode >= 2 && two_per_sm && res_bytes <= 96 * 1024) {
+    a.wres = 1; stage_bytes = kABytes; two_per_sm = false;
+    a.stages = min(kMaxStages, (200 * 1024 - res_bytes) / kABytes);
+  } else {
+    a.stages = two_per_sm ? min(kMaxStages, (100 * 1024) / stage_bytes) : min(kMaxStages, (196 * 1024) / stage_bytes);
+  }
   int cols = 32;
   while (cols < 2 * cout_mma) cols <<= 1;
   a.tmem_cols = cols;
@@ -362,7 +385,7 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   a.out = d->out; a.res = reinterpret_cast<const __nv_bfloat16*>(d->res);
   a.bias = d->bias; a.scale = d->scale; a.shift = d->shift;
   if (a.num_tiles == 0) return 0;
-  const size_t smem = (size_t)a.stages * stage_bytes + 1024 /*align*/ + 16 * kMaxStages + 64 + 3 * 256 * sizeof(float);
+  const size_t smem = (size_t)a.stages * stage_bytes + (a.wres ? res_bytes : 0) + 1024 /*align*/ + 16 * kMaxStages + 64 + 3 * 256 * sizeof(float);
   const int grid = min(a.num_tiles, two_per_sm ? 2 * kNumSMs : kNumSMs);
   if (a.d2s_nout) {
 #define LAVB_D2S(S)                                                                                                     \
