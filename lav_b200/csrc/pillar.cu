@@ -551,7 +551,8 @@ __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
           mma_bf16_16816(acc, ah[0], ah[1], ah[2], ah[3], bl0, bl1);
           mma_bf16_16816(acc, ah[0], ah[1], ah[2], ah[3], bh0, bh1);
           const int col = nn * 8 + 2 * tq;
-          const float sc0 = aff[col], sc1 = aff[col + 1], sh0 = aff[H + col], sh1 = aff[H + col + 1];
+          const float2 sc = *reinterpret_cast<const float2*>(&aff[col]), sh = *reinterpret_cast<const float2*>(&aff[H + col]);
+          const float sc0 = sc.x, sc1 = sc.y, sh0 = sh.x, sh1 = sh.y;
           a2[nn >> 1][(nn & 1) * 2] = pack_bf16(fmaxf(fmaf(acc[0], sc0, sh0), 0.f), fmaxf(fmaf(acc[1], sc1, sh1), 0.f));       // row gq
           a2[nn >> 1][(nn & 1) * 2 + 1] = pack_bf16(fmaxf(fmaf(acc[2], sc0, sh0), 0.f), fmaxf(fmaf(acc[3], sc1, sh1), 0.f));   // row gq + 8
         }
@@ -561,7 +562,8 @@ __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) mma_bf16_16816(acc, a2[kk][0], a2[kk][1], a2[kk][2], a2[kk][3], bfrag[kk][nn][0], bfrag[kk][nn][1]);
           const int col = nn * 8 + 2 * tq;
-          const float sc0 = aff[2 * H + col], sc1 = aff[2 * H + col + 1], sh0 = aff[3 * H + col], sh1 = aff[3 * H + col + 1];
+          const float2 sc = *reinterpret_cast<const float2*>(&aff[2 * H + col]), sh = *reinterpret_cast<const float2*>(&aff[3 * H + col]);
+          const float sc0 = sc.x, sc1 = sc.y, sh0 = sh.x, sh1 = sh.y;
           *reinterpret_cast<float2*>(&Os[(row0 + gq) * kOsPitch + col]) = make_float2(fmaxf(fmaf(acc[0], sc0, sh0), 0.f), fmaxf(fmaf(acc[1], sc1, sh1), 0.f));
           *reinterpret_cast<float2*>(&Os[(row0 + gq + 8) * kOsPitch + col]) = make_float2(fmaxf(fmaf(acc[2], sc0, sh0), 0.f), fmaxf(fmaf(acc[3], sc1, sh1), 0.f));
         }
