@@ -203,6 +203,20 @@ int lavb_convert(const void* d_src, int src_dtype, void* d_dst, int dst_dtype, l
  * (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint), accumulators live in TMEM. */
 int lavb_conv_umma(const lavb_conv_desc* h_desc, void* stream);
 
+/* ---------------------------------------------------------------- EXPERIMENTAL: fused (3x1 -> 1x3) convolution pair
+ * replaces: conv3x1_k -> ReLU -> conv1x3_k -> bn_k [-> + input] -> ReLU of non_bottleneck_1d (lav/models/erfnet.py:37-63) in
+ * one tcgen05 kernel; the intermediate activation stays in shared memory.  Not on the default path (round-2 work item).
+ *   mid = relu(conv3x1_dil(in) + bias1);  out = [relu]((conv1x3_dil(mid) + bias2) * scale2 + shift2 [+ res])
+ * in / out / res: bf16 NHWC (n, h, w, c) contiguous, c in {64, 128}, w in {32, 64, 128}; w1 / w2: bf16 [3 taps][c out][c in];
+ * bias2 / scale2 / shift2 / res may be NULL (scale2 and shift2 together). */
+typedef struct lavb_conv_pair_desc {
+  const void* in; void* out; const void* res;
+  int n, h, w, c, dil, post_relu;
+  const void* w1; const float* bias1;
+  const void* w2; const float* bias2; const float* scale2; const float* shift2;
+} lavb_conv_pair_desc;
+int lavb_conv_pair_umma(const lavb_conv_pair_desc* h_desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,16 @@ class ConvDesc(C.Structure):
     ]
 
 
+class ConvPairDesc(C.Structure):
+    """mirror of lavb_conv_pair_desc"""
+    _fields_ = [
+        ("inp", C.c_void_p), ("out", C.c_void_p), ("res", C.c_void_p),
+        ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int), ("dil", C.c_int), ("post_relu", C.c_int),
+        ("w1", C.c_void_p), ("bias1", C.c_void_p),
+        ("w2", C.c_void_p), ("bias2", C.c_void_p), ("scale2", C.c_void_p), ("shift2", C.c_void_p),
+    ]
+
+
 _SIGS = {
     "lavb_abi_version": (C.c_int, []),
     "lavb_last_error": (C.c_char_p, []),
@@ -68,6 +78,7 @@ _SIGS = {
     "lavb_convert": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "lavb_stem7x7s2_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
+    "lavb_conv_pair_umma": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lavb_maxpool3x3s2_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "lavb_det_peaks_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "lavb_det_peaks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,

@@ -1,0 +1,395 @@
+// EXPERIMENTAL (round-2 work item, not on the default path; enabled by lav_b200.erfnet.FUSE_PAIRS):
+// one kernel for a (3x1 -> 1x3) convolution pair of ERFNet's non_bottleneck_1d (lav/models/erfnet.py:37-63):
+//     mid = relu(conv3x1(x) + b1)                      (vertical taps, dilation d)
+//     out = [relu]( (conv1x3(mid) + b2) * s + t [+ res] )   (horizontal taps, dilation d; BN affine; residual)
+// Un-fused, each of the two layers is HBM-bound (the 64/128-channel layers run at ~4 TB/s effective, profiles/r01_kernels.md);
+// fused, `mid` never leaves the SM.  A tile is 128 pixels made of FULL-WIDTH image rows (W = 64 -> 2 rows, W = 32 -> 4 rows),
+// so the horizontal conv needs no halo: its zero padding is the image border.
+//   stage 1: tcgen05.mma over 3 vertical taps (A = 4-D TMA boxes shifted by the tap, B = W1 blocks) -> TMEM acc1 (2 buffers)
+//   epilogue 1: acc1 -> relu(+b1) -> bf16 -> shared memory, written three times in the SWIZZLE_128B K-major operand layout:
+//               shifted by +d, 0, -d pixels inside each image row (rows that fall off the image border stay zero), i.e. the
+//               three A operands of the horizontal taps
+//   stage 2: tcgen05.mma over the 3 horizontal taps (A = those copies, B = W2 blocks through the same TMA ring) -> TMEM acc2
+//   epilogue 2: affine / residual / ReLU -> bf16 NHWC.
+// Warp roles as conv_umma.cu (warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue), one CTA per SM, persistent.
+// MMA issue order S1(0), S1(1), S2(0), S1(2), S2(1), ... — the producer feeds the ring in exactly that order — so the
+// stage-1 MMAs of the next tile run while the epilogue warps write `mid` of the current one.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+#include "common.cuh"
+
+namespace lavb {
+namespace pair {
+
+constexpr int kBlockM = 128, kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB: one K-block of an A operand
+constexpr int kMaxStages = 8;
+constexpr int kEpiWarps = 8;
+
+struct PairArgs {
+  int n, h, w, c, kchunks, dil, tile_w, tile_h, tiles_per_img, num_tiles, stages, tmem_cols, post_relu;
+  __nv_bfloat16* out; const __nv_bfloat16* res;
+  const float* bias1; const float* bias2; const float* scale2; const float* shift2;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (same encoding as conv_umma.cu)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  const uint32_t lo = (saddr & 0x3FFFFu) >> 4;
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_pair_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                               const __grid_constant__ CUtensorMap tmap_w1,
+                                                                               const __grid_constant__ CUtensorMap tmap_w2,
+                                                                               const __grid_constant__ PairArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B operands need 1024 B alignment
+  const int w_bytes = p.c * kBlockK * 2;                            // one weight K-block: c rows x 128 B
+  const int slot_bytes = kABytes + w_bytes;
+  const uint32_t mid = base + p.stages * slot_bytes;                // [3 taps][kchunks] x 16 KB, K-major SW128
+  const int mid_bytes = 3 * p.kchunks * kABytes;
+  const uint32_t ctrl = mid + mid_bytes;
+  const uint32_t full_bar = ctrl, empty_bar = ctrl + 8 * kMaxStages, tfull1 = ctrl + 16 * kMaxStages, tempty1 = tfull1 + 16,
+                 mid_full = tempty1 + 16, tfull2 = mid_full + 8, tmem_slot = tfull2 + 8;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+  float* ep_b1 = reinterpret_cast<float*>(gen + (tmem_slot - base) + 16);     // bias of conv A
+  float* ep_st = ep_b1 + 128;                                                 // interleaved (scale, shift') of conv B
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w1)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w2)) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull1 + 8 * a, 1); mbar_init(tempty1 + 8 * a, 32 * kEpiWarps); }
+    mbar_init(mid_full, 32 * kEpiWarps);
+    mbar_init(tfull2, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int c = threadIdx.x; c < p.c; c += blockDim.x) {
+    ep_b1[c] = __ldg(p.bias1 + c);
+    const float b = p.bias2 ? __ldg(p.bias2 + c) : 0.f;
+    const float sc = p.scale2 ? __ldg(p.scale2 + c) : 1.f;
+    const float sh = p.shift2 ? __ldg(p.shift2 + c) : 0.f;
+    ep_st[2 * c] = sc;
+    ep_st[2 * c + 1] = fmaf(b, sc, sh);              // (a + b) s + t = a s + (b s + t)
+  }
+  // the shifted copies keep zero rows where a tap falls off the image border: clear `mid` once, data rows are rewritten per tile
+  for (int i = threadIdx.x; i < mid_bytes / 16; i += blockDim.x)
+    *reinterpret_cast<uint4*>(gen + (mid - base) + 16 * i) = make_uint4(0u, 0u, 0u, 0u);
+  proxy_fence_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_p;
+  const int nkb = 3 * p.kchunks;                                    // K-blocks per stage
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int slot = 0; uint32_t phase = 0;
+      auto load_stage1 = [&](int tile) {
+        const int img = tile / p.tiles_per_img, y0 = (tile - img * p.tiles_per_img) * p.tile_h;
+        for (int t = 0; t < 3; ++t)
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(empty_bar + 8 * slot, phase ^ 1);
+            const uint32_t sa = base + slot * slot_bytes;
+            mbar_expect_tx(full_bar + 8 * slot, slot_bytes);
+            tma_load_4d(sa, &tmap_a, full_bar + 8 * slot, kc * kBlockK, 0, y0 + (t - 1) * p.dil, img);
+            tma_load_2d(sa + kABytes, &tmap_w1, full_bar + 8 * slot, kc * kBlockK, t * p.c);
+            if (++slot == p.stages) { slot = 0; phase ^= 1; }
+          }
+      };
+      auto load_stage2 = [&]() {
+        for (int t = 0; t < 3; ++t)
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(empty_bar + 8 * slot, phase ^ 1);
+            const uint32_t sa = base + slot * slot_bytes;
+            mbar_expect_tx(full_bar + 8 * slot, w_bytes);
+            tma_load_2d(sa + kABytes, &tmap_w2, full_bar + 8 * slot, kc * kBlockK, t * p.c);
+            if (++slot == p.stages) { slot = 0; phase ^= 1; }
+          }
+      };
+      if ((int)blockIdx.x < p.num_tiles) load_stage1(blockIdx.x);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        if (tile + (int)gridDim.x < p.num_tiles) load_stage1(tile + gridDim.x);
+        load_stage2();
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, K-major both, N = c, M = 128 (bit layout in conv_umma.cu)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.c >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+      int slot = 0; uint32_t phase = 0;
+      uint32_t te_phase[2] = {0, 0};                 // parity of tempty1[buf] expected next
+      auto stage1 = [&](int buf) {
+        mbar_wait(tempty1 + 8 * buf, te_phase[buf] ^ 1);
+        te_phase[buf] ^= 1;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.c);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar + 8 * slot, phase);
+          tc_fence_after();
+          const uint32_t sa = base + slot * slot_bytes;
+          const uint64_t a_desc = make_sw128_desc(sa), b_desc = make_sw128_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar + 8 * slot);
+          if (++slot == p.stages) { slot = 0; phase ^= 1; }
+        }
+        umma_commit(tfull1 + 8 * buf);
+      };
+      if ((int)blockIdx.x < p.num_tiles) stage1(0);
+      int i = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
+        if (tile + (int)gridDim.x < p.num_tiles) stage1((i + 1) & 1);
+        mbar_wait(mid_full, (uint32_t)(i & 1));      // the epilogue warps have written the three shifted copies of `mid`
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(2 * p.c);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar + 8 * slot, phase);
+          tc_fence_after();
+          const uint32_t sa = base + slot * slot_bytes;
+          const uint64_t a_desc = make_sw128_desc(mid + kb * kABytes), b_desc = make_sw128_desc(sa + kABytes);   // kb = t*kchunks + kc
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar + 8 * slot);
+          if (++slot == p.stages) { slot = 0; phase ^= 1; }
+        }
+        umma_commit(tfull2);                         // acc2 complete; also: `mid` may be rewritten
+      }
+    }
+  } else {
+    const int q = warp & 3;                          // TMEM lane quarter this warp may read (warp id % 4)
+    const int half = (warp - 2) >> 2;                // the two warps of a quarter take alternate 32-column chunks
+    const int m = q * 32 + lane;                     // tile row = pixel
+    const int py = m / p.tile_w, px = m - py * p.tile_w;
+    const float lo_post = p.post_relu ? 0.f : -INFINITY;
+    const int d = p.dil;
+    // destination rows of this pixel's data in the three shifted copies (tap t reads x + (t-1) d): row m - (t-1) d
+    const bool ok0 = px + d < p.tile_w, ok2 = px - d >= 0;
+    const int r0 = m + d, r2 = m - d;
+    uint8_t* midp = gen + (mid - base);
+    int i = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
+      const int buf = i & 1;
+      const int img = tile / p.tiles_per_img, y = (tile - img * p.tiles_per_img) * p.tile_h + py;
+      const bool valid = y < p.h;
+      const long long pix = ((long long)img * p.h + y) * p.w + px;
+      // ---- epilogue 1: acc1 -> relu(+b1) -> bf16 -> three shifted K-major copies in shared memory
+      mbar_wait(tfull1 + 8 * buf, (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      for (int c0 = half * 32; c0 < p.c; c0 += 64) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.c + c0), v);
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          w[j] = pack2(fmaxf(__uint_as_float(v[2 * j]) + ep_b1[c0 + 2 * j], 0.f), fmaxf(__uint_as_float(v[2 * j + 1]) + ep_b1[c0 + 2 * j + 1], 0.f));
+        const int kc = c0 >> 6, jj0 = (c0 & 63) >> 3;            // K-block and first 16-byte piece inside the 128-byte row
+        uint8_t* blk = midp + kc * kABytes;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 val = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          const int jj = jj0 + j;
+          if (ok0) *reinterpret_cast<uint4*>(blk + 0 * p.kchunks * kABytes + r0 * 128 + ((jj ^ (r0 & 7)) << 4)) = val;
+          *reinterpret_cast<uint4*>(blk + 1 * p.kchunks * kABytes + m * 128 + ((jj ^ (m & 7)) << 4)) = val;
+          if (ok2) *reinterpret_cast<uint4*>(blk + 2 * p.kchunks * kABytes + r2 * 128 + ((jj ^ (r2 & 7)) << 4)) = val;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty1 + 8 * buf);                // acc1[buf] may be overwritten by the stage-1 MMAs of tile i+2
+      proxy_fence_async();                           // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      mbar_arrive(mid_full);
+      // ---- epilogue 2: acc2 -> affine (+ residual) -> ReLU -> bf16 NHWC
+      uint4 rr[4];
+      auto load_res = [&](int c0) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.c + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rr[j] = __ldg(rp + j);
+      };
+      if (p.res && valid) load_res(half * 32);       // requested before the accumulator wait
+      mbar_wait(tfull2, (uint32_t)(i & 1));
+      tc_fence_after();
+      for (int c0 = half * 32; c0 < p.c; c0 += 64) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * p.c + c0), v);
+        float f[32];
+        const float4* st4 = reinterpret_cast<const float4*>(ep_st + 2 * c0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 st = st4[j];
+          f[2 * j] = fmaf(__uint_as_float(v[2 * j]), st.x, st.y);
+          f[2 * j + 1] = fmaf(__uint_as_float(v[2 * j + 1]), st.z, st.w);
+        }
+        if (valid) {
+          if (p.res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t wv[4] = {rr[j].x, rr[j].y, rr[j].z, rr[j].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[e]));
+                f[j * 8 + e * 2] += t2.x; f[j * 8 + e * 2 + 1] += t2.y;
+              }
+            }
+            if (c0 + 64 < p.c) load_res(c0 + 64);
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.c + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            op[j] = make_uint4(pack2(fmaxf(f[8 * j], lo_post), fmaxf(f[8 * j + 1], lo_post)), pack2(fmaxf(f[8 * j + 2], lo_post), fmaxf(f[8 * j + 3], lo_post)),
+                               pack2(fmaxf(f[8 * j + 4], lo_post), fmaxf(f[8 * j + 5], lo_post)), pack2(fmaxf(f[8 * j + 6], lo_post), fmaxf(f[8 * j + 7], lo_post)));
+        }
+      }
+      tc_fence_before();                             // acc2 reads are ordered before this thread's next mid_full arrival
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+}  // namespace pair
+}  // namespace lavb
+
+using namespace lavb;
+using namespace lavb::pair;
+
+extern "C" int lavb_conv_pair_umma(const lavb_conv_pair_desc* d, void* stream) {
+  LAVB_CHECK_ARG(d != nullptr, "conv_pair_umma: null descriptor");
+  LAVB_CHECK_ARG(d->c == 64 || d->c == 128, "conv_pair_umma: channels must be 64 or 128 (got %d)", d->c);
+  LAVB_CHECK_ARG(d->w == 32 || d->w == 64 || d->w == 128, "conv_pair_umma: image width must be 32, 64 or 128 (a tile is made of full rows)");
+  LAVB_CHECK_ARG(d->dil >= 1 && d->dil < d->w, "conv_pair_umma: dilation must be in [1, width)");
+  LAVB_CHECK_ARG(d->n >= 0 && d->h >= 1, "conv_pair_umma: bad shape");
+  LAVB_CHECK_ARG(d->w1 && d->w2 && d->bias1 && d->in && d->out, "conv_pair_umma: null operand");
+  LAVB_CHECK_ARG((d->scale2 == nullptr) == (d->shift2 == nullptr), "conv_pair_umma: scale and shift come together");
+  if (d->n == 0) return 0;
+  auto encode = get_encode();
+  LAVB_CHECK_ARG(encode != nullptr, "conv_pair_umma: cuTensorMapEncodeTiled not available from the driver");
+  PairArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = d->n; a.h = d->h; a.w = d->w; a.c = d->c; a.kchunks = d->c / kBlockK; a.dil = d->dil;
+  a.tile_w = d->w; a.tile_h = kBlockM / d->w;
+  a.tiles_per_img = ceil_div(d->h, a.tile_h);
+  a.num_tiles = d->n * a.tiles_per_img;
+  a.post_relu = d->post_relu;
+  a.out = reinterpret_cast<__nv_bfloat16*>(d->out); a.res = reinterpret_cast<const __nv_bfloat16*>(d->res);
+  a.bias1 = d->bias1; a.bias2 = d->bias2; a.scale2 = d->scale2; a.shift2 = d->shift2;
+  const int slot_bytes = kABytes + d->c * kBlockK * 2;
+  const int mid_bytes = 3 * a.kchunks * kABytes;
+  a.stages = min(kMaxStages, (200 * 1024 - mid_bytes) / slot_bytes);
+  a.tmem_cols = d->c == 64 ? 256 : 512;          // acc1 x 2 + acc2 = 3c columns, power of two
+  CUtensorMap tmap_a, tmap_w1, tmap_w2;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->c, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+    cuuint64_t strides[3] = {(cuuint64_t)d->c * 2, (cuuint64_t)d->w * d->c * 2, (cuuint64_t)d->h * d->w * d->c * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)a.tile_w, (cuuint32_t)a.tile_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->in), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LAVB_CHECK_ARG(r == CUDA_SUCCESS, "conv_pair_umma: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  }
+  for (int which = 0; which < 2; ++which) {
+    cuuint64_t dims[2] = {(cuuint64_t)d->c, (cuuint64_t)3 * d->c};
+    cuuint64_t strides[1] = {(cuuint64_t)d->c * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)d->c};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(which ? &tmap_w2 : &tmap_w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(which ? d->w2 : d->w1), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LAVB_CHECK_ARG(r == CUDA_SUCCESS, "conv_pair_umma: cuTensorMapEncodeTiled(W%d) failed with %d", which + 1, (int)r);
+  }
+  const size_t smem = (size_t)a.stages * slot_bytes + mid_bytes + 1024 /*align*/ + 16 * kMaxStages + 96 + 3 * 128 * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    LAVB_CUDA_OK(cudaFuncSetAttribute(conv_pair_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const int grid = min(a.num_tiles, kNumSMs);
+  conv_pair_umma_kernel<<<grid, 64 + 32 * kEpiWarps, smem, (cudaStream_t)stream>>>(tmap_a, tmap_w1, tmap_w2, a);
+  LAVB_LAUNCH_OK();
+  return 0;
+}

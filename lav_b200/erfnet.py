@@ -93,6 +93,9 @@ class _Down:
         return out
 
 
+FUSE_PAIRS = False    # experimental fused (3x1 -> 1x3) tcgen05 kernel (csrc/conv_pair_umma.cu); off until validated on the GPU
+
+
 class _NB1D:
     def __init__(self, m):
         d = m.conv3x1_2.dilation[0]
@@ -104,6 +107,11 @@ class _NB1D:
         self.d = TapConv(m.conv1x3_2.weight, False, 1, (0, d), (1, d), bias=m.conv1x3_2.bias, scale=s2, shift=t2, post_relu=True)
 
     def __call__(self, x, dt):
+        if FUSE_PAIRS and x.dtype == torch.bfloat16 and self.a.umma_ok and x.shape[3] in (64, 128) and x.shape[2] in (32, 64, 128):
+            # experimental: each (3x1 -> 1x3) pair in one tcgen05 kernel, the intermediate stays in shared memory
+            a, b, c, d = (t.phases[0]["w_umma"] for t in (self.a, self.b, self.c, self.d))
+            y = ops.conv_pair_umma(x, a, self.a.bias, b, self.b.bias, self.b.scale, self.b.shift, 1)
+            return ops.conv_pair_umma(y, c, self.c.bias, d, self.d.bias, self.d.scale, self.d.shift, self.c.dilation[0], res=x)
         y = self.a(x)
         y = self.b(y)
         y = self.c(y)

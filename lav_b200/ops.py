@@ -385,3 +385,30 @@ def maxpool3x3s2_nhwc(x):
     check(lib().lavb_maxpool3x3s2_nhwc(_ptr(x), n, h, w, c, _ptr(out), _stream()), "lavb_maxpool3x3s2_nhwc")
     _COUNT[0] += 1
     return out
+
+
+def conv_pair_umma(x, w1, bias1, w2, bias2, scale2, shift2, dil, res=None, post_relu=True):
+    """EXPERIMENTAL fused pair: relu(conv3x1_dil(x) + bias1) -> conv1x3_dil -> (+bias2) * scale2 + shift2 [+ res] [-> relu].
+    x / res: contiguous bf16 NHWC (n, h, w, c), c in {64, 128}, w in {32, 64, 128}; w1 / w2: (3, c, c) bf16 [tap][cout][cin]."""
+    from .capi import ConvPairDesc
+    _need_cuda(x, w1, w2)
+    n, h, w, c = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and w1.is_contiguous() and w2.is_contiguous()
+    assert tuple(w1.shape) == (3, c, c) and tuple(w2.shape) == (3, c, c) and w1.dtype == w2.dtype == torch.bfloat16
+    out = torch.empty_like(x)
+    d = ConvPairDesc()
+    d.inp, d.out = x.data_ptr(), out.data_ptr()
+    d.n, d.h, d.w, d.c, d.dil, d.post_relu = n, h, w, c, int(dil), int(post_relu)
+    d.w1, d.bias1 = w1.data_ptr(), bias1.data_ptr()
+    d.w2 = w2.data_ptr()
+    d.bias2 = bias2.data_ptr() if bias2 is not None else None
+    d.scale2 = scale2.data_ptr() if scale2 is not None else None
+    d.shift2 = shift2.data_ptr() if shift2 is not None else None
+    if res is not None:
+        assert res.is_contiguous() and res.shape == x.shape and res.dtype == torch.bfloat16
+        d.res = res.data_ptr()
+    e0 = _prof_begin()
+    check(lib().lavb_conv_pair_umma(C.byref(d), _stream()), "lavb_conv_pair_umma")
+    _prof_end(f"umma_pair:{c}x{h}x{w}", 2.0 * n * h * w * c * c * 6, e0)
+    _COUNT[0] += 1
+    return out

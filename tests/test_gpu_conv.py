@@ -243,3 +243,30 @@ def test_brake_forward_u8_matches_forward(cuda):
         a = m(wide, tel.permute(0, 3, 1, 2).float()).float()
         b = m.forward_u8(rgbs, tel).float()
     assert (a - b).abs().max().item() < 2e-2, (a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.environ.get("LAVB_EXPERIMENTAL"), reason="experimental fused-pair kernel: set LAVB_EXPERIMENTAL=1")
+@pytest.mark.parametrize("cfg", [(3, 72, 64, 64, 1, True), (2, 36, 32, 128, 2, True), (2, 36, 32, 128, 16, True), (1, 7, 64, 64, 1, False)])
+def test_conv_pair_umma_vs_torch(cuda, cfg):
+    """lavb_conv_pair_umma == relu(conv3x1) -> conv1x3 -> affine (+res) -> relu of erfnet.py:37-63, bf16 operands, tol 1e-2."""
+    from lav_b200 import ops
+    n, h, w, c, dil, use_res = cfg
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(n, c, h, w, generator=g)
+    w1 = torch.randn(c, c, 3, 1, generator=g) * (1.0 / (3 * c) ** 0.5)
+    w2 = torch.randn(c, c, 1, 3, generator=g) * (1.0 / (3 * c) ** 0.5)
+    b1, b2 = torch.randn(c, generator=g) * 0.1, torch.randn(c, generator=g) * 0.1
+    s2, t2 = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    bf = lambda t: t.to(torch.bfloat16).float()
+    mid = bf(F.relu(F.conv2d(bf(x), bf(w1), b1, padding=(dil, 0), dilation=(dil, 1))))
+    ref = F.conv2d(mid, bf(w2), b2, padding=(0, dil), dilation=(1, dil)) * s2[None, :, None, None] + t2[None, :, None, None]
+    if use_res:
+        ref = ref + bf(x)
+    ref = F.relu(ref).permute(0, 2, 3, 1)
+    xd = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    w1u = w1[:, :, :, 0].permute(2, 0, 1).contiguous().to(torch.bfloat16).cuda()       # [tap][cout][cin]
+    w2u = w2[:, :, 0, :].permute(2, 0, 1).contiguous().to(torch.bfloat16).cuda()
+    out = ops.conv_pair_umma(xd, w1u, b1.cuda(), w2u, b2.cuda(), s2.cuda(), t2.cuda(), dil, res=xd if use_res else None).float().cpu()
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-2, err
