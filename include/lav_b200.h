@@ -217,6 +217,14 @@ typedef struct lavb_conv_pair_desc {
 } lavb_conv_pair_desc;
 int lavb_conv_pair_umma(const lavb_conv_pair_desc* h_desc, void* stream);
 
+/* ---------------------------------------------------------------- EXPERIMENTAL: cluster-persistent GRU roll-out
+ * replaces: one call of plan_gru = nn.GRU(4, 512, batch_first=True) (team_code_v2/models/uniplanner.py:45,247-259;
+ * lav/models/bev_planner_v2.py) over `steps` time steps for `nseq` sequences.  Not on the default path (round-2 work item).
+ * d_u (nseq, steps, 4) fp32; d_h0 (nseq, 512) fp32; d_whh_bf16 = weight_hh_l0 (1536, 512) as bf16; d_wih = weight_ih_l0
+ * (1536, 4), d_bih / d_bhh (1536,) fp32; d_out (nseq, steps, 512) fp32 = the GRU's output sequence. */
+int lavb_gru_h512(const float* d_u, const float* d_h0, const void* d_whh_bf16, const float* d_wih, const float* d_bih,
+                  const float* d_bhh, float* d_out, int nseq, int steps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,6 +145,9 @@ def resnet18(pretrained=False, num_channels=3, **kw):
     return ResNet18(num_channels=num_channels)
 
 
+GRU_KERNEL = False    # experimental cluster-persistent plan GRU (csrc/gru_cluster.cu); off until validated and timed on the GPU
+
+
 # ----------------------------------------------------------------------------- planners
 def transform_points(locs, oris):
     cos, sin = torch.cos(oris), torch.sin(oris)
@@ -207,7 +210,19 @@ def _plan_rollout(plan_gru, plan_mlp, num_cmds, num_plan, num_plan_iter, embd, n
     outs = []
     for _ in range(num_plan_iter):
         u = torch.cat([u0[:, None, None].expand(B, num_cmds, num_plan, 2), plan_loc], dim=3)
-        out, _ = plan_gru(u.reshape(B * num_cmds, num_plan, 4), h0)
+        if GRU_KERNEL and u.is_cuda and not torch.is_grad_enabled() and plan_gru.hidden_size == 512 and plan_gru.input_size == 4:
+            # experimental: the whole 20-step roll-out in one cluster-persistent kernel (csrc/gru_cluster.cu)
+            from . import ops
+            whh = plan_gru.weight_hh_l0
+            key = (whh.data_ptr(), whh._version, str(whh.device))
+            cached = plan_gru.__dict__.get("_whh_bf16")
+            if cached is None or cached[0] != key:      # re-derive after load_state_dict / .to()
+                cached = plan_gru.__dict__["_whh_bf16"] = (key, whh.detach().to(torch.bfloat16).contiguous())
+            wb = cached[1]
+            out = ops.gru_h512(u.reshape(B * num_cmds, num_plan, 4).float(), h0[0].float(), wb, plan_gru.weight_ih_l0.detach().float(),
+                               plan_gru.bias_ih_l0.detach().float(), plan_gru.bias_hh_l0.detach().float())
+        else:
+            out, _ = plan_gru(u.reshape(B * num_cmds, num_plan, 4), h0)
         plan_loc = torch.cumsum(plan_mlp(out), dim=1).view(B, num_cmds, num_plan, 2) + plan_loc
         outs.append(plan_loc)
     return torch.stack(outs, dim=1)

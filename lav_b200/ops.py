@@ -412,3 +412,19 @@ def conv_pair_umma(x, w1, bias1, w2, bias2, scale2, shift2, dil, res=None, post_
     _prof_end(f"umma_pair:{c}x{h}x{w}", 2.0 * n * h * w * c * c * 6, e0)
     _COUNT[0] += 1
     return out
+
+
+def gru_h512(u, h0, whh_bf16, wih, bih, bhh):
+    """EXPERIMENTAL cluster-persistent GRU(4 -> 512) roll-out.  u (N, T, 4) fp32, h0 (N, 512) fp32, whh_bf16 (1536, 512) bf16,
+    wih (1536, 4), bih / bhh (1536,) fp32 -> out (N, T, 512) fp32 (the output sequence of nn.GRU(batch_first=True))."""
+    _need_cuda(u, h0, whh_bf16)
+    n, t, k = u.shape
+    assert k == 4 and tuple(h0.shape) == (n, 512) and tuple(whh_bf16.shape) == (1536, 512) and whh_bf16.dtype == torch.bfloat16
+    assert u.dtype == h0.dtype == wih.dtype == bih.dtype == bhh.dtype == torch.float32
+    u, h0 = u.contiguous(), h0.contiguous()
+    assert whh_bf16.is_contiguous() and wih.is_contiguous()
+    out = torch.empty((n, t, 512), dtype=torch.float32, device=u.device)
+    check(lib().lavb_gru_h512(_ptr(u), _ptr(h0), _ptr(whh_bf16), _ptr(wih), _ptr(bih), _ptr(bhh), _ptr(out), n, t, _stream()),
+          "lavb_gru_h512")
+    _COUNT[0] += 1
+    return out

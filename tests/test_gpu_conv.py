@@ -270,3 +270,22 @@ def test_conv_pair_umma_vs_torch(cuda, cfg):
     out = ops.conv_pair_umma(xd, w1u, b1.cuda(), w2u, b2.cuda(), s2.cuda(), t2.cuda(), dil, res=xd if use_res else None).float().cpu()
     err = (out - ref).abs().max().item() / ref.abs().max().item()
     assert err < 1e-2, err
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.environ.get("LAVB_EXPERIMENTAL"), reason="experimental cluster GRU kernel: set LAVB_EXPERIMENTAL=1")
+@pytest.mark.parametrize("nseq", [192, 48, 7])
+def test_gru_cluster_vs_torch(cuda, nseq):
+    """lavb_gru_h512 == nn.GRU(4, 512, batch_first=True) output sequence (uniplanner.py:45,247-259); bf16 recurrent weights and
+    hidden-state copy on the tensor cores, fp32 state: tol 2e-2 of the output scale over 20 steps."""
+    from lav_b200 import ops
+    torch.manual_seed(0)
+    gru = torch.nn.GRU(4, 512, batch_first=True).cuda()
+    u = torch.randn(nseq, 20, 4, device="cuda")
+    h0 = torch.randn(nseq, 512, device="cuda") * 0.5
+    with torch.no_grad():
+        ref, _ = gru(u, h0[None])
+        out = ops.gru_h512(u, h0, gru.weight_hh_l0.to(torch.bfloat16).contiguous(), gru.weight_ih_l0.contiguous(),
+                           gru.bias_ih_l0.contiguous(), gru.bias_hh_l0.contiguous())
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-2, err
