@@ -353,9 +353,9 @@ def main():
                         "d2h_bytes_per_step": int(B * 20 * 2 * 4 + B * 4)},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": roof.get("umma"), "roofline_heads_conv": roof.get("umma_all"), "roofline_pillar": roof.get("pillar")}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # bounded sample (~10-15 s of host work), rank 0 at N=1 only
             a2 = argparse.Namespace(**vars(args))
-            a2.steps, a2.warmup = 3, 1
+            a2.steps, a2.warmup = 24, 2
             import io
             import contextlib
             buf = io.StringIO()
