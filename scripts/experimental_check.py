@@ -1,0 +1,59 @@
+"""Round-2 entry point for the two prepared kernels: numerics + timing, flag off vs on, on one GPU.
+  python scripts/experimental_check.py [B]
+ERFNet with erfnet.FUSE_PAIRS (fused 3x1->1x3 tcgen05 pairs) and the planner roll-out with heads.GRU_KERNEL
+(cluster-persistent GRU).  Prints max-norm difference of the outputs and CUDA-graph replay times."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from lav_b200 import erfnet, heads, synth
+from tests import util
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+dev = torch.device("cuda:0")
+
+
+def graph_time(fn, iters=10):
+    for _ in range(2):
+        out = fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters, out
+
+
+with torch.no_grad():
+    seg, _ = util.seg_model(dev)
+    seg.set_precision("bf16")
+    rgb = synth.rgb_frames().to(dev).repeat(B, 1, 1, 1)
+    res = {}
+    for flag in (False, True):
+        erfnet.FUSE_PAIRS = flag
+        ms, out = graph_time(lambda: seg.forward_nhwc(rgb))
+        res[flag] = (ms, out.float().clone())
+    d = (res[True][1] - res[False][1]).abs().max().item() / res[False][1].abs().max().item()
+    print(f"ERFNet {3 * B} images: unfused {res[False][0]:.3f} ms, fused pairs {res[True][0]:.3f} ms, max-norm diff {d:.2e}")
+    erfnet.FUSE_PAIRS = False
+
+    up, _ = util.uniplanner(dev) if hasattr(util, "uniplanner") else (None, None)
+    gru = up.plan_gru if up is not None else torch.nn.GRU(4, 512, batch_first=True).to(dev)
+    mlp = up.plan_mlp if up is not None else torch.nn.Linear(512, 2).to(dev)
+    embd = torch.randn(B, 512, device=dev) * 0.5
+    nxp = torch.tensor([[0.0, -20.0]] * B, device=dev)
+    cast = torch.randn(B, 6, 20, 2, device=dev) * 0.1
+    res = {}
+    for flag in (False, True):
+        heads.GRU_KERNEL = flag
+        ms, out = graph_time(lambda: heads._plan_rollout(gru, mlp, 6, 20, 5, embd, nxp, cast, 4, 192))
+        res[flag] = (ms, out.float().clone())
+    d = (res[True][1] - res[False][1]).abs().max().item() / res[False][1].abs().max().item()
+    print(f"plan roll-out {6 * B} sequences x 20 steps x 5 iterations: cuDNN {res[False][0]:.3f} ms, cluster kernel {res[True][0]:.3f} ms, "
+          f"max-norm diff {d:.2e}")
+    heads.GRU_KERNEL = False
