@@ -247,7 +247,8 @@ def test_brake_forward_u8_matches_forward(cuda):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.environ.get("LAVB_EXPERIMENTAL"), reason="experimental fused-pair kernel: set LAVB_EXPERIMENTAL=1")
-@pytest.mark.parametrize("cfg", [(3, 72, 64, 64, 1, True), (2, 36, 32, 128, 2, True), (2, 36, 32, 128, 16, True), (1, 7, 64, 64, 1, False)])
+@pytest.mark.parametrize("cfg", [(3, 72, 64, 64, 1, True), (2, 36, 32, 128, 2, True), (2, 36, 32, 128, 16, True), (1, 7, 64, 64, 1, False),
+                                 (24, 72, 64, 64, 1, True), (96, 36, 32, 128, 4, True)])   # last two: several tiles per CTA (persistent loop)
 def test_conv_pair_umma_vs_torch(cuda, cfg):
     """lavb_conv_pair_umma == relu(conv3x1) -> conv1x3 -> affine (+res) -> relu of erfnet.py:37-63, bf16 operands, tol 1e-2."""
     from lav_b200 import ops
