@@ -5,7 +5,6 @@ reference's logical shape (N, 5, H, W), stored channels-last.  ``forward_u8`` in
 frames as the agent holds them (uint8 HWC, lav_agent.py:243) without a float round trip.
 The brake model (RGBBrakePredictionModel) stays a PyTorch head: see lav_b200/heads.py.
 """
-import torch
 from torch import nn
 
 from . import ops
