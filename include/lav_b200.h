@@ -203,6 +203,13 @@ int lavb_convert(const void* d_src, int src_dtype, void* d_dst, int dst_dtype, l
  * (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint), accumulators live in TMEM. */
 int lavb_conv_umma(const lavb_conv_desc* h_desc, void* stream);
 
+/* ---------------------------------------------------------------- EXPERIMENTAL: halo-patch variant of lavb_conv_umma
+ * Same descriptor and semantics as lavb_conv_umma for plain stride-1 same-size convolutions with bf16 output (no sigmoid, no
+ * depth-to-space): each tile's input is fetched once as a halo patch and the taps read it through shifted shared-memory
+ * descriptors.  Returns 4 when the layer is outside its coverage or the patch would not pay (callers then use lavb_conv_umma).
+ * Not on the default path (round-2 work item). */
+int lavb_conv_halo_umma(const lavb_conv_desc* h_desc, void* stream);
+
 /* ---------------------------------------------------------------- EXPERIMENTAL: fused (3x1 -> 1x3) convolution pair
  * replaces: conv3x1_k -> ReLU -> conv1x3_k -> bn_k [-> + input] -> ReLU of non_bottleneck_1d (lav/models/erfnet.py:37-63) in
  * one tcgen05 kernel; the intermediate activation stays in shared memory.  Not on the default path (round-2 work item).

@@ -90,6 +90,7 @@ _SIGS = {
     "lavb_deconv3x3s2_small": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lavb_conv_umma": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "lavb_conv_halo_umma": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
 }
 
 _lib = None

@@ -290,3 +290,35 @@ def test_gru_cluster_vs_torch(cuda, nseq):
                            gru.bias_ih_l0.contiguous(), gru.bias_hh_l0.contiguous())
     err = (out - ref).abs().max().item() / ref.abs().max().item()
     assert err < 2e-2, err
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.environ.get("LAVB_EXPERIMENTAL"), reason="experimental halo-patch conv kernel: set LAVB_EXPERIMENTAL=1")
+@pytest.mark.parametrize("cfg", [
+    # (n, h, w, cin, cout, kh, kw, dil, pre_relu_affine, residual)
+    (2, 40, 24, 64, 64, 3, 3, 1, True, False),        # backbone-style Conv -> ReLU -> BN, partial tiles in both directions
+    (3, 72, 64, 64, 64, 3, 1, 1, False, False),       # ERFNet 3x1
+    (2, 36, 32, 128, 128, 3, 1, 4, False, True),      # dilated 3x1 + residual, streamed weights do not apply (resident)
+    (2, 80, 80, 128, 128, 3, 3, 1, True, False),      # weights streamed through their own ring
+    (32, 160, 160, 64, 64, 3, 3, 1, True, False),     # many tiles per CTA
+])
+def test_conv_halo_umma_vs_umma(cuda, cfg, monkeypatch):
+    """lavb_conv_halo_umma == lavb_conv_umma (same descriptor, same bf16 operands): results must agree to accumulation-order noise."""
+    from lav_b200 import layers
+    n, h, w, cin, cout, kh, kw, dil, pre, use_res = cfg
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(n, h, w, cin, generator=g)).to(torch.bfloat16).cuda()
+    wt = torch.randn(cout, cin, kh, kw, generator=g) * (1.0 / (kh * kw * cin) ** 0.5)
+    bias = torch.randn(cout, generator=g) * 0.1
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    pad = (dil * (kh // 2), dil * (kw // 2))
+    conv = layers.TapConv(wt.cuda(), False, 1, pad, (dil if kh > 1 else 1, dil if kw > 1 else 1), bias=None if pre else bias.cuda(),
+                          pre_relu=pre, scale=scale.cuda(), shift=shift.cuda(), post_relu=not pre)
+    res = x if use_res else None
+    monkeypatch.setattr(layers, "USE_HALO", False)
+    ref = conv(x, res=res).float()
+    monkeypatch.setattr(layers, "USE_HALO", True)
+    out = conv(x, res=res).float()
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 4e-3, err          # both paths round the output to bf16; only the accumulation order differs
