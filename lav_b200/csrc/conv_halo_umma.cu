@@ -300,9 +300,11 @@ extern "C" int lavb_conv_halo_umma(const lavb_conv_desc* d, void* stream) {
   LAVB_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= kMaxTaps, "conv_halo_umma: ntaps must be 1..16");
   LAVB_CHECK_ARG(d->cin % 64 == 0 && d->cin > 0, "conv_halo_umma: cin must be a multiple of 64 (got %d)", d->cin);
   LAVB_CHECK_ARG(d->cout % 8 == 0 && d->cout >= 8 && d->cout <= 256, "conv_halo_umma: cout must be 8..256, multiple of 8 (got %d)", d->cout);
-  LAVB_CHECK_ARG(d->in_sy == 1 && d->in_sx == 1 && d->out_sy == 1 && d->out_sx == 1 && d->out_oy == 0 && d->out_ox == 0 &&
-                 d->hog == d->hout && d->wog == d->wout && d->hin == d->hout && d->win == d->wout && d->d2s_nout == 0 && !d->sigmoid,
-                 "conv_halo_umma: plain stride-1 same-size convolutions only");
+  if (!(d->in_sy == 1 && d->in_sx == 1 && d->out_sy == 1 && d->out_sx == 1 && d->out_oy == 0 && d->out_ox == 0 &&
+        d->hog == d->hout && d->wog == d->wout && d->hin == d->hout && d->win == d->wout && d->d2s_nout == 0 && !d->sigmoid)) {
+    set_error("conv_halo_umma: plain stride-1 same-size convolutions only");
+    return 4;
+  }
   const int cout_mma = (d->cout + 31) / 32 * 32;
   LAVB_CHECK_ARG(d->res == nullptr || (cout_mma == d->cout && d->res_dtype == LAVB_BF16 && d->res_cstride % 8 == 0 && d->res_coff % 8 == 0),
                  "conv_halo_umma: residual must be bf16, 16 B aligned, cout %% 32 == 0");
