@@ -1,7 +1,7 @@
 """Round-2 entry point for the two prepared kernels: numerics + timing, flag off vs on, on one GPU.
   python scripts/experimental_check.py [B]
-ERFNet with erfnet.FUSE_PAIRS (fused 3x1->1x3 tcgen05 pairs) and the planner roll-out with heads.GRU_KERNEL
-(cluster-persistent GRU).  Prints max-norm difference of the outputs and CUDA-graph replay times."""
+ERFNet with erfnet.FUSE_PAIRS (fused 3x1->1x3 tcgen05 pairs), ERFNet / BEV backbone with layers.USE_HALO (halo-patch conv)
+and the planner roll-out with heads.GRU_KERNEL (cluster-persistent GRU).  Prints max-norm difference of the outputs and CUDA-graph replay times."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -41,6 +41,21 @@ with torch.no_grad():
     d = (res[True][1] - res[False][1]).abs().max().item() / res[False][1].abs().max().item()
     print(f"ERFNet {3 * B} images: unfused {res[False][0]:.3f} ms, fused pairs {res[True][0]:.3f} ms, max-norm diff {d:.2e}")
     erfnet.FUSE_PAIRS = False
+
+    # halo-patch conv kernel: ERFNet (its 3x1 layers) and the BEV backbone (3x3 layers)
+    from lav_b200 import layers
+    lid, _ = util.lidar_model(dev)
+    lid.set_precision("bf16")
+    canvas = (torch.randn(B, 320, 320, 128, device=dev) * 0.3).to(torch.bfloat16)      # [hi | lo] split canvas
+    for name, fn in (("ERFNet", lambda: seg.forward_nhwc(rgb)), ("backbone", lambda: lid.backbone.forward_nhwc(canvas))):
+        res = {}
+        for flag in (False, True):
+            layers.USE_HALO = flag
+            ms, out = graph_time(fn)
+            res[flag] = (ms, out.float().clone())
+        d = (res[True][1] - res[False][1]).abs().max().item() / res[False][1].abs().max().item()
+        print(f"{name}: per-tap tiles {res[False][0]:.3f} ms, halo patches {res[True][0]:.3f} ms, max-norm diff {d:.2e}")
+    layers.USE_HALO = False
 
     up, _ = util.uniplanner(dev) if hasattr(util, "uniplanner") else (None, None)
     gru = up.plan_gru if up is not None else torch.nn.GRU(4, 512, batch_first=True).to(dev)
