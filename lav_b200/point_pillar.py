@@ -33,6 +33,7 @@ class _PillarScatterMax(torch.autograd.Function):
     """scatter_max over canvas cells with arg-routed backward (torch_scatter.scatter_max semantics)."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)     # under autocast the point MLP hands over bf16
     def forward(ctx, h, cell, n_cells):
         canvas, arg = ops.pillar_scatter_max(h, cell, n_cells, want_argmax=True)
         ctx.save_for_backward(arg, cell)
@@ -40,6 +41,7 @@ class _PillarScatterMax(torch.autograd.Function):
         return canvas
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g):
         arg, cell = ctx.saved_tensors
         return ops.pillar_scatter_max_bwd(g, arg, cell, ctx.m), None, None

@@ -14,6 +14,8 @@ The full step (``LAVTrainer.train_lidar``) adds the UniPlanner distillation bran
 frozen BEVPlanner teacher under no_grad (lav_b200/heads.py, pinned bit-exact against the reference on CPU) — and the
 motion losses of lav_final_v2.py:190-225.
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
 from torch import nn
@@ -168,7 +170,7 @@ class LAVTrainer:
 
     def __init__(self, lidar_model, uniplanner, lr=3e-4, device=None, box_weight=1.0, ori_weight=1.0, seg_weight=2.0,
                  perception_weight=4.0, other_weight=0.5, cmd_weight=0.1, branch_weights=(5, 5, 5, 1, 1, 1), distill=True,
-                 cmd_smooth=0.2, perceive_only=False, motion_only=False, bucket_bytes=25 << 20):
+                 cmd_smooth=0.2, perceive_only=False, motion_only=False, bucket_bytes=25 << 20, amp=False):
         self.lidar_model, self.uniplanner = lidar_model.train(), uniplanner.train()
         uniplanner.bev_planner.eval()
         for p in uniplanner.bev_planner.parameters():
@@ -189,6 +191,9 @@ class LAVTrainer:
         self.w = dict(box=box_weight, ori=ori_weight, seg=seg_weight, perc=perception_weight, other=other_weight, cmd=cmd_weight)
         self.distill, self.cmd_smooth = distill, cmd_smooth
         self.perceive_only, self.motion_only = perceive_only, motion_only
+        # amp=True: model forwards under bf16 autocast (fp32 master weights, losses and Adam in fp32).  The reference trains in
+        # fp32 (cuDNN TF32); this is an opt-in throughput mode, off by default and not yet measured.
+        self.amp = bool(amp)
 
     def losses(self, lidars, num_points, heatmaps, sizemaps, orimaps, bev, ego_locs, cmds, nxps, bras, locs, oris, typs):
         up = self.uniplanner
@@ -196,11 +201,16 @@ class LAVTrainer:
         seg_bev = bev[:, [0, 1, 2]]
         cmds = cmds.long()
         idxs = (1 - bras).bool()
-        outs = self.lidar_model(lidars, num_points)
-        features, ph, ps, po, pb = outs
+        ctx = torch.autocast("cuda", dtype=torch.bfloat16) if self.amp else contextlib.nullcontext()
+        with ctx:
+            outs = self.lidar_model(lidars, num_points)
+            features, ph, ps, po, pb = outs
+            planner_out = up(features, bev, ego_locs.float(), locs.float(), oris.float(), nxps.float(), typs)
+        if self.amp:       # losses in fp32
+            ph, ps, po, pb = ph.float(), ps.float(), po.float(), pb.float()
+            planner_out = tuple(t.float() if torch.is_floating_point(t) else t for t in planner_out)
         (other_next_locs, other_cast_locs, other_cast_cmds, other_cast_locs_expert, other_cast_cmds_expert, ego_next_locs,
-         ego_plan_locs, ego_cast_locs, ego_cast_cmds, ego_cast_locs_expert, ego_plan_locs_expert) = up(
-            features, bev, ego_locs.float(), locs.float(), oris.float(), nxps.float(), typs)
+         ego_plan_locs, ego_cast_locs, ego_cast_cmds, ego_cast_locs_expert, ego_plan_locs_expert) = planner_out
         hm, box, ori = DetLoss()(ph, heatmaps, ps, sizemaps, po, orimaps)
         det_loss = hm + self.w["box"] * box + self.w["ori"] * ori
         seg_loss = torch.mean(F.binary_cross_entropy(pb, seg_bev, reduction='none') * self.seg_mask) * self.w["seg"]

@@ -6,14 +6,14 @@ import torch, torch.distributed as dist
 import bench
 from lav_b200.train import LAVTrainer, synthetic_train_batch
 
-ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=32); ap.add_argument("--steps", type=int, default=5)
+ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=32); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--amp", action="store_true", help="bf16 autocast forwards (opt-in)")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 (seg, lid, uni, bra), _ = bench.build_models()
-tr = LAVTrainer(lid.to(dev), uni.to(dev), device=dev)
+tr = LAVTrainer(lid.to(dev), uni.to(dev), device=dev, amp=args.amp)
 batch = synthetic_train_batch(args.batch, dev, seed=2021 + rank)
 for _ in range(2):
     tr.train_lidar(*batch)
