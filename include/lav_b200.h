@@ -203,6 +203,11 @@ int lavb_convert(const void* d_src, int src_dtype, void* d_dst, int dst_dtype, l
  * (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint), accumulators live in TMEM. */
 int lavb_conv_umma(const lavb_conv_desc* h_desc, void* stream);
 
+/* ---------------------------------------------------------------- EXPERIMENTAL: lavb_conv_umma with 2 CTAs/SM x 8 epilogue warps
+ * Same descriptor and semantics as lavb_conv_umma; covers layers with cout <= 128 and no depth-to-space epilogue, returns 4
+ * otherwise (callers then use lavb_conv_umma).  Not on the default path (round-2 work item). */
+int lavb_conv_umma16(const lavb_conv_desc* h_desc, void* stream);
+
 /* ---------------------------------------------------------------- EXPERIMENTAL: halo-patch variant of lavb_conv_umma
  * Same descriptor and semantics as lavb_conv_umma for plain stride-1 same-size convolutions with bf16 output (no sigmoid, no
  * depth-to-space): each tile's input is fetched once as a halo patch and the taps read it through shifted shared-memory

@@ -91,6 +91,7 @@ _SIGS = {
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lavb_conv_umma": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "lavb_conv_halo_umma": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "lavb_conv_umma16": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
 }
 
 _lib = None

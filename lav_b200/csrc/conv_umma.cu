@@ -16,6 +16,11 @@
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
 #include <stdlib.h>
+// conv_umma16.cu re-includes this file with these two set to 2 / 8 (8 epilogue warps AND two CTAs per SM for the narrow layers)
+#ifndef LAVB_UMMA_EW8_MINBLOCKS
+#define LAVB_UMMA_EW8_MINBLOCKS 1
+#define LAVB_UMMA_NARROW_EW 4
+#endif
 #include <cudaTypedefs.h>
 #include "common.cuh"
 
@@ -105,7 +110,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // kEpiWarps = 4: one warp per quarter and TWO co-resident CTAs per SM (half the smem ring each): two independent tile
 //                pipelines hide the per-tile serial chain (commit -> epilogue -> tmem_empty) of the narrow layers.
 template <bool kOutF32, bool kRes, bool kSigmoid, bool kPreBias, int kEpiWarps, bool kD2S = false>
-__global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : 1) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : LAVB_UMMA_EW8_MINBLOCKS) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                 const __grid_constant__ CUtensorMap tmap_b,
                                                                 const __grid_constant__ UmmaArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -419,7 +424,7 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   }
 #define LAVB_UMMA_CASE(F, R, S, B)                                                                                      \
   if (f32 == F && res == R && sig == S && pb == B) {                                                                    \
-    if (two_per_sm) LAVB_UMMA_LAUNCH(F, R, S, B, 4) else LAVB_UMMA_LAUNCH(F, R, S, B, 8)                                \
+    if (two_per_sm) LAVB_UMMA_LAUNCH(F, R, S, B, LAVB_UMMA_NARROW_EW) else LAVB_UMMA_LAUNCH(F, R, S, B, 8)              \
   }
   LAVB_UMMA_CASE(false, false, false, false) LAVB_UMMA_CASE(false, true, false, false)
   LAVB_UMMA_CASE(true, false, false, false)  LAVB_UMMA_CASE(true, true, false, false)

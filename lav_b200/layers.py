@@ -12,6 +12,7 @@ from . import ops
 USE_UMMA = True   # tests flip this to compare the tcgen05 path with the CUDA-core path
 UMMA_STRIDED = True   # stride-2 convs through the tensor map's element strides
 USE_HALO = False      # experimental halo-patch tcgen05 kernel (csrc/conv_halo_umma.cu) for stride-1 layers with cout <= 128
+USE_EPI16 = False     # experimental: narrow layers (cout <= 128) with 2 CTAs/SM x 8 epilogue warps (csrc/conv_umma16.cu)
 
 
 def bn_affine(bn, eps=None):
@@ -115,7 +116,8 @@ class TapConv:
                     and (UMMA_STRIDED or ph["in_s"] == (1, 1)))
             ops.conv_taps(x, self.cin_k, in_coff, out, self.cout, out_coff, hog, wog, ph["in_s"], ph["out_s"], ph["out_o"],
                           ph["taps"], ph["w_umma"] if umma else ph["w"], self.bias, self.scale, self.shift, res, res_coff,
-                          self.pre_relu, self.post_relu, self.sigmoid, umma=umma, halo=umma and USE_HALO and self.cout <= 128)
+                          self.pre_relu, self.post_relu, self.sigmoid, umma=umma, halo=umma and USE_HALO and self.cout <= 128,
+                          epi16=umma and USE_EPI16 and self.cout <= 128)
         return out
 
 

@@ -163,7 +163,7 @@ def pillar_scatter_max_bwd(gcanvas, arg, cell, m):
 
 # ----------------------------------------------------------------------------- convolution
 def conv_taps(x, cin, in_coff, out, cout, out_coff, hog, wog, in_s, out_s, out_o, taps, w, bias=None, scale=None, shift=None,
-              res=None, res_coff=0, pre_relu=False, post_relu=False, sigmoid=False, umma=False, d2s_nout=0, halo=False):
+              res=None, res_coff=0, pre_relu=False, post_relu=False, sigmoid=False, umma=False, d2s_nout=0, halo=False, epi16=False):
     """x, out, res: contiguous NHWC buffers (N,H,W,Ctot).  taps: list of (dy,dx).
     umma=False: CUDA-core kernel, w (ntaps,cin,cout_pad16) fp32.
     umma=True : tcgen05 kernel, x bf16, w (ntaps,cout,cin) bf16."""
@@ -207,6 +207,10 @@ def conv_taps(x, cin, in_coff, out, cout, out_coff, hog, wog, in_s, out_s, out_o
             rc = lib().lavb_conv_halo_umma(C.byref(d), _stream())       # experimental; 4 = "not covered / does not pay"
             if rc not in (0, 4):
                 check(rc, "lavb_conv_halo_umma")
+        if rc == 4 and epi16:
+            rc = lib().lavb_conv_umma16(C.byref(d), _stream())          # experimental; 4 = "not covered"
+            if rc not in (0, 4):
+                check(rc, "lavb_conv_umma16")
         if rc == 4:
             check(lib().lavb_conv_umma(C.byref(d), _stream()), "lavb_conv_umma")
         _prof_end(f"umma:{cin}->{cout}x{len(taps)}taps@{hog}x{wog}", 2.0 * x.shape[0] * hog * wog * cout * cin * len(taps), e0)

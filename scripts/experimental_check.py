@@ -56,6 +56,15 @@ with torch.no_grad():
         d = (res[True][1] - res[False][1]).abs().max().item() / res[False][1].abs().max().item()
         print(f"{name}: per-tap tiles {res[False][0]:.3f} ms, halo patches {res[True][0]:.3f} ms, max-norm diff {d:.2e}")
     layers.USE_HALO = False
+    for name, fn in (("ERFNet", lambda: seg.forward_nhwc(rgb)), ("backbone", lambda: lid.backbone.forward_nhwc(canvas))):
+        res = {}
+        for flag in (False, True):
+            layers.USE_EPI16 = flag
+            ms, out = graph_time(fn)
+            res[flag] = (ms, out.float().clone())
+        d = (res[True][1] - res[False][1]).abs().max().item()
+        print(f"{name}: 2 CTAs x 4 epilogue warps {res[False][0]:.3f} ms, 2 CTAs x 8 epilogue warps {res[True][0]:.3f} ms, max |diff| {d:.2e}")
+    layers.USE_EPI16 = False
 
     up, _ = util.uniplanner(dev) if hasattr(util, "uniplanner") else (None, None)
     gru = up.plan_gru if up is not None else torch.nn.GRU(4, 512, batch_first=True).to(dev)

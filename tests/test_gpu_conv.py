@@ -322,3 +322,28 @@ def test_conv_halo_umma_vs_umma(cuda, cfg, monkeypatch):
     torch.cuda.synchronize()
     err = (out - ref).abs().max().item() / ref.abs().max().item()
     assert err < 4e-3, err          # both paths round the output to bf16; only the accumulation order differs
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.environ.get("LAVB_EXPERIMENTAL"), reason="experimental 2-CTA x 8-epilogue-warp variant: set LAVB_EXPERIMENTAL=1")
+@pytest.mark.parametrize("cfg", [(3, 72, 64, 64, 64, 3, 1, 1, False, True), (2, 36, 32, 128, 128, 1, 3, 8, False, True),
+                                 (2, 80, 80, 128, 128, 3, 3, 1, True, False), (16, 160, 160, 64, 64, 3, 3, 1, True, False)])
+def test_conv_umma16_vs_umma(cuda, cfg, monkeypatch):
+    """lavb_conv_umma16 (same source, 8 epilogue warps + 2 CTAs/SM) == lavb_conv_umma bit for bit (same MMA order, same epilogue math)."""
+    from lav_b200 import layers
+    n, h, w, cin, cout, kh, kw, dil, pre, use_res = cfg
+    g = torch.Generator().manual_seed(12)
+    x = (torch.randn(n, h, w, cin, generator=g)).to(torch.bfloat16).cuda()
+    wt = torch.randn(cout, cin, kh, kw, generator=g) * (1.0 / (kh * kw * cin) ** 0.5)
+    bias = torch.randn(cout, generator=g) * 0.1
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    pad = (dil * (kh // 2), dil * (kw // 2))
+    conv = layers.TapConv(wt.cuda(), False, 1, pad, (dil if kh > 1 else 1, dil if kw > 1 else 1), bias=None if pre else bias.cuda(),
+                          pre_relu=pre, scale=scale.cuda(), shift=shift.cuda(), post_relu=not pre)
+    res = x if use_res else None
+    monkeypatch.setattr(layers, "USE_EPI16", False)
+    ref = conv(x, res=res)
+    monkeypatch.setattr(layers, "USE_EPI16", True)
+    out = conv(x, res=res)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
