@@ -1,14 +1,19 @@
-"""Round-2 entry point for the two prepared kernels: numerics + timing, flag off vs on, on one GPU.
-  python scripts/experimental_check.py [B]
-ERFNet with erfnet.FUSE_PAIRS (fused 3x1->1x3 tcgen05 pairs), ERFNet / BEV backbone with layers.USE_HALO (halo-patch conv)
-and the planner roll-out with heads.GRU_KERNEL (cluster-persistent GRU).  Prints max-norm difference of the outputs and CUDA-graph replay times."""
+"""Round-2 entry point for the prepared (off-by-default) kernels: flag off vs flag on, numerics + CUDA-graph replay time.
+  python scripts/experimental_check.py [B] [pairs] [halo] [epi16] [gru]        (no selector = all four)
+    pairs : erfnet.FUSE_PAIRS   fused (3x1 -> 1x3) tcgen05 pairs            -> ERFNet
+    halo  : layers.USE_HALO     halo-patch tcgen05 convolution               -> ERFNet, BEV backbone
+    epi16 : layers.USE_EPI16    narrow layers, 2 CTAs/SM x 8 epilogue warps  -> ERFNet, BEV backbone
+    gru   : heads.GRU_KERNEL    cluster-persistent plan GRU                  -> planner roll-out
+Run each selector in its own process under `timeout` (scripts/round2_first_call.sh): a hang then costs one item."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from lav_b200 import erfnet, heads, synth
+from lav_b200 import erfnet, heads, layers, synth
 from tests import util
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+args = sys.argv[1:]
+B = int(args[0]) if args and args[0].isdigit() else 32
+WHICH = {a for a in args if not a.isdigit()} or {"pairs", "halo", "epi16", "gru"}
 dev = torch.device("cuda:0")
 
 
@@ -29,55 +34,39 @@ def graph_time(fn, iters=10):
     return a.elapsed_time(b) / iters, out
 
 
+def compare(label, module, flag, fn):
+    res = {}
+    for on in (False, True):
+        setattr(module, flag, on)
+        ms, out = graph_time(fn)
+        res[on] = (ms, out.float().clone())
+    setattr(module, flag, False)
+    d = (res[True][1] - res[False][1]).abs().max().item() / max(res[False][1].abs().max().item(), 1e-30)
+    print(f"{label}: {flag} off {res[False][0]:.3f} ms, on {res[True][0]:.3f} ms ({res[False][0] / res[True][0]:.2f}x), max-norm diff {d:.2e}", flush=True)
+
+
 with torch.no_grad():
-    seg, _ = util.seg_model(dev)
-    seg.set_precision("bf16")
-    rgb = synth.rgb_frames().to(dev).repeat(B, 1, 1, 1)
-    res = {}
-    for flag in (False, True):
-        erfnet.FUSE_PAIRS = flag
-        ms, out = graph_time(lambda: seg.forward_nhwc(rgb))
-        res[flag] = (ms, out.float().clone())
-    d = (res[True][1] - res[False][1]).abs().max().item() / res[False][1].abs().max().item()
-    print(f"ERFNet {3 * B} images: unfused {res[False][0]:.3f} ms, fused pairs {res[True][0]:.3f} ms, max-norm diff {d:.2e}")
-    erfnet.FUSE_PAIRS = False
-
-    # halo-patch conv kernel: ERFNet (its 3x1 layers) and the BEV backbone (3x3 layers)
-    from lav_b200 import layers
-    lid, _ = util.lidar_model(dev)
-    lid.set_precision("bf16")
-    canvas = (torch.randn(B, 320, 320, 128, device=dev) * 0.3).to(torch.bfloat16)      # [hi | lo] split canvas
-    for name, fn in (("ERFNet", lambda: seg.forward_nhwc(rgb)), ("backbone", lambda: lid.backbone.forward_nhwc(canvas))):
-        res = {}
-        for flag in (False, True):
-            layers.USE_HALO = flag
-            ms, out = graph_time(fn)
-            res[flag] = (ms, out.float().clone())
-        d = (res[True][1] - res[False][1]).abs().max().item() / res[False][1].abs().max().item()
-        print(f"{name}: per-tap tiles {res[False][0]:.3f} ms, halo patches {res[True][0]:.3f} ms, max-norm diff {d:.2e}")
-    layers.USE_HALO = False
-    for name, fn in (("ERFNet", lambda: seg.forward_nhwc(rgb)), ("backbone", lambda: lid.backbone.forward_nhwc(canvas))):
-        res = {}
-        for flag in (False, True):
-            layers.USE_EPI16 = flag
-            ms, out = graph_time(fn)
-            res[flag] = (ms, out.float().clone())
-        d = (res[True][1] - res[False][1]).abs().max().item()
-        print(f"{name}: 2 CTAs x 4 epilogue warps {res[False][0]:.3f} ms, 2 CTAs x 8 epilogue warps {res[True][0]:.3f} ms, max |diff| {d:.2e}")
-    layers.USE_EPI16 = False
-
-    up, _ = util.uniplanner(dev) if hasattr(util, "uniplanner") else (None, None)
-    gru = up.plan_gru if up is not None else torch.nn.GRU(4, 512, batch_first=True).to(dev)
-    mlp = up.plan_mlp if up is not None else torch.nn.Linear(512, 2).to(dev)
-    embd = torch.randn(B, 512, device=dev) * 0.5
-    nxp = torch.tensor([[0.0, -20.0]] * B, device=dev)
-    cast = torch.randn(B, 6, 20, 2, device=dev) * 0.1
-    res = {}
-    for flag in (False, True):
-        heads.GRU_KERNEL = flag
-        ms, out = graph_time(lambda: heads._plan_rollout(gru, mlp, 6, 20, 5, embd, nxp, cast, 4, 192))
-        res[flag] = (ms, out.float().clone())
-    d = (res[True][1] - res[False][1]).abs().max().item() / res[False][1].abs().max().item()
-    print(f"plan roll-out {6 * B} sequences x 20 steps x 5 iterations: cuDNN {res[False][0]:.3f} ms, cluster kernel {res[True][0]:.3f} ms, "
-          f"max-norm diff {d:.2e}")
-    heads.GRU_KERNEL = False
+    if WHICH & {"pairs", "halo", "epi16"}:
+        seg, _ = util.seg_model(dev)
+        seg.set_precision("bf16")
+        rgb = synth.rgb_frames().to(dev).repeat(B, 1, 1, 1)
+        lid, _ = util.lidar_model(dev)
+        lid.set_precision("bf16")
+        canvas = (torch.randn(B, 320, 320, 128, device=dev) * 0.3).to(torch.bfloat16)       # [hi | lo] split canvas
+        run_seg, run_bb = (lambda: seg.forward_nhwc(rgb)), (lambda: lid.backbone.forward_nhwc(canvas))
+        if "epi16" in WHICH:
+            compare(f"ERFNet {3 * B} images", layers, "USE_EPI16", run_seg)
+            compare(f"BEV backbone {B} frames", layers, "USE_EPI16", run_bb)
+        if "halo" in WHICH:
+            compare(f"ERFNet {3 * B} images", layers, "USE_HALO", run_seg)
+            compare(f"BEV backbone {B} frames", layers, "USE_HALO", run_bb)
+        if "pairs" in WHICH:
+            compare(f"ERFNet {3 * B} images", erfnet, "FUSE_PAIRS", run_seg)
+    if "gru" in WHICH:
+        gru = torch.nn.GRU(4, 512, batch_first=True).to(dev)
+        mlp = torch.nn.Linear(512, 2).to(dev)
+        embd = torch.randn(B, 512, device=dev) * 0.5
+        nxp = torch.tensor([[0.0, -20.0]] * B, device=dev)
+        cast = torch.randn(B, 6, 20, 2, device=dev) * 0.1
+        compare(f"plan roll-out {6 * B} sequences x 20 steps x 5 iterations", heads, "GRU_KERNEL",
+                lambda: heads._plan_rollout(gru, mlp, 6, 20, 5, embd, nxp, cast, 4, 192))
