@@ -4,6 +4,8 @@
     halo  : layers.USE_HALO     halo-patch tcgen05 convolution               -> ERFNet, BEV backbone
     epi16 : layers.USE_EPI16    narrow layers, 2 CTAs/SM x 8 epilogue warps  -> ERFNet, BEV backbone
     gru   : heads.GRU_KERNEL    cluster-persistent plan GRU                  -> planner roll-out
+    trunk : ResNet-18 trunk of the brake model on the tcgen05 kernels (resnet_umma.py), with and without USE_HALO / USE_EPI16
+            (in round 1 that trunk was 5-20 % slower than BN-folded cuDNN; the narrow-layer switches may flip it)
 Run each selector in its own process under `timeout` (scripts/round2_first_call.sh): a hang then costs one item."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -62,6 +64,25 @@ with torch.no_grad():
             compare(f"BEV backbone {B} frames", layers, "USE_HALO", run_bb)
         if "pairs" in WHICH:
             compare(f"ERFNet {3 * B} images", erfnet, "FUSE_PAIRS", run_seg)
+    if "trunk" in WHICH:
+        import bench
+        (_, _, _, bra), _ = bench.build_models()
+        bra = bra.to(dev).eval()
+        bra.conv_backbone.to(torch.bfloat16).to(memory_format=torch.channels_last)
+        bra.attn1.to(torch.bfloat16); bra.attn2.to(torch.bfloat16)
+        g = torch.Generator().manual_seed(1)
+        rgbs = torch.randint(0, 256, (B, 3, 288, 256, 3), generator=g, dtype=torch.uint8).to(dev)
+        tel = torch.randint(0, 256, (B, 192, 480, 3), generator=g, dtype=torch.uint8).to(dev)
+        base = None
+        for umma_trunk, halo, epi16 in ((False, False, False), (True, False, False), (True, True, False), (True, False, True)):
+            bra.conv_backbone.use_umma_trunk = umma_trunk
+            layers.USE_HALO, layers.USE_EPI16 = halo, epi16
+            ms, out = graph_time(lambda: bra.forward_u8(rgbs, tel))
+            base = out.float().clone() if base is None else base
+            d = (out.float() - base).abs().max().item()
+            print(f"brake model {B} frames: tcgen05 trunk {umma_trunk}, halo {halo}, epi16 {epi16}: {ms:.3f} ms, max |diff| vs cuDNN trunk {d:.2e}", flush=True)
+        bra.conv_backbone.use_umma_trunk = False
+        layers.USE_HALO = layers.USE_EPI16 = False
     if "gru" in WHICH:
         gru = torch.nn.GRU(4, 512, batch_first=True).to(dev)
         mlp = torch.nn.Linear(512, 2).to(dev)
