@@ -1,6 +1,6 @@
 """bench.py — agent frames/s of the LAV frame path (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision bf16|fp32] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision f16|fp32] [--impl ours|reference]
 
 A "step" = one tick of B independent agents per GPU: 3xRGB 288x256 -> ERFNet -> point painting of a
 40k-point sweep -> stack 3 sweeps (120k pts) -> pillars -> BEV backbone + heads -> detection decode ->
@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=64, help="agent frames per step per GPU")
-    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--precision", default="f16")
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--pipelines", type=int, default=2, help="agent groups per GPU that overlap host decode with GPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")

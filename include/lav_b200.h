@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LAVB_ABI_VERSION 1
+#define LAVB_ABI_VERSION 2
 
 int lavb_abi_version(void);
 const char* lavb_last_error(void);
@@ -31,7 +31,11 @@ const char* lavb_last_error(void);
 int lavb_device_cc(void);
 
 /* ---------------------------------------------------------------- element types */
-enum { LAVB_F32 = 0, LAVB_BF16 = 1 };
+enum { LAVB_F32 = 0, LAVB_BF16 = 1, LAVB_F16 = 2 };
+/* The 16-bit storage type of the tensor-core path ("h16" below) is fixed when the library is built: IEEE half (LAVB_F16) by
+ * default — fp32 accumulation everywhere, every fp32 -> half conversion saturates at +-65504 — or bfloat16 with
+ * -DLAVB_H16_BF16.  Entry points that take a dtype accept LAVB_F32 and this value only. */
+int lavb_h16_dtype(void);
 
 /* ---------------------------------------------------------------- point painting
  * replaces: InferModel.point_painting / forward_paint (team_code_v2/model_inference.py:44-50,75-93),
@@ -57,12 +61,33 @@ int lavb_paint_batched(const float* d_pts, int frames, int n, int pt_stride, lon
                        long long s_c, long long s_y, long long s_x, const float* h_cams, int mode, float* d_out,
                        int out_stride, long long out_frame_stride, int out_col0, int copy_cols, void* stream);
 
+/* painting straight from the ERFNet decoder's last 16-channel feature map: the segmentation head's final layer
+ * replaces: Decoder.output_conv = ConvTranspose2d(16, c_cls, 2, stride 2) (lav/models/erfnet.py:122-124,132) + torch.softmax
+ *           (lav_agent_fast.py:264) + the background suppression and gather of forward_paint (model_inference.py:44-50,75-93),
+ * evaluated for the hit pixel only, so the (h x w x c_cls) logit maps are never materialised.
+ * d_feat: NHWC (frames*ncam, h/2, w/2, 16) fp32 or h16 = input of output_conv; d_deconv: 2*2*16*8 + 8 floats =
+ * w[v%2][u%2][c_in][k] (k >= c_cls zero) | bias[8].  Output row as lavb_paint mode 2: copy_cols point columns, then c_cls-1
+ * painted channels at out_col0. */
+int lavb_paint_deconv_batched(const float* d_pts, int frames, int n, int pt_stride, long long pts_frame_stride,
+                              const void* d_feat, int feat_dtype, int ncam, int c_cls, int h, int w,
+                              const float* d_deconv, const float* h_cams, float* d_out, int out_stride,
+                              long long out_frame_stride, int out_col0, int copy_cols, void* stream);
+
 /* ---------------------------------------------------------------- sweep stacking
  * replaces: LAVAgent.get_stacked_lidar + move_lidar_points (team_code_v2/lav_agent_fast.py:363-383,547-565)
  * and the ego-roof filter LAVAgent.preprocess (lav_agent.py:448-457, roof_filter!=0 marks dropped rows x=NaN).
  * dst row = [xyz @ R + (dx,dy,0) | src cols 3..src_cols | one_hot(time_idx, n_time)];  h_R is 3x3 row-major. */
 int lavb_stack_sweep(const float* d_src, int n, int src_cols, const float* h_R, float dx, float dy,
                      int time_idx, int n_time, int roof_filter, float* d_dst, void* stream);
+
+/* Ego-roof filter as an order-preserving drop (np.delete semantics).
+ * replaces: LAVAgent.preprocess (team_code_v2/lav_agent.py:448-457; applied to the raw sweep before painting at :236 and
+ *           lav_agent_fast.py:247): rows with x in (-2.4,0), y in (-0.8,0.8), z in (-1.5,-1) are removed, the others keep their order.
+ * `frames` independent sweeps of n rows x cols floats (frame f at d_src + f*src_frame_stride); the kept rows of frame f are written
+ * to d_dst + f*dst_frame_stride, their number to d_counts[f] (may be NULL); with pad_nan the remaining rows [count, n) are filled
+ * with NaN (the fixed-shape pipeline's padding — every kernel drops NaN rows).  d_dst must not alias d_src. */
+int lavb_roof_filter(const float* d_src, int frames, int n, int cols, long long src_frame_stride, float* d_dst,
+                     long long dst_frame_stride, int* d_counts, int pad_nan, void* stream);
 
 /* table-driven variant: d_jobs is a DEVICE array of n_jobs 72-byte records
  *   { const float* src; float* dst; int n; int time_idx; float R[9]; float dx, dy; int pad; }
@@ -88,9 +113,9 @@ int lavb_pillar_forward(const float* d_pts, int pt_stride, int d,
                         void* d_canvas, int canvas_dtype, void* d_workspace, void* stream);
 
 /* Sorted, atomic-free variant for the tensor-core pipeline: counting sort of the points by canvas cell, layer 1 in
- * fp32, layer 2 on the tensor cores (bf16 operands, fp32 accumulate), one canvas row written per pillar and the rows
- * of empty cells zero-filled by the scan pass.  out_mode 0: fp32 canvas [B][ny][nx][h2]; 1: bf16 canvas
- * [B][ny][nx][hi(h2) | lo(h2)] (the error-free split lavb_split_bf16 produces).  Same semantics otherwise. */
+ * fp32, layer 2 on the tensor cores (h16 operands, fp32 accumulate), one canvas row written per pillar and the rows
+ * of empty cells zero-filled by the scan pass.  out_mode 0: fp32 canvas [B][ny][nx][h2]; 1: h16 canvas
+ * [B][ny][nx][hi(h2) | lo(h2)] (the error-free split lavb_split_h16 produces).  Same semantics otherwise. */
 size_t lavb_pillar_sorted_workspace_bytes(int batch, int nx, int ny, long long total_points);
 int lavb_pillar_forward_sorted(const float* d_pts, int pt_stride, int d,
                                const long long* h_cloud_start, const int* h_cloud_count, int batch,
@@ -98,6 +123,18 @@ int lavb_pillar_forward_sorted(const float* d_pts, int pt_stride, int d,
                                const float* d_w1, const float* d_s1, const float* d_t1, int h1,
                                const float* d_w2, const float* d_s2, const float* d_t2, int h2,
                                void* d_canvas, int out_mode, void* d_workspace, void* stream);
+
+/* Tile-binned variant (the 16-bit pipeline's encoder): the points are binned by canvas tile (8 x 16 cells) into 48-byte records and
+ * one CTA produces each tile start to finish in shared memory — per-pillar centroids, decorate, layer 1 (hi/lo-split MMAs ~ fp32),
+ * layer 2 (h16 MMAs), max-pool by shared-memory atomics — and writes it, zeros included, as full 256-byte cell rows.  Same
+ * arguments, semantics and out_mode as lavb_pillar_forward_sorted; no per-cell global arrays, no canvas zero-fill pass. */
+size_t lavb_pillar_tiled_workspace_bytes(int batch, int nx, int ny, long long total_points);
+int lavb_pillar_forward_tiled(const float* d_pts, int pt_stride, int d,
+                              const long long* h_cloud_start, const int* h_cloud_count, int batch,
+                              float min_x, float max_x, float min_y, float max_y, float ppm, int nx, int ny,
+                              const float* d_w1, const float* d_s1, const float* d_t1, int h1,
+                              const float* d_w2, const float* d_s2, const float* d_t2, int h2,
+                              void* d_canvas, int out_mode, void* d_workspace, void* stream);
 
 /* training-mode pieces (BatchNorm1d batch statistics over all in-window points, arg-routed backward).
  * stage 0: voxelise + decorate -> d_feat [M][d+5] (M = number of in-window points, returned in *h_m),
@@ -161,12 +198,12 @@ int lavb_rgb_normalize(const void* d_rgb, int src_is_u8_nhwc, int n, int h, int 
 /* ---------------------------------------------------------------- brake-model stem on raw camera bytes
  * replaces: Normalize + ResNet conv1(7x7,s2,p3,3->64) + bn1 + ReLU of RGBBrakePredictionModel (team_code_v2/models/rgb.py:66-70,
  * lav/models/resnet.py:178,235-238).  d_img: uint8 (batch, ncam, h, cam_w, 3) — the logical image is the ncam cameras side by
- * side (h x ncam*cam_w), ncam <= 4, cam_w % 4 == 0; d_w: BatchNorm-folded weights bf16 [64][160] with
+ * side (h x ncam*cam_w), ncam <= 4, cam_w % 4 == 0; d_w: BatchNorm-folded weights h16 [64][160] with
  * k = ky*22 + kx*3 + c (slot 21 of every window row and k >= 154 are zero); d_bias [64]; h_mean/h_std: the 3 ImageNet
- * constants; d_out: bf16 NHWC (batch, h/2, ncam*cam_w/2, 64). */
+ * constants; d_out: h16 NHWC (batch, h/2, ncam*cam_w/2, 64). */
 int lavb_stem7x7s2_u8(const void* d_img, int batch, int ncam, int h, int cam_w, const void* d_w, const float* d_bias,
                       const float* h_mean, const float* h_std, void* d_out, void* stream);
-/* replaces: ResNet.maxpool = MaxPool2d(3, 2, 1) (lav/models/resnet.py:181,238) on bf16 NHWC (n, h, w, c), c % 8 == 0
+/* replaces: ResNet.maxpool = MaxPool2d(3, 2, 1) (lav/models/resnet.py:181,238) on h16 NHWC (n, h, w, c), c % 8 == 0
  * -> (n, (h-1)/2+1, (w-1)/2+1, c). */
 int lavb_maxpool3x3s2_nhwc(const void* d_in, int n, int h, int w, int c, void* d_out, void* stream);
 
@@ -189,37 +226,25 @@ int lavb_crop_bilinear(const void* d_feat, int dtype, int b, int h, int w, int c
                        const float* d_theta, int k, int crop, void* d_out, void* stream);
 
 /* dtype / layout helpers */
-/* fp32 [rows][c] -> bf16 [rows][hi(c) | lo(c)] with hi = bf16(x), lo = bf16(x - hi) (error-free split of the canvas so the
+/* fp32 [rows][c] -> h16 [rows][hi(c) | lo(c)] with hi = h16(x), lo = h16(x - hi) (error-free split of the canvas so the
  * first tensor-core conv sees ~fp32 input precision; its weights are duplicated along cin by the host). */
-int lavb_split_bf16(const float* d_src, void* d_dst, long long rows, int c, void* stream);
+int lavb_split_h16(const float* d_src, void* d_dst, long long rows, int c, void* stream);
 int lavb_convert(const void* d_src, int src_dtype, void* d_dst, int dst_dtype, long long count, void* stream);
 
 /* ---------------------------------------------------------------- tcgen05 implicit-GEMM tap-list convolution
- * replaces (bf16 path): the Conv2d -> ReLU -> BatchNorm2d layers of ConvBackbone (lidar.py:57-131), the fused 4-head
+ * replaces (h16 path): the Conv2d -> ReLU -> BatchNorm2d layers of ConvBackbone (lidar.py:57-131), the fused 4-head
  *           384->256 conv (lidar.py:152-154) and the 64/128-channel factorised convs of ERFNet (erfnet.py:31-61).
- * Same descriptor and epilogue semantics as lavb_conv_taps, with these differences: input is bf16 NHWC, cin % 64 == 0,
- * cout % 32 == 0 and <= 256, channel offsets/strides multiples of 8; d->w points to BF16 weights laid out
+ * Same descriptor and epilogue semantics as lavb_conv_taps, with these differences: input is h16 NHWC, cin % 64 == 0,
+ * cout % 32 == 0 and <= 256, channel offsets/strides multiples of 8; d->w points to h16 weights laid out
  * [ntaps][cout][cin] (K contiguous).  Tiles are 8 x 16 output-grid pixels; operands are fetched by TMA
  * (cuTensorMapEncodeTiled through cudaGetDriverEntryPoint), accumulators live in TMEM. */
 int lavb_conv_umma(const lavb_conv_desc* h_desc, void* stream);
 
-/* ---------------------------------------------------------------- EXPERIMENTAL: lavb_conv_umma with 2 CTAs/SM x 8 epilogue warps
- * Same descriptor and semantics as lavb_conv_umma; covers layers with cout <= 128 and no depth-to-space epilogue, returns 4
- * otherwise (callers then use lavb_conv_umma).  Not on the default path (round-2 work item). */
-int lavb_conv_umma16(const lavb_conv_desc* h_desc, void* stream);
-
-/* ---------------------------------------------------------------- EXPERIMENTAL: halo-patch variant of lavb_conv_umma
- * Same descriptor and semantics as lavb_conv_umma for plain stride-1 same-size convolutions with bf16 output (no sigmoid, no
- * depth-to-space): each tile's input is fetched once as a halo patch and the taps read it through shifted shared-memory
- * descriptors.  Returns 4 when the layer is outside its coverage or the patch would not pay (callers then use lavb_conv_umma).
- * Not on the default path (round-2 work item). */
-int lavb_conv_halo_umma(const lavb_conv_desc* h_desc, void* stream);
-
-/* ---------------------------------------------------------------- EXPERIMENTAL: fused (3x1 -> 1x3) convolution pair
+/* ---------------------------------------------------------------- fused (3x1 -> 1x3) convolution pair
  * replaces: conv3x1_k -> ReLU -> conv1x3_k -> bn_k [-> + input] -> ReLU of non_bottleneck_1d (lav/models/erfnet.py:37-63) in
- * one tcgen05 kernel; the intermediate activation stays in shared memory.  Not on the default path (round-2 work item).
+ * one tcgen05 kernel; the intermediate activation stays in shared memory.
  *   mid = relu(conv3x1_dil(in) + bias1);  out = [relu]((conv1x3_dil(mid) + bias2) * scale2 + shift2 [+ res])
- * in / out / res: bf16 NHWC (n, h, w, c) contiguous, c in {64, 128}, w in {32, 64, 128}; w1 / w2: bf16 [3 taps][c out][c in];
+ * in / out / res: h16 NHWC (n, h, w, c) contiguous, c in {64, 128}, w in {32, 64, 128}; w1 / w2: h16 [3 taps][c out][c in];
  * bias2 / scale2 / shift2 / res may be NULL (scale2 and shift2 together). */
 typedef struct lavb_conv_pair_desc {
   const void* in; void* out; const void* res;
@@ -229,12 +254,20 @@ typedef struct lavb_conv_pair_desc {
 } lavb_conv_pair_desc;
 int lavb_conv_pair_umma(const lavb_conv_pair_desc* h_desc, void* stream);
 
-/* ---------------------------------------------------------------- EXPERIMENTAL: cluster-persistent GRU roll-out
+/* ---------------------------------------------------------------- fused 16-channel non_bottleneck_1d block
+ * replaces: non_bottleneck_1d(16, dropprob, dilated=1) of the ERFNet decoder (lav/models/erfnet.py:37-63, Decoder layers 4 and 5) —
+ * conv3x1 -> ReLU -> conv1x3 -> bn1 -> ReLU -> conv3x1 -> ReLU -> conv1x3 -> bn2 -> (+ input) -> ReLU — in one kernel, all four
+ * intermediates in shared memory.  d_in / d_out: h16 NHWC (n, h, w, 16), distinct buffers, w % 16 == 0; d_w4: fp32
+ * [4 convs][3 taps][16 cin][16 cout]; d_st: fp32 [4 convs][16 cout][2] = (scale, shift) with epi(a) = relu(a * scale + shift)
+ * (conv bias folded into shift; scale = 1 for the two convs that have no BatchNorm). */
+int lavb_erf_nb16(const void* d_in, void* d_out, int n, int h, int w, const float* d_w4, const float* d_st, void* stream);
+
+/* ---------------------------------------------------------------- cluster-persistent GRU roll-out
  * replaces: one call of plan_gru = nn.GRU(4, 512, batch_first=True) (team_code_v2/models/uniplanner.py:45,247-259;
- * lav/models/bev_planner_v2.py) over `steps` time steps for `nseq` sequences.  Not on the default path (round-2 work item).
- * d_u (nseq, steps, 4) fp32; d_h0 (nseq, 512) fp32; d_whh_bf16 = weight_hh_l0 (1536, 512) as bf16; d_wih = weight_ih_l0
+ * lav/models/bev_planner_v2.py) over `steps` time steps for `nseq` sequences.
+ * d_u (nseq, steps, 4) fp32; d_h0 (nseq, 512) fp32; d_whh_h16 = weight_hh_l0 (1536, 512) as h16; d_wih = weight_ih_l0
  * (1536, 4), d_bih / d_bhh (1536,) fp32; d_out (nseq, steps, 512) fp32 = the GRU's output sequence. */
-int lavb_gru_h512(const float* d_u, const float* d_h0, const void* d_whh_bf16, const float* d_wih, const float* d_bih,
+int lavb_gru_h512(const float* d_u, const float* d_h0, const void* d_whh_h16, const float* d_wih, const float* d_bih,
                   const float* d_bhh, float* d_out, int nseq, int steps, void* stream);
 
 #ifdef __cplusplus

@@ -6,6 +6,8 @@ this class the tensors it already holds and gets back what it feeds to the PID /
 State per agent (``SweepHistory``): the FIFO of painted sweeps + ego poses that get_stacked_lidar reads
 (lav_agent_fast.py:363-383), resident on the device.
 """
+import contextlib
+import copy
 import math
 from collections import deque
 
@@ -15,6 +17,7 @@ import torch
 from . import ops
 from .model_inference import InferModel
 
+FUSE_SEG_HEAD = True  # ERFNet's last layer (ConvTranspose2d 16->5, k2 s2) + softmax evaluated inside the painting gather
 FORK_BRAKE = True     # run the brake predictor as a parallel branch of the perception graph
 STEM_U8 = True        # brake-model stem (7x7 s2 on 3 channels) in the lav_b200 kernel, straight from the camera bytes
 UMMA_TRUNKS = False   # ResNet-18 trunks (brake / planner embedder) on the tcgen05 conv kernel: correct (tested) but measured 5-20%
@@ -63,32 +66,56 @@ def stack_into(dst, sweeps, roof_filter=False):
 
 class FramePipeline:
     def __init__(self, seg_model, lidar_model, uniplanner, bra_model, camera_x=1.5, camera_z=2.4, device=torch.device("cuda"),
-                 precision="bf16"):
+                 precision="f16"):
         self.device = device
         self.seg_model = seg_model.to(device).eval()
-        self.bra_model = bra_model.to(device).eval() if bra_model is not None else None
-        self.infer_model = InferModel(lidar_model.to(device).eval(), uniplanner.to(device).eval(), camera_x, camera_z, device)
+        # the PyTorch heads are cast for the 16-bit path: the pipeline works on PRIVATE copies, so a model object shared with a
+        # trainer / checkpoint writer / fp32 parity check keeps its fp32 master weights (set_precision re-copies from these)
+        self._src_uniplanner = uniplanner.to(device).eval()
+        self._src_bra = bra_model.to(device).eval() if bra_model is not None else None
+        self._lidar_model, self._cam = lidar_model.to(device).eval(), (camera_x, camera_z)
+        self.bra_model = None
         self.set_precision(precision)
 
     def set_precision(self, precision):
+        assert precision in ("fp32", "f16"), precision
         self.precision = precision
-        if precision == "fp32":   # exact path: keep cuDNN (PyTorch heads) out of TF32 as well
-            torch.backends.cudnn.allow_tf32 = False
-            torch.backends.cuda.matmul.allow_tf32 = False
         self.seg_model.set_precision(precision)
-        self.infer_model.lidar_model.set_precision(precision)
-        dt = torch.bfloat16 if precision == "bf16" else torch.float32
-        emb = self.infer_model.uniplanner.lidar_conv_emb
-        emb.to(dt).to(memory_format=torch.channels_last)
-        emb[0].use_umma_trunk = (precision == "bf16") and UMMA_TRUNKS
-        if self.bra_model is not None:
-            self.bra_model.conv_backbone.to(dt).to(memory_format=torch.channels_last)
-            self.bra_model.attn1.to(dt); self.bra_model.attn2.to(dt)
-            self.bra_model.conv_backbone.use_umma_trunk = (precision == "bf16") and UMMA_TRUNKS
+        self._lidar_model.set_precision(precision)
+        dt = ops.h16() if precision == "f16" else torch.float32
+        up = copy.deepcopy(self._src_uniplanner)
+        up.lidar_conv_emb.to(dt).to(memory_format=torch.channels_last)
+        up.lidar_conv_emb[0].use_umma_trunk = (precision == "f16") and UMMA_TRUNKS
+        self.infer_model = InferModel(self._lidar_model, up, self._cam[0], self._cam[1], self.device)
+        if self._src_bra is not None:
+            bra = copy.deepcopy(self._src_bra)
+            bra.conv_backbone.to(dt).to(memory_format=torch.channels_last)
+            bra.attn1.to(dt); bra.attn2.to(dt)
+            bra.conv_backbone.use_umma_trunk = (precision == "f16") and UMMA_TRUNKS
+            self.bra_model = bra
         return self
+
+    @contextlib.contextmanager
+    def _math_mode(self):
+        """exact path: the cuDNN / cuBLAS heads must not drop to TF32 — scoped to the pipeline's own calls, the process-wide
+        flags are restored afterwards."""
+        if self.precision != "fp32":
+            yield
+            return
+        prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            yield
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
 
     @torch.no_grad()
     def step(self, rgbs_u8, tel_u8, lidars, histories, nxps, cmds, poses=None):
+        with self._math_mode():
+            return self._step(rgbs_u8, tel_u8, lidars, histories, nxps, cmds, poses)
+
+    def _step(self, rgbs_u8, tel_u8, lidars, histories, nxps, cmds, poses=None):
         """One tick of B agents.
         rgbs_u8 (B,3,288,256,3) uint8 RGB; tel_u8 (B,192,480,3) uint8 or None; lidars: list of (N_b,4) fp32 (roof-filtered
         current sweep, lav_agent_fast.py:233-247); histories: list of SweepHistory (updated in place); nxps (B,2); cmds (B,)
@@ -97,11 +124,24 @@ class FramePipeline:
         B = rgbs_u8.shape[0]
         im = self.infer_model
         # (1) semantic segmentation of the 3 cameras of every agent: logits NHWC (B*3,288,256,5)
-        logits = self.seg_model.forward_nhwc(rgbs_u8.reshape(B * 3, *rgbs_u8.shape[2:]))
-        logits = logits.view(B, 3, *logits.shape[1:]).permute(0, 1, 4, 2, 3)      # logical (B,3,5,H,W), channels-last storage
+        imgs = rgbs_u8.reshape(B * 3, *rgbs_u8.shape[2:])
+        if FUSE_SEG_HEAD:
+            feat, table, ncls = self.seg_model.forward_features_nhwc(imgs)
+            cams = np.stack([c.packed() for c in im.coord_converters])
+        else:
+            logits = self.seg_model.forward_nhwc(imgs)
+            logits = logits.view(B, 3, *logits.shape[1:]).permute(0, 1, 4, 2, 3)      # logical (B,3,5,H,W), channels-last storage
         # (2) paint the current sweep (softmax + background suppression fused into the gather) and push to the FIFO
         for b in range(B):
-            fused = im.forward_paint(lidars[b], logits[b], logits=True)
+            if FUSE_SEG_HEAD and table is not None:
+                cur = lidars[b].float().contiguous()[None]
+                fused = ops.paint_deconv_batched(cur, feat[3 * b:3 * b + 3], ncls, table, cams, cur.shape[2],
+                                                 torch.empty((1, cur.shape[1], cur.shape[2] + ncls - 1), device=self.device),
+                                                 tuple(rgbs_u8.shape[2:4]))[0]
+            else:
+                if FUSE_SEG_HEAD:
+                    raise RuntimeError("FUSE_SEG_HEAD needs the v2 output_conv (ConvTranspose2d 16->C, k2 s2)")
+                fused = im.forward_paint(lidars[b], logits[b], logits=True)
             loc, ori = poses[b] if poses is not None else (np.zeros(2), 0.0)
             histories[b].push(fused, loc, ori)
         # (3) stack t, t-5, t-10 into the batch buffer
@@ -126,22 +166,30 @@ class StaticFramePipeline(FramePipeline):
     """Fixed-shape variant for throughput: B agents, N points per sweep (shorter sweeps are padded with NaN rows, which
     every kernel drops), all buffers static, the whole tick captured in two CUDA graphs:
       G1: seg -> batched paint -> table-driven stack -> pillars -> backbone -> heads -> peak extraction -> brake
-      G2[K]: crops -> embed -> GRU roll-outs for K detected vehicles + B egos (one graph per distinct K, cached)
+      G2[Kb]: crops -> embed -> GRU roll-outs for the K detected vehicles + B egos.  K varies tick by tick (0 .. 15 B in real
+             driving), so K is padded to the next multiple of K_BUCKET with dummy crops whose outputs are dropped: at most
+             15 B / K_BUCKET + 1 distinct graphs exist, they share ONE memory pool, and an LRU keeps G2_CACHE of them.
     Between them the detections are decoded on the host exactly like InferModel.det_inference (one small D2H).
     The sweep FIFO of lav_agent_fast.py:267-274 is a device ring buffer; which slots feed the stack kernel is data in
     a device job table, so the captured graph never changes."""
 
     KEEP = NUM_FRAME_STACK * GAP + 1          # ticks t .. t-10
+    K_BUCKET = 8                              # detected-vehicle counts are padded to a multiple of this
+    G2_CACHE = 6                              # captured G2 graphs kept (least recently used is dropped)
 
     def __init__(self, seg_model, lidar_model, uniplanner, bra_model, batch, n_points, camera_x=1.5, camera_z=2.4,
-                 device=torch.device("cuda"), precision="bf16", use_graphs=True):
+                 device=torch.device("cuda"), precision="f16", use_graphs=True, roof_filter=False):
+        """roof_filter: the sweeps handed to step() are RAW sensor sweeps; the ego-roof drop of LAVAgent.preprocess
+        (lav_agent_fast.py:247) then runs on the device as the first kernel of G1 (order preserving, NaN-padded)."""
         super().__init__(seg_model, lidar_model, uniplanner, bra_model, camera_x, camera_z, device, precision)
         B, N, T = batch, n_points, NUM_FRAME_STACK + 1
         self.B, self.N, self.T, self.use_graphs = B, N, T, use_graphs
+        self.roof_filter = roof_filter
         dev = device
         self.rgbs = torch.zeros((B, 3, 288, 256, 3), dtype=torch.uint8, device=dev)
         self.tels = torch.zeros((B, 192, 480, 3), dtype=torch.uint8, device=dev)
         self.lidar = torch.full((B, N, 4), float("nan"), device=dev)
+        self.lidar_raw = torch.full((B, N, 4), float("nan"), device=dev) if roof_filter else self.lidar
         self.cur = torch.full((B, N, 8), float("nan"), device=dev)
         self.ring = torch.full((B, self.KEEP, N, 8), float("nan"), device=dev)
         self.ring_pose = np.zeros((B, self.KEEP, 3))                 # loc x, loc y, ori per slot
@@ -154,7 +202,8 @@ class StaticFramePipeline(FramePipeline):
         self.tick = 0
         self.stream = torch.cuda.Stream(device=dev)
         self._g1 = None
-        self._g2 = {}
+        self._g2 = {}            # Kb -> (graph, outputs, static inputs); insertion order = recency (LRU)
+        self._g2_pool = None     # one graph memory pool for every G2[Kb]
         self._launches = []      # lav_b200 kernel launches per captured graph (G1 first)
         self._cams = np.stack([c.packed() for c in self.infer_model.coord_converters])
 
@@ -216,9 +265,15 @@ class StaticFramePipeline(FramePipeline):
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 bra = self._brake()
-        logits = self.seg_model.forward_nhwc(self.rgbs.view(B * 3, 288, 256, 3))
-        logits = logits.view(B, 3, *logits.shape[1:]).permute(0, 1, 4, 2, 3)
-        ops.paint_batched(self.lidar, logits, self._cams, 2, 4, self.cur)
+        if self.roof_filter:
+            ops.roof_filter(self.lidar_raw, pad_nan=True, out=self.lidar)
+        if FUSE_SEG_HEAD:
+            feat, table, ncls = self.seg_model.forward_features_nhwc(self.rgbs.view(B * 3, 288, 256, 3))
+            ops.paint_deconv_batched(self.lidar, feat, ncls, table, self._cams, 4, self.cur, (288, 256))
+        else:
+            logits = self.seg_model.forward_nhwc(self.rgbs.view(B * 3, 288, 256, 3))
+            logits = logits.view(B, 3, *logits.shape[1:]).permute(0, 1, 4, 2, 3)
+            ops.paint_batched(self.lidar, logits, self._cams, 2, 4, self.cur)
         ops.stack_jobs(self.jobs_dev, B * self.T, N, 8, self.T)
         feats, center, box, ori, seg = im.lidar_model.forward_nhwc(self.stacked, [self.T * N] * B)
         packed = ops.det_peaks(center, box, ori)        # sigmoid + 7x7 NMS + top-15 + map reads in two small kernels
@@ -231,7 +286,7 @@ class StaticFramePipeline(FramePipeline):
 
     def _brake(self):
         B = self.B
-        if STEM_U8 and self.bra_model.conv_backbone.conv1.weight.dtype == torch.bfloat16:
+        if STEM_U8 and self.bra_model.conv_backbone.conv1.weight.dtype == ops.h16():
             return self.bra_model.forward_u8(self.rgbs, self.tels)
         wide = self.rgbs.permute(0, 2, 1, 3, 4).reshape(B, 288, 768, 3).permute(0, 3, 1, 2).float()
         tel = self.tels.permute(0, 3, 1, 2).float()
@@ -240,7 +295,7 @@ class StaticFramePipeline(FramePipeline):
     def _g2_body(self, K, locs, oris, fidx):
         return self.infer_model.uniplanner.infer_device(self._o1["features"].permute(0, 3, 1, 2), locs, oris, fidx, K, self.nxps, self.cmds)
 
-    def _capture(self, fn):
+    def _capture(self, fn, pool=None):
         for _ in range(2):
             out = fn()                                       # warm-up: cuDNN plans, workspaces, plan caches
         torch.cuda.synchronize()
@@ -250,7 +305,7 @@ class StaticFramePipeline(FramePipeline):
             self._launches.append(ops.launches() - c0)
             return None, out
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, pool=pool):
             out = fn()
         self._launches.append(ops.launches() - c0)      # lav_b200 kernels recorded in this graph
         return g, out
@@ -267,13 +322,13 @@ class StaticFramePipeline(FramePipeline):
     @torch.no_grad()
     def begin(self, rgbs_u8, tel_u8, lidars, nxps, cmds, poses=None):
         """stage inputs and launch G1 (asynchronous)."""
-        with torch.cuda.stream(self.stream):
+        with torch.cuda.stream(self.stream), self._math_mode():
             self._begin(rgbs_u8, tel_u8, lidars, nxps, cmds, poses)
 
     @torch.no_grad()
     def finish(self, fixed_dets=None):
         """decode detections on the host, launch G2, return the outputs (device tensors, valid on self.stream)."""
-        with torch.cuda.stream(self.stream):
+        with torch.cuda.stream(self.stream), self._math_mode():
             out = self._finish(fixed_dets)
         torch.cuda.current_stream().wait_stream(self.stream)
         return out
@@ -284,12 +339,12 @@ class StaticFramePipeline(FramePipeline):
         if tel_u8 is not None:
             self.tels.copy_(tel_u8, non_blocking=True)
         if torch.is_tensor(lidars) and lidars.shape[1] == N:
-            self.lidar.copy_(lidars, non_blocking=True)
+            self.lidar_raw.copy_(lidars, non_blocking=True)
         else:
             for b, l in enumerate(lidars):
-                self.lidar[b, :l.shape[0]].copy_(l, non_blocking=True)
+                self.lidar_raw[b, :l.shape[0]].copy_(l, non_blocking=True)
                 if l.shape[0] < N:
-                    self.lidar[b, l.shape[0]:].fill_(float("nan"))
+                    self.lidar_raw[b, l.shape[0]:].fill_(float("nan"))
         self.nxps.copy_(torch.as_tensor(nxps, dtype=torch.float32), non_blocking=True)
         self.cmds.copy_(torch.as_tensor(cmds, dtype=torch.long), non_blocking=True)
         self._fill_jobs(poses)
@@ -314,21 +369,29 @@ class StaticFramePipeline(FramePipeline):
             l, o = up.det_to_locs(veh[b], H, W)
             locs += l; oris += o; fidx += [b] * len(l); counts.append(len(l))
         K = len(locs)
-        if K not in self._g2:
-            st = dict(locs=torch.zeros((K + B, 2), device=self.device), oris=torch.zeros((K + B,), device=self.device),
-                      fidx=torch.zeros((K + B,), dtype=torch.int32, device=self.device))
-            st["fidx"][K:] = torch.arange(B, dtype=torch.int32, device=self.device)
-            g, out = self._capture(lambda: self._g2_body(K, st["locs"], st["oris"], st["fidx"]))
-            self._g2[K] = (g, out, st)
-        g, out, st = self._g2[K]
+        Kb = -(-K // self.K_BUCKET) * self.K_BUCKET          # rows K..Kb are dummy crops (frame 0, origin), outputs dropped
+        if Kb in self._g2:
+            self._g2[Kb] = self._g2.pop(Kb)                  # mark most recently used
+        else:
+            if len(self._g2) >= self.G2_CACHE:
+                self._g2.pop(next(iter(self._g2)))           # evict the least recently used graph (its blocks return to the pool)
+            if self._g2_pool is None and self.use_graphs:
+                self._g2_pool = torch.cuda.graph_pool_handle()
+            st = dict(locs=torch.zeros((Kb + B, 2), device=self.device), oris=torch.zeros((Kb + B,), device=self.device),
+                      fidx=torch.zeros((Kb + B,), dtype=torch.int32, device=self.device))
+            st["fidx"][Kb:] = torch.arange(B, dtype=torch.int32, device=self.device)
+            g, out = self._capture(lambda: self._g2_body(Kb, st["locs"], st["oris"], st["fidx"]), pool=self._g2_pool)
+            self._g2[Kb] = (g, out, st)
+        g, out, st = self._g2[Kb]
         if K > 0:
             pk = torch.tensor([l + [o, float(f)] for l, o, f in zip(locs, oris, fidx)], dtype=torch.float32).to(self.device, non_blocking=True)
             st["locs"][:K].copy_(pk[:, :2]); st["oris"][:K].copy_(pk[:, 2]); st["fidx"][:K].copy_(pk[:, 3])
         if g is not None:
             g.replay()
         else:
-            out = self._g2_body(K, st["locs"], st["oris"], st["fidx"])
+            out = self._g2_body(Kb, st["locs"], st["oris"], st["fidx"])
         ee, epl, ecl, ocl, occ = out
+        ocl, occ = ocl[:K], occ[:K]
         return dict(ego_embd=ee, ego_plan_locs=epl, ego_cast_locs=ecl, other_cast_locs=torch.split(ocl, counts),
                     other_cast_cmds=torch.split(occ, counts), pred_bev=o1["pred_bev"], det=dets, features=o1["features"],
                     pred_bra=o1["pred_bra"])

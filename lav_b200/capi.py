@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "liblavb200.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 
 
 class LavbError(RuntimeError):
@@ -45,13 +45,19 @@ _SIGS = {
     "lavb_abi_version": (C.c_int, []),
     "lavb_last_error": (C.c_char_p, []),
     "lavb_device_cc": (C.c_int, []),
+    "lavb_h16_dtype": (C.c_int, []),
     "lavb_paint": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                              C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int,
                              C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "lavb_paint_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "lavb_paint_deconv_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int,
+                                            C.c_void_p]),
     "lavb_stack_jobs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "lavb_roof_filter": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int,
+                                   C.c_void_p]),
     "lavb_stack_sweep": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p]),
     "lavb_pillar_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
@@ -64,6 +70,11 @@ _SIGS = {
                                              C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                              C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "lavb_pillar_tiled_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_longlong]),
+    "lavb_pillar_forward_tiled": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                            C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                            C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "lavb_pillar_decorate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -74,12 +85,13 @@ _SIGS = {
     "lavb_pool2_affine_relu": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "lavb_rgb_normalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
-    "lavb_split_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "lavb_split_h16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "lavb_convert": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
     "lavb_stem7x7s2_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "lavb_gru_h512": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                 C.c_void_p]),
+    "lavb_erf_nb16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lavb_conv_pair_umma": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lavb_maxpool3x3s2_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "lavb_det_peaks_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
@@ -90,8 +102,6 @@ _SIGS = {
     "lavb_deconv3x3s2_small": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lavb_conv_umma": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
-    "lavb_conv_halo_umma": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
-    "lavb_conv_umma16": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
 }
 
 _lib = None
@@ -114,10 +124,15 @@ def lib():
             fn = getattr(handle, name)          # AttributeError here == header/library drift
             fn.restype = res
             fn.argtypes = args
-        if handle.lavb_abi_version() != 1:
+        if handle.lavb_abi_version() != 2:
             raise LavbError("liblavb200.so ABI version mismatch")
         _lib = handle
     return _lib
+
+
+def h16_code():
+    """element-type code of the 16-bit storage type the library was built with (LAVB_F16 unless -DLAVB_H16_BF16)."""
+    return lib().lavb_h16_dtype()
 
 
 def check(code, what):

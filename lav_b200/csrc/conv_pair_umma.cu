@@ -29,7 +29,7 @@ constexpr int kEpiWarps = 8;
 
 struct PairArgs {
   int n, h, w, c, kchunks, dil, tile_w, tile_h, tiles_per_img, num_tiles, stages, tmem_cols, post_relu;
-  __nv_bfloat16* out; const __nv_bfloat16* res;
+  h16* out; const h16* res;
   const float* bias1; const float* bias2; const float* scale2; const float* shift2;
 };
 
@@ -75,7 +75,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   return (uint64_t)lo | ((uint64_t)hi << 32);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_h16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -95,7 +95,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  const h162 v = floats2h162(a, b);
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_pair_umma_kernel(
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, K-major both, N = c, M = 128 (bit layout in conv_umma.cu)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.c >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (kH16Fmt << 7) | (kH16Fmt << 10) | ((uint32_t)(p.c >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
       int slot = 0; uint32_t phase = 0;
       uint32_t te_phase[2] = {0, 0};                 // parity of tempty1[buf] expected next
       auto stage1 = [&](int buf) {
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_pair_umma_kernel(
           const uint64_t a_desc = make_sw128_desc(sa), b_desc = make_sw128_desc(sa + kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            umma_h16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
           umma_commit(empty_bar + 8 * slot);
           if (++slot == p.stages) { slot = 0; phase ^= 1; }
         }
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_pair_umma_kernel(
           const uint64_t a_desc = make_sw128_desc(mid + kb * kABytes), b_desc = make_sw128_desc(sa + kABytes);   // kb = t*kchunks + kc
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            umma_h16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
           umma_commit(empty_bar + 8 * slot);
           if (++slot == p.stages) { slot = 0; phase ^= 1; }
         }
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_pair_umma_kernel(
               const uint32_t wv[4] = {rr[j].x, rr[j].y, rr[j].z, rr[j].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[e]));
+                const float2 t2 = h1622float2(*reinterpret_cast<const h162*>(&wv[e]));
                 f[j * 8 + e * 2] += t2.x; f[j * 8 + e * 2 + 1] += t2.y;
               }
             }
@@ -355,7 +355,7 @@ extern "C" int lavb_conv_pair_umma(const lavb_conv_pair_desc* d, void* stream) {
   a.tiles_per_img = ceil_div(d->h, a.tile_h);
   a.num_tiles = d->n * a.tiles_per_img;
   a.post_relu = d->post_relu;
-  a.out = reinterpret_cast<__nv_bfloat16*>(d->out); a.res = reinterpret_cast<const __nv_bfloat16*>(d->res);
+  a.out = reinterpret_cast<h16*>(d->out); a.res = reinterpret_cast<const h16*>(d->res);
   a.bias1 = d->bias1; a.bias2 = d->bias2; a.scale2 = d->scale2; a.shift2 = d->shift2;
   const int slot_bytes = kABytes + d->c * kBlockK * 2;
   const int mid_bytes = 3 * a.kchunks * kABytes;
@@ -367,7 +367,7 @@ extern "C" int lavb_conv_pair_umma(const lavb_conv_pair_desc* d, void* stream) {
     cuuint64_t strides[3] = {(cuuint64_t)d->c * 2, (cuuint64_t)d->w * d->c * 2, (cuuint64_t)d->h * d->w * d->c * 2};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)a.tile_w, (cuuint32_t)a.tile_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->in), dims, strides, box, estr,
+    CUresult r = encode(&tmap_a, LAVB_TMAP_H16, 4, const_cast<void*>(d->in), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LAVB_CHECK_ARG(r == CUDA_SUCCESS, "conv_pair_umma: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
@@ -377,17 +377,13 @@ extern "C" int lavb_conv_pair_umma(const lavb_conv_pair_desc* d, void* stream) {
     cuuint64_t strides[1] = {(cuuint64_t)d->c * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)d->c};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(which ? &tmap_w2 : &tmap_w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(which ? d->w2 : d->w1), dims,
+    CUresult r = encode(which ? &tmap_w2 : &tmap_w1, LAVB_TMAP_H16, 2, const_cast<void*>(which ? d->w2 : d->w1), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LAVB_CHECK_ARG(r == CUDA_SUCCESS, "conv_pair_umma: cuTensorMapEncodeTiled(W%d) failed with %d", which + 1, (int)r);
   }
   const size_t smem = (size_t)a.stages * slot_bytes + mid_bytes + 1024 /*align*/ + 16 * kMaxStages + 96 + 3 * 128 * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    LAVB_CUDA_OK(cudaFuncSetAttribute(conv_pair_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  LAVB_CUDA_OK(ensure_dyn_smem((const void*)conv_pair_umma_kernel, 227 * 1024));
   const int grid = min(a.num_tiles, kNumSMs);
   conv_pair_umma_kernel<<<grid, 64 + 32 * kEpiWarps, smem, (cudaStream_t)stream>>>(tmap_a, tmap_w1, tmap_w2, a);
   LAVB_LAUNCH_OK();

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256) conv_small_kernel(const __grid_constant__
 // loaded straight from global memory (a pixel's 16 channels are 32 contiguous bytes = exactly one fragment row), the
 // weights of a 16-wide output chunk live in registers as B fragments, and the epilogue is the usual fused one.
 __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." LAVB_H16_PTX "." LAVB_H16_PTX ".f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(128) conv_c16_mma_kernel(const __grid_constant
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const float* wp = a.w + ((long long)t * 16 + (2 * tq + 8 * h)) * a.cout_pad + co0 + nn * 8 + gq;
-        const __nv_bfloat162 b2 = __floats2bfloat162_rn(t < a.ntaps ? __ldg(wp) : 0.f, t < a.ntaps ? __ldg(wp + a.cout_pad) : 0.f);
+        const h162 b2 = floats2h162(t < a.ntaps ? __ldg(wp) : 0.f, t < a.ntaps ? __ldg(wp + a.cout_pad) : 0.f);
         bf[t][nn][h] = *reinterpret_cast<const uint32_t*>(&b2);
       }
   float e_bias[2][2], e_scale[2][2], e_shift[2][2];
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(128) conv_c16_mma_kernel(const __grid_constant
     }
   const float lo_pre = a.pre_relu ? 0.f : -INFINITY, lo_post = a.post_relu ? 0.f : -INFINITY;
   const bool pair_ok = (a.out_coff % 2 == 0) && (a.out_cstride % 2 == 0) && (a.res == nullptr || (a.res_coff % 2 == 0 && a.res_cstride % 2 == 0));
-  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(a.in) + (long long)img * a.hin * a.win * a.in_cstride + a.in_coff + 2 * tq;
+  const h16* in = reinterpret_cast<const h16*>(a.in) + (long long)img * a.hin * a.win * a.in_cstride + a.in_coff + 2 * tq;
   // the 4 pixels this lane touches: rows gq, gq+8 of both m-tiles
   int gx[4]; bool pv[4];
 #pragma unroll
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(128) conv_c16_mma_kernel(const __grid_constant
     if (t < a.ntaps) {
       const int iy = gy * a.in_sy + a.dy[t];
       const bool row_ok = iy >= 0 && iy < a.hin;
-      const __nv_bfloat16* rowp = in + (long long)iy * a.win * a.in_cstride;
+      const h16* rowp = in + (long long)iy * a.win * a.in_cstride;
       uint32_t af[4][2];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(128) conv_c16_mma_kernel(const __grid_constant
 template <typename TIn, typename TOut>
 static int launch_conv(ConvArgs& a, cudaStream_t st) {
   const long long M = (long long)a.n * a.hog * a.wog;
-  if constexpr (std::is_same<TIn, __nv_bfloat16>::value) {
+  if constexpr (std::is_same<TIn, h16>::value) {
     if (a.cin == 16 && a.ntaps <= 9 && a.in_coff % 2 == 0 && a.in_cstride % 2 == 0) {   // tensor-core path for 16-channel layers
       // rows per block: as many as keeps >= ~16 blocks per SM in flight, at most 8
       const long long row_blocks = (long long)a.n * a.hog * ceil_div(a.wog, 128) * (a.cout_pad / 16);
@@ -506,9 +506,9 @@ extern "C" int lavb_conv_taps(const lavb_conv_desc* d, void* stream) {
   LAVB_CHECK_ARG(d->res == nullptr || d->res_dtype == d->out_dtype, "conv_taps: residual dtype must equal output dtype");
   cudaStream_t st = (cudaStream_t)stream;
   if (d->in_dtype == LAVB_F32 && d->out_dtype == LAVB_F32) return launch_conv<float, float>(a, st);
-  if (d->in_dtype == LAVB_BF16 && d->out_dtype == LAVB_BF16) return launch_conv<__nv_bfloat16, __nv_bfloat16>(a, st);
-  if (d->in_dtype == LAVB_F32 && d->out_dtype == LAVB_BF16) return launch_conv<float, __nv_bfloat16>(a, st);
-  if (d->in_dtype == LAVB_BF16 && d->out_dtype == LAVB_F32) return launch_conv<__nv_bfloat16, float>(a, st);
+  if (d->in_dtype == LAVB_H16 && d->out_dtype == LAVB_H16) return launch_conv<h16, h16>(a, st);
+  if (d->in_dtype == LAVB_F32 && d->out_dtype == LAVB_H16) return launch_conv<float, h16>(a, st);
+  if (d->in_dtype == LAVB_H16 && d->out_dtype == LAVB_F32) return launch_conv<h16, float>(a, st);
   LAVB_CHECK_ARG(false, "conv_taps: unsupported dtype combination");
 }
 
@@ -524,16 +524,16 @@ extern "C" int lavb_pool2_affine_relu(const void* d_in, int dtype, int n, int hi
   if (vec && dtype == LAVB_F32) {
     pool2_vec4_kernel<float><<<ceil_div(total / 4, 256), 256, 0, st>>>((const float*)d_in, n, hin, win, c, in_cstride, in_coff, d_scale,
                                                                         d_shift, (float*)d_out, out_cstride, out_coff);
-  } else if (vec && dtype == LAVB_BF16) {
-    pool2_vec4_kernel<__nv_bfloat16><<<ceil_div(total / 4, 256), 256, 0, st>>>((const __nv_bfloat16*)d_in, n, hin, win, c, in_cstride,
-                                                                                in_coff, d_scale, d_shift, (__nv_bfloat16*)d_out,
+  } else if (vec && dtype == LAVB_H16) {
+    pool2_vec4_kernel<h16><<<ceil_div(total / 4, 256), 256, 0, st>>>((const h16*)d_in, n, hin, win, c, in_cstride,
+                                                                                in_coff, d_scale, d_shift, (h16*)d_out,
                                                                                 out_cstride, out_coff);
   } else if (dtype == LAVB_F32)
     pool2_kernel<float><<<ceil_div(total, 256), 256, 0, st>>>((const float*)d_in, n, hin, win, c, in_cstride, in_coff, d_scale,
                                                                d_shift, (float*)d_out, out_cstride, out_coff);
-  else if (dtype == LAVB_BF16)
-    pool2_kernel<__nv_bfloat16><<<ceil_div(total, 256), 256, 0, st>>>((const __nv_bfloat16*)d_in, n, hin, win, c, in_cstride,
-                                                                       in_coff, d_scale, d_shift, (__nv_bfloat16*)d_out,
+  else if (dtype == LAVB_H16)
+    pool2_kernel<h16><<<ceil_div(total, 256), 256, 0, st>>>((const h16*)d_in, n, hin, win, c, in_cstride,
+                                                                       in_coff, d_scale, d_shift, (h16*)d_out,
                                                                        out_cstride, out_coff);
   else LAVB_CHECK_ARG(false, "pool2: bad dtype");
   LAVB_LAUNCH_OK();

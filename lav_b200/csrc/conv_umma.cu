@@ -39,7 +39,7 @@ struct UmmaArgs {
   int pre_relu, post_relu, sigmoid, d2s_nout, cout_store;
   int wres;   // weights-stationary: all ntaps*kchunks B blocks are loaded once per CTA and stay in shared memory
   int dy[kMaxTaps], dx[kMaxTaps];
-  void* out; const __nv_bfloat16* res;
+  void* out; const h16* res;
   const float* bias; const float* scale; const float* shift;
 };
 
@@ -86,7 +86,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   return (uint64_t)lo | ((uint64_t)hi << 32);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_h16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : LAVB
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both, N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.cout >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (kH16Fmt << 7) | (kH16Fmt << 10) | ((uint32_t)(p.cout >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       if (wres) { mbar_wait(wbar, 0); tc_fence_after(); }
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : LAVB
           const uint64_t a_desc = make_sw128_desc(sa), b_desc = make_sw128_desc(wres ? bres + kb * b_bytes : sa + kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)   // +32 B per K16 step inside the 128 B swizzle atom
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            umma_h16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
           umma_commit(empty_bar + 8 * stage);      // frees the smem slot once these MMAs have read it
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : LAVB
               const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 t2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                const float2 t2 = h1622float2(*reinterpret_cast<const h162*>(&w[e]));
                 f[j * 8 + e * 2] += t2.x; f[j * 8 + e * 2 + 1] += t2.y;
               }
             }
@@ -271,13 +271,13 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : LAVB
             for (int j = 0; j < 8; ++j)
               if (c0 + 4 * j < p.cout_store) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cstride + p.out_coff + c0);
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<h16*>(p.out) + pix * p.out_cstride + p.out_coff + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint32_t w[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
+                const h162 b2 = floats2h162(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
                 w[e] = *reinterpret_cast<const uint32_t*>(&b2);
               }
               if (c0 + 8 * j < p.cout_store) op[j] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -315,8 +315,8 @@ using namespace lavb;
 
 extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   LAVB_CHECK_ARG(d != nullptr, "conv_umma: null descriptor");
-  LAVB_CHECK_ARG(d->in_dtype == LAVB_BF16, "conv_umma: input must be bf16");
-  LAVB_CHECK_ARG(d->out_dtype == LAVB_BF16 || d->out_dtype == LAVB_F32, "conv_umma: bad output dtype");
+  LAVB_CHECK_ARG(d->in_dtype == LAVB_H16, "conv_umma: input must be bf16");
+  LAVB_CHECK_ARG(d->out_dtype == LAVB_H16 || d->out_dtype == LAVB_F32, "conv_umma: bad output dtype");
   LAVB_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= kMaxTaps, "conv_umma: ntaps must be 1..16");
   LAVB_CHECK_ARG(d->cin % 64 == 0 && d->cin > 0, "conv_umma: cin must be a multiple of 64 (got %d)", d->cin);
   LAVB_CHECK_ARG(d->cout % 8 == 0 && d->cout >= 8 && d->cout <= 256, "conv_umma: cout must be 8..256, multiple of 8 (got %d)", d->cout);
@@ -324,7 +324,7 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   LAVB_CHECK_ARG(d->res == nullptr || cout_mma == d->cout, "conv_umma: residual needs cout %% 32 == 0");
   LAVB_CHECK_ARG(d->in_cstride % 8 == 0 && d->in_coff % 8 == 0 && d->in_coff + d->cin <= d->in_cstride, "conv_umma: input slice misaligned");
   LAVB_CHECK_ARG(d->out_cstride % 8 == 0 && d->out_coff % 8 == 0 && d->out_coff + d->cout <= d->out_cstride, "conv_umma: output slice misaligned");
-  LAVB_CHECK_ARG(d->res == nullptr || (d->res_dtype == LAVB_BF16 && d->res_cstride % 8 == 0 && d->res_coff % 8 == 0), "conv_umma: residual must be bf16, 16 B aligned");
+  LAVB_CHECK_ARG(d->res == nullptr || (d->res_dtype == LAVB_H16 && d->res_cstride % 8 == 0 && d->res_coff % 8 == 0), "conv_umma: residual must be bf16, 16 B aligned");
   LAVB_CHECK_ARG((d->scale == nullptr) == (d->shift == nullptr), "conv_umma: scale and shift come together");
   LAVB_CHECK_ARG(d->in_sy >= 1 && d->in_sy <= 8 && d->in_sx >= 1 && d->in_sx <= 8, "conv_umma: bad input stride");
   auto encode = get_encode();
@@ -332,13 +332,13 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
 
   CUtensorMap tmap_a, tmap_b;
   {
-    const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(d->in) + d->in_coff;
+    const h16* in = reinterpret_cast<const h16*>(d->in) + d->in_coff;
     cuuint64_t dims[4] = {(cuuint64_t)d->cin, (cuuint64_t)d->win, (cuuint64_t)d->hin, (cuuint64_t)d->n};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_cstride * 2, (cuuint64_t)d->win * d->in_cstride * 2,
                              (cuuint64_t)d->hin * d->win * d->in_cstride * 2};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(kTileW * d->in_sx), (cuuint32_t)(kTileH * d->in_sy), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->in_sx, (cuuint32_t)d->in_sy, 1};
-    CUresult r = encode(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(in), dims, strides, box, estr,
+    CUresult r = encode(&tmap_a, LAVB_TMAP_H16, 4, const_cast<h16*>(in), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LAVB_CHECK_ARG(r == CUDA_SUCCESS, "conv_umma: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
@@ -348,7 +348,7 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
     cuuint64_t strides[1] = {(cuuint64_t)d->cin * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)cout_mma};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<float*>(d->w), dims, strides, box, estr,
+    CUresult r = encode(&tmap_b, LAVB_TMAP_H16, 2, const_cast<float*>(d->w), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LAVB_CHECK_ARG(r == CUDA_SUCCESS, "conv_umma: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
@@ -387,7 +387,7 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
                    d->out_sx == 2 && d->res == nullptr, "conv_umma: depth-to-space epilogue needs cout=32, fp32 out, out_s=2, no residual");
   }
   for (int t = 0; t < d->ntaps; ++t) { a.dy[t] = d->dy[t]; a.dx[t] = d->dx[t]; }
-  a.out = d->out; a.res = reinterpret_cast<const __nv_bfloat16*>(d->res);
+  a.out = d->out; a.res = reinterpret_cast<const h16*>(d->res);
   a.bias = d->bias; a.scale = d->scale; a.shift = d->shift;
   if (a.num_tiles == 0) return 0;
   const size_t smem = (size_t)a.stages * stage_bytes + (a.wres ? res_bytes : 0) + 1024 /*align*/ + 16 * kMaxStages + 64 + 3 * 256 * sizeof(float);
@@ -395,12 +395,7 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   if (a.d2s_nout) {
 #define LAVB_D2S(S)                                                                                                     \
     {                                                                                                                   \
-      static bool configured = false;                                                                                   \
-      if (!configured) {                                                                                                \
-        LAVB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<true, false, S, false, 4, true>,                            \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));                    \
-        configured = true;                                                                                              \
-      }                                                                                                                 \
+      LAVB_CUDA_OK(ensure_dyn_smem((const void*)conv_umma_kernel<true, false, S, false, 4, true>, 112 * 1024));         \
       conv_umma_kernel<true, false, S, false, 4, true><<<grid, 64 + 32 * 4, smem, (cudaStream_t)stream>>>(tmap_a, tmap_b, a); \
       LAVB_LAUNCH_OK();                                                                                                 \
       return 0;                                                                                                         \
@@ -412,12 +407,8 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   // epilogue variants are compiled separately so the inner loop carries no runtime flag tests
 #define LAVB_UMMA_LAUNCH(F, R, S, B, EW)                                                                                \
   {                                                                                                                     \
-    static bool configured = false; /* once per process and variant, never during a later stream capture */            \
-    if (!configured) {                                                                                                  \
-      LAVB_CUDA_OK(cudaFuncSetAttribute(conv_umma_kernel<F, R, S, B, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        EW == 4 ? 112 * 1024 : 227 * 1024));                                            \
-      configured = true;                                                                                                \
-    }                                                                                                                   \
+    /* once per (variant, device), never during a later stream capture (callers warm up first) */                       \
+    LAVB_CUDA_OK(ensure_dyn_smem((const void*)conv_umma_kernel<F, R, S, B, EW>, EW == 4 ? 112 * 1024 : 227 * 1024));    \
     conv_umma_kernel<F, R, S, B, EW><<<grid, 64 + 32 * EW, smem, (cudaStream_t)stream>>>(tmap_a, tmap_b, a);            \
     LAVB_LAUNCH_OK();                                                                                                   \
     return 0;                                                                                                           \

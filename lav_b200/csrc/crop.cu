@@ -16,22 +16,22 @@ template <> struct Vec16<float> {
   }
   static __device__ __forceinline__ void store(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 };
-template <> struct Vec16<__nv_bfloat16> {
+template <> struct Vec16<h16> {
   static constexpr int N = 8;
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+  static __device__ __forceinline__ void load(const h16* p, float (&v)[8]) {
     const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
     const uint32_t u[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[e]));
+      const float2 f = h1622float2(*reinterpret_cast<const h162*>(&u[e]));
       v[2 * e] = f.x; v[2 * e + 1] = f.y;
     }
   }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+  static __device__ __forceinline__ void store(h16* p, const float (&v)[8]) {
     uint32_t u[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      const h162 h = floats2h162(v[2 * e], v[2 * e + 1]);
       u[e] = *reinterpret_cast<const uint32_t*>(&h);
     }
     *reinterpret_cast<uint4*>(p) = make_uint4(u[0], u[1], u[2], u[3]);
@@ -100,9 +100,9 @@ extern "C" int lavb_crop_bilinear(const void* d_feat, int dtype, int b, int h, i
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == LAVB_F32)
     crop_kernel<float><<<blocks, 256, 0, st>>>((const float*)d_feat, b, h, w, c, d_frame_idx, d_theta, k, crop, (float*)d_out);
-  else if (dtype == LAVB_BF16)
-    crop_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)d_feat, b, h, w, c, d_frame_idx, d_theta, k, crop,
-                                                           (__nv_bfloat16*)d_out);
+  else if (dtype == LAVB_H16)
+    crop_kernel<h16><<<blocks, 256, 0, st>>>((const h16*)d_feat, b, h, w, c, d_frame_idx, d_theta, k, crop,
+                                                           (h16*)d_out);
   else LAVB_CHECK_ARG(false, "crop_bilinear: bad dtype");
   LAVB_LAUNCH_OK();
   return 0;

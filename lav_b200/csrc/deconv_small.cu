@@ -108,14 +108,10 @@ extern "C" int lavb_deconv3x3s2_small(const void* d_in, int dtype, int n, int h,
   dim3 grid(n * ceil_div(h, kTH) * ceil_div(w, kTW), groups);
   const size_t smem = ((size_t)cin_g * 36 + (size_t)(kTH + 1) * (kTW + 1) * kPitch) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  static bool configured = false;
-  if (!configured) {
-    LAVB_CUDA_OK(cudaFuncSetAttribute(deconv3x3s2_small_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    LAVB_CUDA_OK(cudaFuncSetAttribute(deconv3x3s2_small_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    configured = true;
-  }
+  LAVB_CUDA_OK(ensure_dyn_smem((const void*)deconv3x3s2_small_kernel<float>, 64 * 1024));
+  LAVB_CUDA_OK(ensure_dyn_smem((const void*)deconv3x3s2_small_kernel<h16>, 64 * 1024));
   if (dtype == LAVB_F32) deconv3x3s2_small_kernel<float><<<grid, kTH * kTW, smem, st>>>(a);
-  else if (dtype == LAVB_BF16) deconv3x3s2_small_kernel<__nv_bfloat16><<<grid, kTH * kTW, smem, st>>>(a);
+  else if (dtype == LAVB_H16) deconv3x3s2_small_kernel<h16><<<grid, kTH * kTW, smem, st>>>(a);
   else LAVB_CHECK_ARG(false, "deconv_small: bad dtype");
   LAVB_LAUNCH_OK();
   return 0;

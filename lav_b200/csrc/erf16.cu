@@ -1,0 +1,172 @@
+// Fused non_bottleneck_1d block for the 16-channel ERFNet decoder stage (lav/models/erfnet.py:37-63, Decoder layers 4-5):
+//     t1 = relu(conv3x1_1(x) + b)         t2 = relu(bn1(conv1x3_1(t1) + b))
+//     t3 = relu(conv3x1_2(t2) + b)        y  = relu(bn2(conv1x3_2(t3) + b) + x)          (dilation 1, Dropout2d inactive in eval)
+// in ONE kernel: a CTA owns 8 output rows of one image at full width, stages the 12 input rows it needs (+-2 halo rows for the two
+// vertical convs) in shared memory and runs the four convolutions there, ping-ponging between two row buffers.  Each conv tap is
+// one K16 step of mma.sync m16n8k16 (16 input channels = one k-step, 16 output channels = two n-tiles); A fragments come from
+// shared memory by ldmatrix.x4 (16 consecutive pixels of a row x 16 channels), the 4 x 3 x 2 weight fragments live in
+// registers.  Layer by layer this stage moved every activation through HBM eight times (8 launches of conv_c16_mma, ~56 us each
+// at 96 images); fused, the block reads its input once (+ halo re-reads that hit L2) and writes its output once.
+//
+// Shared-memory row layout: (W + 2) pixels of 32 B (one zero guard pixel on each side = the horizontal zero padding); the two
+// 16-byte halves of a pixel are swapped when bit 2 of the pixel index is set, which makes both the ldmatrix row reads and the
+// fragment-layout epilogue stores bank-conflict free.
+#include "common.cuh"
+
+namespace lavb {
+
+constexpr int kNbRowsOut = 8, kNbHalo = 2, kNbRows = kNbRowsOut + 2 * kNbHalo;      // 12 staged rows per tile
+constexpr int kNbThreads = 256;
+
+struct Nb16Args {
+  const h16* in; h16* out;
+  int n, h, w;
+  const float* w4;        // [4 convs][3 taps][16 cin][16 cout] fp32
+  const float* st;        // [4 convs][16 cout][2] = (scale, shift) with the conv bias folded in: epi(a) = relu(a * s + t)
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." LAVB_H16_PTX "." LAVB_H16_PTX ".f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// byte offset of (pixel index incl. guard, 16-byte half) inside a buffer
+__device__ __forceinline__ uint32_t px_off(int pix, int half) { return (uint32_t)pix * 32u + (uint32_t)((half ^ ((pix >> 2) & 1)) << 4); }
+
+// One convolution stage over tile rows [row_lo, row_hi): kVert = 3x1 (taps along rows) else 1x3 (taps along columns).
+// kRes: add the residual found in `dst` at the output position and write in place (dst holds x there).
+template <bool kVert, bool kRes>
+__device__ __forceinline__ void nb16_stage(uint32_t src, uint32_t dst, int pitch, int w, int row_lo, int row_hi, int g_row0, int h,
+                                           const uint32_t (&bf)[3][2][2], const float (&st)[2][2][2], int warp, int lane) {
+  const int tpr = w >> 4;                       // m16 tiles per row
+  const int gq = lane >> 2, tq = lane & 3;
+  const int mi = lane & 7, mj = lane >> 3;      // ldmatrix: this lane addresses row mi of matrix mj
+  for (int mt = warp; mt < (row_hi - row_lo) * tpr; mt += kNbThreads / 32) {
+    const int r = row_lo + mt / tpr, c0 = (mt % tpr) << 4;
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap) {
+      const int rr = kVert ? r + tap - 1 : r, cc = kVert ? c0 : c0 + tap - 1;
+      const int pix = rr * pitch + cc + mi + ((mj & 1) << 3) + 1;
+      uint32_t a[4];
+      ldsm_x4(src + px_off(pix, mj >> 1), a);
+      mma16816(acc[0], a, bf[tap][0][0], bf[tap][0][1]);
+      mma16816(acc[1], a, bf[tap][1][0], bf[tap][1][1]);
+    }
+    const bool inside = (unsigned)(g_row0 + r) < (unsigned)h;     // rows outside the image are the next conv's zero padding
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {                        // accumulator rows gq (c[0], c[1]) and gq + 8 (c[2], c[3])
+      const int pix = r * pitch + c0 + gq + 8 * hrow + 1;
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) {
+        const uint32_t addr = dst + px_off(pix, nn) + (uint32_t)tq * 4u;
+        float v0 = fmaf(acc[nn][2 * hrow], st[nn][0][0], st[nn][0][1]), v1 = fmaf(acc[nn][2 * hrow + 1], st[nn][1][0], st[nn][1][1]);
+        if (kRes) {
+          uint32_t xr;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(xr) : "r"(addr));
+          const float2 xf = unpack_h16(xr);
+          v0 += xf.x; v1 += xf.y;
+        }
+        const uint32_t o = inside ? pack_h16(fmaxf(v0, 0.f), fmaxf(v1, 0.f)) : 0u;
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(o) : "memory");
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kNbThreads, 2) erf_nb16_kernel(const __grid_constant__ Nb16Args p) {
+  extern __shared__ __align__(128) uint8_t nb_sm[];
+  const int pitch = p.w + 2;
+  const uint32_t buf_bytes = (uint32_t)kNbRows * pitch * 32u;
+  const uint32_t A = (uint32_t)__cvta_generic_to_shared(nb_sm), B = A + buf_bytes;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int tiles_y = (p.h + kNbRowsOut - 1) / kNbRowsOut;
+  const int img = blockIdx.x / tiles_y, ty = blockIdx.x - img * tiles_y;
+  const int g_row0 = ty * kNbRowsOut - kNbHalo;             // global row of tile row 0
+
+  // weight fragments (B operand, "col" layout): b0 = W[k = 2tq, 2tq+1][n = gq], b1 = W[k = 2tq+8, +9][n = gq] per n-tile
+  uint32_t bf[4][3][2][2];
+  float st[4][2][2][2];                                     // [conv][n-tile][col 2tq / 2tq+1][scale, shift]
+#pragma unroll
+  for (int cv = 0; cv < 4; ++cv) {
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) {
+        const float* wp = p.w4 + ((cv * 3 + tap) * 16) * 16 + nn * 8 + gq;          // [cin][cout]
+        bf[cv][tap][nn][0] = pack_h16(__ldg(wp + (2 * tq) * 16), __ldg(wp + (2 * tq + 1) * 16));
+        bf[cv][tap][nn][1] = pack_h16(__ldg(wp + (2 * tq + 8) * 16), __ldg(wp + (2 * tq + 9) * 16));
+      }
+#pragma unroll
+    for (int nn = 0; nn < 2; ++nn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(p.st) + cv * 16 + nn * 8 + 2 * tq + e);
+        st[cv][nn][e][0] = v.x; st[cv][nn][e][1] = v.y;
+      }
+  }
+  // zero both buffers' guard pixels (the stages never write them)
+  for (int i = tid; i < 2 * kNbRows * 2 * 2; i += kNbThreads) {
+    const int buf = i / (kNbRows * 4), rem = i % (kNbRows * 4), r = rem >> 2, side = (rem >> 1) & 1, half = rem & 1;
+    const int pix = r * pitch + (side ? p.w + 1 : 0);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"((buf ? B : A) + px_off(pix, half)), "r"(0u) : "memory");
+  }
+  // stage 0: x rows [g_row0, g_row0 + 12) -> A (zeros outside the image)
+  const h16* src_img = p.in + (size_t)img * p.h * p.w * 16;
+  const int chunks_per_row = p.w * 2;
+  for (int i = tid; i < kNbRows * chunks_per_row; i += kNbThreads) {
+    const int r = i / chunks_per_row, c = i - r * chunks_per_row, px = c >> 1, half = c & 1;
+    const int gr = g_row0 + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if ((unsigned)gr < (unsigned)p.h) v = __ldg(reinterpret_cast<const uint4*>(src_img + ((size_t)gr * p.w + px) * 16) + half);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(A + px_off(r * pitch + px + 1, half)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+  __syncthreads();
+  nb16_stage<true, false>(A, B, pitch, p.w, 1, kNbRows - 1, g_row0, p.h, bf[0], st[0], warp, lane);       // t1: rows 1..10
+  __syncthreads();
+  nb16_stage<false, false>(B, A, pitch, p.w, 1, kNbRows - 1, g_row0, p.h, bf[1], st[1], warp, lane);      // t2: rows 1..10
+  __syncthreads();
+  nb16_stage<true, false>(A, B, pitch, p.w, 2, kNbRows - 2, g_row0, p.h, bf[2], st[2], warp, lane);       // t3: rows 2..9
+  __syncthreads();
+  // the residual: x rows 2..9 back into A (L2 hits), then the last conv adds it in place
+  for (int i = tid; i < kNbRowsOut * chunks_per_row; i += kNbThreads) {
+    const int r = kNbHalo + i / chunks_per_row, c = i % chunks_per_row, px = c >> 1, half = c & 1;
+    const int gr = g_row0 + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if ((unsigned)gr < (unsigned)p.h) v = __ldg(reinterpret_cast<const uint4*>(src_img + ((size_t)gr * p.w + px) * 16) + half);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(A + px_off(r * pitch + px + 1, half)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+  __syncthreads();
+  nb16_stage<false, true>(B, A, pitch, p.w, 2, kNbRows - 2, g_row0, p.h, bf[3], st[3], warp, lane);       // y: rows 2..9, in place over x
+  __syncthreads();
+  h16* dst_img = p.out + (size_t)img * p.h * p.w * 16;
+  for (int i = tid; i < kNbRowsOut * chunks_per_row; i += kNbThreads) {
+    const int r = kNbHalo + i / chunks_per_row, c = i % chunks_per_row, px = c >> 1, half = c & 1;
+    const int gr = g_row0 + r;
+    if ((unsigned)gr >= (unsigned)p.h) continue;
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(A + px_off(r * pitch + px + 1, half)));
+    *(reinterpret_cast<uint4*>(dst_img + ((size_t)gr * p.w + px) * 16) + half) = v;
+  }
+}
+
+}  // namespace lavb
+
+using namespace lavb;
+
+extern "C" int lavb_erf_nb16(const void* d_in, void* d_out, int n, int h, int w, const float* d_w4, const float* d_st, void* stream) {
+  LAVB_CHECK_ARG(n >= 0 && h >= 1 && w >= 16 && w % 16 == 0 && w <= 256, "erf_nb16: width must be a multiple of 16, <= 256 (got %d)", w);
+  LAVB_CHECK_ARG(d_in != d_out, "erf_nb16: in-place is not supported (halo rows of neighbouring tiles are re-read)");
+  if (n == 0) return 0;
+  Nb16Args a;
+  a.in = reinterpret_cast<const h16*>(d_in); a.out = reinterpret_cast<h16*>(d_out);
+  a.n = n; a.h = h; a.w = w; a.w4 = d_w4; a.st = d_st;
+  const int smem = 2 * kNbRows * (w + 2) * 32;
+  LAVB_CUDA_OK(ensure_dyn_smem((const void*)erf_nb16_kernel, smem));
+  const int tiles_y = (h + kNbRowsOut - 1) / kNbRowsOut;
+  erf_nb16_kernel<<<n * tiles_y, kNbThreads, smem, (cudaStream_t)stream>>>(a);
+  LAVB_LAUNCH_OK();
+  return 0;
+}

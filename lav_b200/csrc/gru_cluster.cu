@@ -35,21 +35,21 @@ __device__ __forceinline__ void gru_ldmatrix_x4(uint32_t addr, uint32_t& r0, uin
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
 __device__ __forceinline__ void gru_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." LAVB_H16_PTX "." LAVB_H16_PTX ".f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ float gru_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
 __global__ void __launch_bounds__(256, 1) gru_cluster_kernel(const float* __restrict__ u, const float* __restrict__ h0,
-                                                             const __nv_bfloat16* __restrict__ whh, const float* __restrict__ wih,
+                                                             const h16* __restrict__ whh, const float* __restrict__ wih,
                                                              const float* __restrict__ bih, const float* __restrict__ bhh,
                                                              float* __restrict__ out, int nseq, int steps) {
   extern __shared__ __align__(16) uint8_t gsm[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();                       // which 32 hidden units this CTA owns
   const int seq0 = ((int)blockIdx.x / kGruCluster) * kGruSeq;       // first sequence of this cluster
-  __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(gsm + GruSmem::w);
-  __nv_bfloat16* Hb = reinterpret_cast<__nv_bfloat16*>(gsm + GruSmem::hb);
+  h16* Ws = reinterpret_cast<h16*>(gsm + GruSmem::w);
+  h16* Hb = reinterpret_cast<h16*>(gsm + GruSmem::hb);
   float* G = reinterpret_cast<float*>(gsm + GruSmem::g);
   float* Hm = reinterpret_cast<float*>(gsm + GruSmem::hm);
   float* Wi = reinterpret_cast<float*>(gsm + GruSmem::wih);
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256, 1) gru_cluster_kernel(const float* __rest
   for (int i = tid; i < kGruSeq * kGruH; i += 256) {
     const int s = i / kGruH, k = i - s * kGruH;
     const float v = (seq0 + s < nseq) ? __ldg(h0 + (long long)(seq0 + s) * kGruH + k) : 0.f;
-    Hb[s * kGruHPitch + k] = __float2bfloat16_rn(v);
+    Hb[s * kGruHPitch + k] = float2h16(v);
     const int j = k - rank * kGruUnits;
     if (j >= 0 && j < kGruUnits) Hm[s * kGruUnits + j] = v;
   }
@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(256, 1) gru_cluster_kernel(const float* __rest
   const int gs = tid >> 3, gu = (tid & 7) * 4;                      // gate role: sequence, first of 4 hidden units
   const bool seq_ok = seq0 + gs < nseq;
   for (int t = 0; t < steps; ++t) {
-    const __nv_bfloat16* hc = Hb + (t & 1) * kGruSeq * kGruHPitch;
-    __nv_bfloat16* hn = Hb + ((t & 1) ^ 1) * kGruSeq * kGruHPitch;
+    const h16* hc = Hb + (t & 1) * kGruSeq * kGruHPitch;
+    h16* hn = Hb + ((t & 1) ^ 1) * kGruSeq * kGruHPitch;
     // ---- (1) G[32 seq][96] = h (32 x 512) . Wslice^T on the tensor cores
     float acc[3][4];
 #pragma unroll
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256, 1) gru_cluster_kernel(const float* __rest
       gru_ldmatrix_x4(a_base + kk * 32, a0, a1, a2, a3);
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const __nv_bfloat16* wp = Ws + ((ng * 3 + j) * 8 + gq) * kGruWPitch + kk * 16 + 2 * tq;
+        const h16* wp = Ws + ((ng * 3 + j) * 8 + gq) * kGruWPitch + kk * 16 + 2 * tq;
         gru_mma(acc[j], a0, a1, a2, a3, *reinterpret_cast<const uint32_t*>(wp), *reinterpret_cast<const uint32_t*>(wp + 8));
       }
     }
@@ -128,10 +128,10 @@ __global__ void __launch_bounds__(256, 1) gru_cluster_kernel(const float* __rest
     if (seq_ok)
       *reinterpret_cast<float4*>(out + ((long long)(seq0 + gs) * steps + t) * kGruH + rank * kGruUnits + gu) = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
     {
-      const __nv_bfloat162 p0 = __floats2bfloat162_rn(hnew[0], hnew[1]), p1 = __floats2bfloat162_rn(hnew[2], hnew[3]);
+      const h162 p0 = floats2h162(hnew[0], hnew[1]), p1 = floats2h162(hnew[2], hnew[3]);
       uint2 pk;
       pk.x = *reinterpret_cast<const uint32_t*>(&p0); pk.y = *reinterpret_cast<const uint32_t*>(&p1);
-      __nv_bfloat16* dst = hn + gs * kGruHPitch + rank * kGruUnits + gu;   // same offset in every CTA's shared memory
+      h16* dst = hn + gs * kGruHPitch + rank * kGruUnits + gu;   // same offset in every CTA's shared memory
 #pragma unroll
       for (int peer = 0; peer < kGruCluster; ++peer)
         *reinterpret_cast<uint2*>(cluster.map_shared_rank(dst, peer)) = pk;
@@ -144,16 +144,12 @@ __global__ void __launch_bounds__(256, 1) gru_cluster_kernel(const float* __rest
 
 using namespace lavb;
 
-extern "C" int lavb_gru_h512(const float* d_u, const float* d_h0, const void* d_whh_bf16, const float* d_wih, const float* d_bih,
+extern "C" int lavb_gru_h512(const float* d_u, const float* d_h0, const void* d_whh_h16, const float* d_wih, const float* d_bih,
                              const float* d_bhh, float* d_out, int nseq, int steps, void* stream) {
   LAVB_CHECK_ARG(nseq >= 0 && steps >= 1, "gru_h512: bad shape");
   if (nseq == 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    LAVB_CUDA_OK(cudaFuncSetAttribute(gru_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GruSmem::total));
-    LAVB_CUDA_OK(cudaFuncSetAttribute(gru_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    configured = true;
-  }
+  LAVB_CUDA_OK(ensure_dyn_smem((const void*)gru_cluster_kernel, GruSmem::total));
+  LAVB_CUDA_OK(cudaFuncSetAttribute(gru_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(ceil_div(nseq, kGruSeq) * kGruCluster);
@@ -164,7 +160,7 @@ extern "C" int lavb_gru_h512(const float* d_u, const float* d_h0, const void* d_
   attr.id = cudaLaunchAttributeClusterDimension;
   attr.val.clusterDim.x = kGruCluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
-  LAVB_CUDA_OK(cudaLaunchKernelEx(&cfg, gru_cluster_kernel, d_u, d_h0, reinterpret_cast<const __nv_bfloat16*>(d_whh_bf16), d_wih, d_bih,
+  LAVB_CUDA_OK(cudaLaunchKernelEx(&cfg, gru_cluster_kernel, d_u, d_h0, reinterpret_cast<const h16*>(d_whh_h16), d_wih, d_bih,
                                   d_bhh, d_out, nseq, steps));
   return 0;
 }

@@ -393,8 +393,8 @@ __global__ void __launch_bounds__(256) pillar_fill_kernel(const float* __restric
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+__device__ __forceinline__ void mma_h16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." LAVB_H16_PTX "." LAVB_H16_PTX ".f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
@@ -416,12 +416,12 @@ struct EncSmem {                      // shared-memory plan of pillar_encode_sor
 template <bool kSplitOut>
 __device__ __forceinline__ void emit_pair(void* canvas, int cell, int c, float m0, float m1) {     // channels c, c+1 (c even)
   if (kSplitOut) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(canvas) + (long long)cell * 128;
-    const __nv_bfloat162 hi = __floats2bfloat162_rn(m0, m1);
-    const float2 hf = __bfloat1622float2(hi);
-    const __nv_bfloat162 lo = __floats2bfloat162_rn(m0 - hf.x, m1 - hf.y);
-    *reinterpret_cast<__nv_bfloat162*>(o + c) = hi;
-    *reinterpret_cast<__nv_bfloat162*>(o + 64 + c) = lo;
+    h16* o = reinterpret_cast<h16*>(canvas) + (long long)cell * 128;
+    const h162 hi = floats2h162(m0, m1);
+    const float2 hf = h1622float2(hi);
+    const h162 lo = floats2h162(m0 - hf.x, m1 - hf.y);
+    *reinterpret_cast<h162*>(o + c) = hi;
+    *reinterpret_cast<h162*>(o + 64 + c) = lo;
   } else {
     *reinterpret_cast<float2*>(reinterpret_cast<float*>(canvas) + (long long)cell * 64 + c) = make_float2(m0, m1);
   }
@@ -429,23 +429,19 @@ __device__ __forceinline__ void emit_pair(void* canvas, int cell, int c, float m
 template <bool kSplitOut>
 __device__ __forceinline__ void emit_one(void* canvas, int cell, int c, float m) {
   if (kSplitOut) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(canvas) + (long long)cell * 128;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(m);
-    o[c] = hi; o[64 + c] = __float2bfloat16_rn(m - __bfloat162float(hi));
+    h16* o = reinterpret_cast<h16*>(canvas) + (long long)cell * 128;
+    const h16 hi = float2h16(m);
+    o[c] = hi; o[64 + c] = float2h16(m - h162float(hi));
   } else {
     reinterpret_cast<float*>(canvas)[(long long)cell * 64 + c] = m;
   }
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&v);
-}
 // fp32 pair -> bf16 hi pair + bf16 residual pair (error-free split to ~2^-16 relative)
 __device__ __forceinline__ void split_pair(float2 f, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(f.x, f.y);
-  const float2 hf = __bfloat1622float2(h);
+  const h162 h = floats2h162(f.x, f.y);
+  const float2 hf = h1622float2(h);
   hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = pack_bf16(f.x - hf.x, f.y - hf.y);
+  lo = pack_h16(f.x - hf.x, f.y - hf.y);
 }
 
 // Pillar encoder over the cell-sorted point order (both MLP layers on the tensor cores, no canvas atomics).
@@ -472,8 +468,8 @@ __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
   extern __shared__ __align__(128) uint8_t sm[];
   float* fs = reinterpret_cast<float*>(sm + EncSmem::fs);
   float* Os = reinterpret_cast<float*>(sm + EncSmem::os);
-  __nv_bfloat16* w1h = reinterpret_cast<__nv_bfloat16*>(sm + EncSmem::w1h);
-  __nv_bfloat16* w1l = reinterpret_cast<__nv_bfloat16*>(sm + EncSmem::w1l);
+  h16* w1h = reinterpret_cast<h16*>(sm + EncSmem::w1h);
+  h16* w1l = reinterpret_cast<h16*>(sm + EncSmem::w1l);
   float* aff = reinterpret_cast<float*>(sm + EncSmem::aff);
   int* cells = reinterpret_cast<int*>(sm + EncSmem::cells);
   float* pmax = reinterpret_cast<float*>(sm + EncSmem::pmax);
@@ -484,9 +480,9 @@ __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
   for (int i = tid; i < H * F; i += kRows) {                                      // w1 is [64 n][16 k]
     const float v = __ldg(w1 + i);
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const h16 hi = float2h16(v);
     w1h[(i / F) * kW1Pitch + i % F] = hi;
-    w1l[(i / F) * kW1Pitch + i % F] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    w1l[(i / F) * kW1Pitch + i % F] = float2h16(v - h162float(hi));
   }
   for (int i = tid; i < H; i += kRows) { aff[i] = __ldg(s1 + i); aff[H + i] = __ldg(t1 + i); aff[2 * H + i] = __ldg(s2 + i); aff[3 * H + i] = __ldg(t2 + i); }
   // layer-2 weight fragments (B operand, "col" layout = rows of w2 [64 n][64 k]): b0 (k = 16kk + 2tq.., n = 8nn + gq), b1 (k + 8)
@@ -497,8 +493,8 @@ __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
     for (int nn = 0; nn < 8; ++nn) {
       const float* wp = w2 + (nn * 8 + gq) * H + kk * 16 + tq * 2;
       const float2 lo = __ldg(reinterpret_cast<const float2*>(wp)), hi = __ldg(reinterpret_cast<const float2*>(wp + 8));
-      bfrag[kk][nn][0] = pack_bf16(lo.x, lo.y);
-      bfrag[kk][nn][1] = pack_bf16(hi.x, hi.y);
+      bfrag[kk][nn][0] = pack_h16(lo.x, lo.y);
+      bfrag[kk][nn][1] = pack_h16(hi.x, hi.y);
     }
   __syncthreads();
   int it = 0;               // batch counter: parity of the quarter tables
@@ -542,25 +538,25 @@ __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
         uint32_t a2[4][4];        // layer-2 A fragments (bf16 h), one k16 step per pair of layer-1 n-tiles
 #pragma unroll
         for (int nn = 0; nn < 8; ++nn) {
-          const __nv_bfloat16* wh = w1h + (nn * 8 + gq) * kW1Pitch + 2 * tq;
-          const __nv_bfloat16* wl = w1l + (nn * 8 + gq) * kW1Pitch + 2 * tq;
+          const h16* wh = w1h + (nn * 8 + gq) * kW1Pitch + 2 * tq;
+          const h16* wl = w1l + (nn * 8 + gq) * kW1Pitch + 2 * tq;
           const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(wh), bh1 = *reinterpret_cast<const uint32_t*>(wh + 8);
           const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(wl), bl1 = *reinterpret_cast<const uint32_t*>(wl + 8);
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          mma_bf16_16816(acc, al[0], al[1], al[2], al[3], bh0, bh1);       // small terms first
-          mma_bf16_16816(acc, ah[0], ah[1], ah[2], ah[3], bl0, bl1);
-          mma_bf16_16816(acc, ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+          mma_h16_16816(acc, al[0], al[1], al[2], al[3], bh0, bh1);       // small terms first
+          mma_h16_16816(acc, ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+          mma_h16_16816(acc, ah[0], ah[1], ah[2], ah[3], bh0, bh1);
           const int col = nn * 8 + 2 * tq;
           const float2 sc = *reinterpret_cast<const float2*>(&aff[col]), sh = *reinterpret_cast<const float2*>(&aff[H + col]);
           const float sc0 = sc.x, sc1 = sc.y, sh0 = sh.x, sh1 = sh.y;
-          a2[nn >> 1][(nn & 1) * 2] = pack_bf16(fmaxf(fmaf(acc[0], sc0, sh0), 0.f), fmaxf(fmaf(acc[1], sc1, sh1), 0.f));       // row gq
-          a2[nn >> 1][(nn & 1) * 2 + 1] = pack_bf16(fmaxf(fmaf(acc[2], sc0, sh0), 0.f), fmaxf(fmaf(acc[3], sc1, sh1), 0.f));   // row gq + 8
+          a2[nn >> 1][(nn & 1) * 2] = pack_h16(fmaxf(fmaf(acc[0], sc0, sh0), 0.f), fmaxf(fmaf(acc[1], sc1, sh1), 0.f));       // row gq
+          a2[nn >> 1][(nn & 1) * 2 + 1] = pack_h16(fmaxf(fmaf(acc[2], sc0, sh0), 0.f), fmaxf(fmaf(acc[3], sc1, sh1), 0.f));   // row gq + 8
         }
 #pragma unroll
         for (int nn = 0; nn < 8; ++nn) {
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) mma_bf16_16816(acc, a2[kk][0], a2[kk][1], a2[kk][2], a2[kk][3], bfrag[kk][nn][0], bfrag[kk][nn][1]);
+          for (int kk = 0; kk < 4; ++kk) mma_h16_16816(acc, a2[kk][0], a2[kk][1], a2[kk][2], a2[kk][3], bfrag[kk][nn][0], bfrag[kk][nn][1]);
           const int col = nn * 8 + 2 * tq;
           const float2 sc = *reinterpret_cast<const float2*>(&aff[2 * H + col]), sh = *reinterpret_cast<const float2*>(&aff[3 * H + col]);
           const float sc0 = sc.x, sc1 = sc.y, sh0 = sh.x, sh1 = sh.y;
@@ -643,6 +639,341 @@ static SortedWs carve_sorted(void* base, int batch, int nx, int ny, long long to
   w.ocell = reinterpret_cast<int*>(take((size_t)total_pts * 4));
   w.bytes = (size_t)(p - reinterpret_cast<char*>(base));
   return w;
+}
+
+
+// =====================================================================================================================
+// Tile-binned pillar encoder (the 16-bit pipeline's encoder): the canvas is cut into tiles of kTileR x kTileC cells and
+// every tile is produced start to finish by one CTA, in shared memory:
+//   K1 tile_count   : per point -> canvas tile id; per-block shared-memory histogram -> one global atomic per (block, tile)
+//   K2 tile_scatter : every block re-derives its frame's exclusive tile offsets from the counts (800 entries: cheaper than a
+//                     launch), ranks its points inside the block through shared-memory atomics, reserves one range per
+//                     (block, tile) and writes the in-window points as 48-byte records [pt(11) | packed local cell] in tile
+//                     order — out-of-window points stop here
+//   K3 tile_encode  : CTA = one tile at a time (static interleave over the grid): per-pillar centroid sums in shared memory
+//                     (pass A over the tile's records), then decorate + layer 1 (hi/lo-split MMAs ~ fp32) + layer 2 (h16 MMAs)
+//                     exactly as the sorted kernel did, and the max-pool as shared-memory atomicMax on the fp32 tile
+//                     (post-ReLU values are >= +0: int max on the bit pattern, zero = identity = empty cell); the finished
+//                     tile — zeros included — leaves as full 256-byte cell rows, kTileC cells (4 KB) contiguous.
+// No per-cell global arrays (stats / count / offsets / cursor), no canvas memset or zero-fill pass, no index indirection:
+// global traffic = points read twice (K1 touches x,y), records written + read once, canvas written once.
+// =====================================================================================================================
+constexpr int kTileR = 8, kTileC = 16, kTileCells = kTileR * kTileC;     // 128 cells: a 2 m x 4 m patch at 4 px/m
+constexpr int kRecF = 12;                                                // floats per binned record (48 B)
+constexpr int kBinPts = 2048;                                            // points per block in K1 / K2
+constexpr int kMaxTiles = 2048;                                          // tiles per frame the shared-memory histograms cover
+
+struct TileGrid { int tiles_r, tiles_c, tiles; };
+
+// canvas row / col BEFORE the clamp of scatter_points: row in [-1, ny-1], col in [0, nx] (index == n can occur by rounding)
+__device__ __forceinline__ void raw_row_col(const Grid& g, int xi, int yi, int& row, int& col) { row = g.ny - 1 - xi; col = yi; }
+
+__device__ __forceinline__ int tile_of(const Grid& g, const TileGrid& tg, int xi, int yi, int& packed) {
+  int row, col;
+  raw_row_col(g, xi, yi, row, col);
+  const int crow = row < 0 ? 0 : row, ccol = col > g.nx - 1 ? g.nx - 1 : col;
+  const int tr = crow / kTileR, tc = ccol / kTileC;
+  // local pillar slot: (row - r0 + 1) in [0, kTileR], (col - c0) in [0, kTileC] — the overflow row/col keeps its own centroid
+  packed = ((row - tr * kTileR + 1) << 8) | (col - tc * kTileC);
+  return tr * tg.tiles_c + tc;
+}
+
+__global__ void __launch_bounds__(256) tile_count_kernel(const float* __restrict__ pts, int pt_stride,
+                                                         const __grid_constant__ Clouds clouds, const __grid_constant__ Grid g,
+                                                         const __grid_constant__ TileGrid tg, int* __restrict__ tile_count) {
+  __shared__ int hist[kMaxTiles];
+  const int b = blockIdx.y;
+  const int n = clouds.cum[b + 1] - clouds.cum[b];
+  const int i0 = blockIdx.x * kBinPts;
+  if (i0 >= n) return;
+  for (int t = threadIdx.x; t < tg.tiles; t += 256) hist[t] = 0;
+  __syncthreads();
+  const float* base = pts + clouds.start[b] * pt_stride;
+  for (int i = i0 + threadIdx.x; i < min(n, i0 + kBinPts); i += 256) {
+    const float* p = base + (size_t)i * pt_stride;
+    int xi, yi, packed;
+    if (!locate(g, __ldg(p), __ldg(p + 1), xi, yi)) continue;
+    atomicAdd(&hist[tile_of(g, tg, xi, yi, packed)], 1);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < tg.tiles; t += 256)
+    if (hist[t]) atomicAdd(&tile_count[b * tg.tiles + t], hist[t]);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) tile_scatter_kernel(const float* __restrict__ pts, int pt_stride,
+                                                           const __grid_constant__ Clouds clouds, const __grid_constant__ Grid g,
+                                                           const __grid_constant__ TileGrid tg, const int* __restrict__ tile_count,
+                                                           int* __restrict__ tile_cursor, int* __restrict__ tile_off,
+                                                           float4* __restrict__ recs) {
+  __shared__ int off[kMaxTiles];      // exclusive offsets of this frame's tiles (relative to the frame's first record)
+  __shared__ int hist[kMaxTiles];     // per-block count -> then the block's base slot per tile
+  __shared__ int wsum[8];
+  const int b = blockIdx.y;
+  const int n = clouds.cum[b + 1] - clouds.cum[b];
+  const int i0 = blockIdx.x * kBinPts;
+  if (i0 >= n && blockIdx.x != 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // block-wide exclusive scan of the frame's tile counts, 256 entries per round
+  int carry = 0;
+  for (int t0 = 0; t0 < tg.tiles; t0 += 256) {
+    const int t = t0 + threadIdx.x;
+    const int c = t < tg.tiles ? __ldg(tile_count + b * tg.tiles + t) : 0;
+    int x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const int v = wsum[w]; if (w < warp) woff += v; tot += v; }
+    if (t < tg.tiles) { off[t] = carry + woff + x - c; hist[t] = 0; }
+    carry += tot;
+    __syncthreads();
+  }
+  if (blockIdx.x == 0) {   // one block per frame publishes the offsets for the encode kernel
+    for (int t = threadIdx.x; t < tg.tiles; t += 256) tile_off[b * tg.tiles + t] = off[t];
+    if (threadIdx.x == 0) tile_off[clouds.batch * tg.tiles + b] = carry;      // records of frame b (tail of the table)
+  }
+  if (i0 >= n) return;
+  // rank inside the block
+  const float* base = pts + clouds.start[b] * pt_stride;
+  int my_tile[kBinPts / 256], my_rank[kBinPts / 256], my_packed[kBinPts / 256];
+#pragma unroll
+  for (int k = 0; k < kBinPts / 256; ++k) {
+    const int i = i0 + k * 256 + threadIdx.x;
+    my_tile[k] = -1;
+    if (i < n) {
+      const float* p = base + (size_t)i * pt_stride;
+      int xi, yi;
+      if (locate(g, __ldg(p), __ldg(p + 1), xi, yi)) {
+        my_tile[k] = tile_of(g, tg, xi, yi, my_packed[k]);
+        my_rank[k] = atomicAdd(&hist[my_tile[k]], 1);
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < tg.tiles; t += 256) {
+    const int c = hist[t];
+    if (c) hist[t] = clouds.cum[b] + off[t] + atomicAdd(&tile_cursor[b * tg.tiles + t], c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kBinPts / 256; ++k) {
+    if (my_tile[k] < 0) continue;
+    const int i = i0 + k * 256 + threadIdx.x;
+    const float* p = base + (size_t)i * pt_stride;
+    float f[kRecF];
+#pragma unroll
+    for (int e = 0; e < D; ++e) f[e] = __ldg(p + e);
+#pragma unroll
+    for (int e = D; e < kRecF - 1; ++e) f[e] = 0.f;
+    f[kRecF - 1] = __int_as_float(my_packed[k]);
+    float4* r = recs + (size_t)(hist[my_tile[k]] + my_rank[k]) * (kRecF / 4);
+    r[0] = make_float4(f[0], f[1], f[2], f[3]);
+    r[1] = make_float4(f[4], f[5], f[6], f[7]);
+    r[2] = make_float4(f[8], f[9], f[10], f[11]);
+  }
+}
+
+struct TileSmem {                     // shared-memory plan of pillar_tile_encode_kernel (bytes from the base)
+  static constexpr int tile = 0;                                             // [128 cells][64] fp32, XOR-swizzled columns
+  static constexpr int stats = tile + kTileCells * 64 * 4;                   // [(kTileR+1)*(kTileC+1)] float4 (sum x,y,z,n)
+  static constexpr int fs = stats + (kTileR + 1) * (kTileC + 1) * 16;        // [128][kFsPitch] fp32 decorated features
+  static constexpr int w1h = fs + kRows * kFsPitch * 4;                      // [64][kW1Pitch] h16 (hi)
+  static constexpr int w1l = w1h + 64 * kW1Pitch * 2;                        // (lo)
+  static constexpr int aff = w1l + 64 * kW1Pitch * 2;                        // s1 | t1 | s2 | t2
+  static constexpr int cells = aff + 4 * 64 * 4;                             // [128] int: clamped local cell of each row (-1 = none)
+  static constexpr int total = cells + kRows * 4;
+};
+
+// column swizzle of the fp32 tile: one ATOMS instruction of the MMA epilogue touches 8 rows (cells) x 4 column pairs with the
+// same column parity; XOR-ing bits 3-4 and bit 0 of the column with 3 bits of the cell index spreads 8 distinct cell classes
+// over all 32 banks.
+__device__ __forceinline__ int tile_swz(int cell) { return ((cell & 3) << 3) | ((cell >> 2) & 1); }
+
+template <int D, bool kSplitOut>
+__global__ void __launch_bounds__(kRows, 3) pillar_tile_encode_kernel(
+    const float4* __restrict__ recs, const __grid_constant__ Clouds clouds, const __grid_constant__ Grid g,
+    const __grid_constant__ TileGrid tg, const int* __restrict__ tile_count, const int* __restrict__ tile_off,
+    const float* __restrict__ w1, const float* __restrict__ s1, const float* __restrict__ t1, const float* __restrict__ w2,
+    const float* __restrict__ s2, const float* __restrict__ t2, void* __restrict__ canvas) {
+  constexpr int F = D + 5, H = 64;
+  static_assert(F == 16, "layer 1 is one k16 MMA step");
+  extern __shared__ __align__(128) uint8_t sm[];
+  float* tile = reinterpret_cast<float*>(sm + TileSmem::tile);
+  float* stats = reinterpret_cast<float*>(sm + TileSmem::stats);
+  float* fs = reinterpret_cast<float*>(sm + TileSmem::fs);
+  h16* w1h = reinterpret_cast<h16*>(sm + TileSmem::w1h);
+  h16* w1l = reinterpret_cast<h16*>(sm + TileSmem::w1l);
+  float* aff = reinterpret_cast<float*>(sm + TileSmem::aff);
+  int* cells = reinterpret_cast<int*>(sm + TileSmem::cells);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
+  for (int i = tid; i < H * F; i += kRows) {                                      // w1 is [64 n][16 k]
+    const float v = __ldg(w1 + i);
+    const h16 hi = float2h16(v);
+    w1h[(i / F) * kW1Pitch + i % F] = hi;
+    w1l[(i / F) * kW1Pitch + i % F] = float2h16(v - h162float(hi));
+  }
+  for (int i = tid; i < H; i += kRows) { aff[i] = __ldg(s1 + i); aff[H + i] = __ldg(t1 + i); aff[2 * H + i] = __ldg(s2 + i); aff[3 * H + i] = __ldg(t2 + i); }
+  uint32_t bfrag[4][8][2];       // layer-2 weight fragments (B operand "col" = rows of w2 [64 n][64 k])
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+    for (int nn = 0; nn < 8; ++nn) {
+      const float* wp = w2 + (nn * 8 + gq) * H + kk * 16 + tq * 2;
+      const float2 lo = __ldg(reinterpret_cast<const float2*>(wp)), hi = __ldg(reinterpret_cast<const float2*>(wp + 8));
+      bfrag[kk][nn][0] = pack_h16(lo.x, lo.y);
+      bfrag[kk][nn][1] = pack_h16(hi.x, hi.y);
+    }
+  const int total_tiles = clouds.batch * tg.tiles;
+  constexpr int kRowBytes = 256;                                                  // fp32 [64] or h16 [hi 64 | lo 64]
+  for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+    const int b = work / tg.tiles, t = work - b * tg.tiles;
+    const int tr = t / tg.tiles_c, tc = t - tr * tg.tiles_c;
+    const int r0 = tr * kTileR, c0 = tc * kTileC;
+    const int n_t = __ldg(tile_count + work);
+    uint8_t* cbase = reinterpret_cast<uint8_t*>(canvas) + ((size_t)b * g.ny * g.nx) * kRowBytes;
+    if (n_t == 0) {    // empty tile: zeros straight to the canvas (16 B per lane, a half-warp = one cell row)
+      for (int e = tid; e < kTileCells * 16; e += kRows) {
+        const int cell = e >> 4, lr = cell / kTileC, lc = cell - lr * kTileC;
+        if (r0 + lr < g.ny && c0 + lc < g.nx)
+          __stcs(reinterpret_cast<uint4*>(cbase + ((size_t)(r0 + lr) * g.nx + c0 + lc) * kRowBytes) + (e & 15), make_uint4(0u, 0u, 0u, 0u));
+      }
+      continue;
+    }
+    __syncthreads();                               // previous tile's write-out has finished reading `tile`
+    for (int e = tid; e < kTileCells * 16; e += kRows) reinterpret_cast<float4*>(tile)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = tid; e < (kTileR + 1) * (kTileC + 1); e += kRows) reinterpret_cast<float4*>(stats)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const float4* rec = recs + ((size_t)clouds.cum[b] + __ldg(tile_off + work)) * (kRecF / 4);
+    // ---- pass A: per-pillar centroid sums
+    for (int i = tid; i < n_t; i += kRows) {
+      const float4 p0 = __ldg(rec + (size_t)i * 3);
+      const int packed = __float_as_int(__ldg(reinterpret_cast<const float*>(rec + (size_t)i * 3 + 2) + 3));
+      float* st = stats + ((packed >> 8) * (kTileC + 1) + (packed & 255)) * 4;
+      atomicAdd(st, p0.x); atomicAdd(st + 1, p0.y); atomicAdd(st + 2, p0.z); atomicAdd(st + 3, 1.f);
+    }
+    __syncthreads();
+    // ---- pass B: decorate + MLP + max-pool, 128 rows per round, warp w owns rows [32w, 32w+32) end to end
+    for (int base = 0; base < n_t; base += kRows) {
+      {
+        float f[F];
+#pragma unroll
+        for (int k = 0; k < F; ++k) f[k] = 0.f;
+        int cell = -1;
+        const int i = base + tid;
+        if (i < n_t) {
+          const float4 p0 = __ldg(rec + (size_t)i * 3), p1 = __ldg(rec + (size_t)i * 3 + 1), p2 = __ldg(rec + (size_t)i * 3 + 2);
+          const int packed = __float_as_int(p2.w);
+          const int lr1 = packed >> 8, lc = packed & 255;
+          const float4 st = *reinterpret_cast<const float4*>(stats + (lr1 * (kTileC + 1) + lc) * 4);
+          // un-clamped pillar indices back from the local slot: row = r0 + lr1 - 1, xi = ny - 1 - row; yi = c0 + lc
+          const int xi = g.ny - 1 - (r0 + lr1 - 1), yi = c0 + lc;
+          f[0] = p0.x; f[1] = p0.y; f[2] = p0.z; f[3] = p0.w; f[4] = p1.x; f[5] = p1.y; f[6] = p1.z; f[7] = p1.w;
+          f[8] = p2.x; f[9] = p2.y; f[10] = p2.z;
+          f[D + 0] = __fsub_rn(f[0], __fdiv_rn(st.x, st.w));
+          f[D + 1] = __fsub_rn(f[1], __fdiv_rn(st.y, st.w));
+          f[D + 2] = __fsub_rn(f[2], __fdiv_rn(st.z, st.w));
+          f[D + 3] = __fsub_rn(f[0], __fadd_rn(__fdiv_rn((float)yi, g.ppm), g.min_x));
+          f[D + 4] = __fsub_rn(f[1], __fadd_rn(__fdiv_rn((float)xi, g.ppm), g.min_y));
+          const int lr = lr1 > 0 ? lr1 - 1 : 0, lcc = lc < kTileC ? lc : kTileC - 1;
+          cell = lr * kTileC + (c0 + lcc > g.nx - 1 ? g.nx - 1 - c0 : lcc);
+        }
+        cells[tid] = cell;
+#pragma unroll
+        for (int k = 0; k < F; k += 4) *reinterpret_cast<float4*>(&fs[tid * kFsPitch + k]) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const int row0 = warp * 32 + mt * 16;
+        if (base + row0 >= n_t) break;                                   // whole m-tile past the end (warp-uniform)
+        uint32_t ah[4], al[4];
+        split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq) * kFsPitch + 2 * tq]), ah[0], al[0]);
+        split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq + 8) * kFsPitch + 2 * tq]), ah[1], al[1]);
+        split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq) * kFsPitch + 2 * tq + 8]), ah[2], al[2]);
+        split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq + 8) * kFsPitch + 2 * tq + 8]), ah[3], al[3]);
+        uint32_t a2[4][4];
+#pragma unroll
+        for (int nn = 0; nn < 8; ++nn) {
+          const h16* wh = w1h + (nn * 8 + gq) * kW1Pitch + 2 * tq;
+          const h16* wl = w1l + (nn * 8 + gq) * kW1Pitch + 2 * tq;
+          const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(wh), bh1 = *reinterpret_cast<const uint32_t*>(wh + 8);
+          const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(wl), bl1 = *reinterpret_cast<const uint32_t*>(wl + 8);
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_h16_16816(acc, al[0], al[1], al[2], al[3], bh0, bh1);       // small terms first
+          mma_h16_16816(acc, ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+          mma_h16_16816(acc, ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+          const int col = nn * 8 + 2 * tq;
+          const float2 sc = *reinterpret_cast<const float2*>(&aff[col]), sh = *reinterpret_cast<const float2*>(&aff[H + col]);
+          a2[nn >> 1][(nn & 1) * 2] = pack_h16(fmaxf(fmaf(acc[0], sc.x, sh.x), 0.f), fmaxf(fmaf(acc[1], sc.y, sh.y), 0.f));
+          a2[nn >> 1][(nn & 1) * 2 + 1] = pack_h16(fmaxf(fmaf(acc[2], sc.x, sh.x), 0.f), fmaxf(fmaf(acc[3], sc.y, sh.y), 0.f));
+        }
+        const int cell_a = cells[row0 + gq], cell_b = cells[row0 + gq + 8];
+        int* ta = reinterpret_cast<int*>(tile) + cell_a * 64;
+        int* tb = reinterpret_cast<int*>(tile) + cell_b * 64;
+        const int sa = tile_swz(cell_a), sb = tile_swz(cell_b);
+#pragma unroll
+        for (int nn = 0; nn < 8; ++nn) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) mma_h16_16816(acc, a2[kk][0], a2[kk][1], a2[kk][2], a2[kk][3], bfrag[kk][nn][0], bfrag[kk][nn][1]);
+          const int col = nn * 8 + 2 * tq;
+          const float2 sc = *reinterpret_cast<const float2*>(&aff[2 * H + col]), sh = *reinterpret_cast<const float2*>(&aff[3 * H + col]);
+          const float v0 = fmaf(acc[0], sc.x, sh.x), v1 = fmaf(acc[1], sc.y, sh.y);
+          const float v2 = fmaf(acc[2], sc.x, sh.x), v3 = fmaf(acc[3], sc.y, sh.y);
+          if (cell_a >= 0) {
+            if (v0 > 0.f) atomicMax(ta + (col ^ sa), __float_as_int(v0));
+            if (v1 > 0.f) atomicMax(ta + ((col + 1) ^ sa), __float_as_int(v1));
+          }
+          if (cell_b >= 0) {
+            if (v2 > 0.f) atomicMax(tb + (col ^ sb), __float_as_int(v2));
+            if (v3 > 0.f) atomicMax(tb + ((col + 1) ^ sb), __float_as_int(v3));
+          }
+        }
+      }
+      __syncwarp();                                  // the warp's fs / cells rows are rewritten by the next round
+    }
+    __syncthreads();
+    // ---- write-out: a half-warp emits one cell row (16 lanes x 4 channels), zeros included
+    for (int e = tid; e < kTileCells * 16; e += kRows) {
+      const int cell = e >> 4, q = e & 15, lr = cell / kTileC, lc = cell - lr * kTileC;
+      if (r0 + lr >= g.ny || c0 + lc >= g.nx) continue;
+      const int sw = tile_swz(cell);
+      // logical channels 4q..4q+3 live at physical (4q ^ (sw & ~1)) with the pair elements swapped when sw & 1
+      const float4 v = *reinterpret_cast<const float4*>(tile + cell * 64 + ((4 * q) ^ (sw & ~1)));
+      const float m0 = (sw & 1) ? v.y : v.x, m1 = (sw & 1) ? v.x : v.y, m2 = (sw & 1) ? v.w : v.z, m3 = (sw & 1) ? v.z : v.w;
+      uint8_t* row = cbase + ((size_t)(r0 + lr) * g.nx + c0 + lc) * kRowBytes;
+      if (kSplitOut) {
+        const uint32_t h0 = pack_h16(m0, m1), h1 = pack_h16(m2, m3);
+        const float2 f0 = unpack_h16(h0), f1 = unpack_h16(h1);
+        __stcs(reinterpret_cast<uint2*>(row) + q, make_uint2(h0, h1));
+        __stcs(reinterpret_cast<uint2*>(row + 128) + q, make_uint2(pack_h16(m0 - f0.x, m1 - f0.y), pack_h16(m2 - f1.x, m3 - f1.y)));
+      } else {
+        __stcs(reinterpret_cast<float4*>(row) + q, make_float4(m0, m1, m2, m3));
+      }
+    }
+  }
+}
+
+struct TiledWs { int* tile_count; int* tile_cursor; int* tile_off; float4* recs; size_t bytes; };
+static TiledWs carve_tiled(void* base, int batch, int tiles, long long total_pts) {
+  TiledWs w;
+  char* p = reinterpret_cast<char*>(base);
+  auto take = [&](size_t n) { char* r = p; p += (n + 255) / 256 * 256; return r; };
+  w.tile_count = reinterpret_cast<int*>(take((size_t)batch * tiles * 4));
+  w.tile_cursor = reinterpret_cast<int*>(take((size_t)batch * tiles * 4));      // adjacent to tile_count: one memset
+  w.tile_off = reinterpret_cast<int*>(take(((size_t)batch * tiles + batch) * 4));
+  w.recs = reinterpret_cast<float4*>(take((size_t)total_pts * kRecF * 4));
+  w.bytes = (size_t)(p - reinterpret_cast<char*>(base));
+  return w;
+}
+static TileGrid make_tile_grid(int nx, int ny) {
+  TileGrid tg;
+  tg.tiles_r = ceil_div(ny, kTileR); tg.tiles_c = ceil_div(nx, kTileC); tg.tiles = tg.tiles_r * tg.tiles_c;
+  return tg;
 }
 
 }  // namespace lavb
@@ -780,12 +1111,8 @@ extern "C" int lavb_pillar_forward_sorted(const float* d_pts, int pt_stride, int
                                                                              w.order, w.ocell);
   LAVB_LAUNCH_OK();
   const size_t smem = EncSmem::total;
-  static bool configured = false;
-  if (!configured) {
-    LAVB_CUDA_OK(cudaFuncSetAttribute(pillar_encode_sorted_kernel<11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    LAVB_CUDA_OK(cudaFuncSetAttribute(pillar_encode_sorted_kernel<11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    configured = true;
-  }
+  LAVB_CUDA_OK(ensure_dyn_smem((const void*)pillar_encode_sorted_kernel<11, false>, 72 * 1024));
+  LAVB_CUDA_OK(ensure_dyn_smem((const void*)pillar_encode_sorted_kernel<11, true>, 72 * 1024));
   const int ntiles = min(ceil_div(total, kRows), kNumSMs * 3);     // persistent: 3 resident blocks per SM
   if (out_mode == 0)
     pillar_encode_sorted_kernel<11, false><<<ntiles, kRows, smem, st>>>(d_pts, pt_stride, clouds, g, w.stats, w.order, w.ocell,
@@ -793,6 +1120,52 @@ extern "C" int lavb_pillar_forward_sorted(const float* d_pts, int pt_stride, int
   else
     pillar_encode_sorted_kernel<11, true><<<ntiles, kRows, smem, st>>>(d_pts, pt_stride, clouds, g, w.stats, w.order, w.ocell,
                                                                        w.tile_start, w.total, d_w1, d_s1, d_t1, d_w2, d_s2, d_t2, d_canvas);
+  LAVB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" size_t lavb_pillar_tiled_workspace_bytes(int batch, int nx, int ny, long long total_points) {
+  return carve_tiled(nullptr, batch, make_tile_grid(nx, ny).tiles, total_points).bytes;
+}
+
+extern "C" int lavb_pillar_forward_tiled(const float* d_pts, int pt_stride, int d, const long long* h_cloud_start,
+                                         const int* h_cloud_count, int batch, float min_x, float max_x, float min_y,
+                                         float max_y, float ppm, int nx, int ny, const float* d_w1, const float* d_s1,
+                                         const float* d_t1, int h1, const float* d_w2, const float* d_s2, const float* d_t2,
+                                         int h2, void* d_canvas, int out_mode, void* d_workspace, void* stream) {
+  Clouds clouds;
+  if (fill_clouds(clouds, h_cloud_start, h_cloud_count, batch)) return 1;
+  LAVB_CHECK_ARG(d == 11 && h1 == 64 && h2 == 64, "pillar_forward_tiled: only the v2 configuration (D=11, features [64,64]) is built");
+  LAVB_CHECK_ARG(out_mode == 0 || out_mode == 1, "pillar_forward_tiled: out_mode 0 (fp32) or 1 (h16 hi|lo split)");
+  LAVB_CHECK_ARG(pt_stride >= d, "pillar_forward_tiled: pt_stride < d");
+  const TileGrid tg = make_tile_grid(nx, ny);
+  LAVB_CHECK_ARG(tg.tiles <= kMaxTiles, "pillar_forward_tiled: grid of %d x %d cells has more than %d tiles", nx, ny, kMaxTiles);
+  LAVB_CHECK_ARG((long long)batch * tg.tiles < (1LL << 31), "pillar_forward_tiled: too many tiles");
+  cudaStream_t st = (cudaStream_t)stream;
+  Grid g{min_x, max_x, min_y, max_y, ppm, nx, ny};
+  const int total = clouds.cum[batch];
+  const TiledWs w = carve_tiled(d_workspace, batch, tg.tiles, total);
+  LAVB_CUDA_OK(cudaMemsetAsync(w.tile_count, 0, (size_t)(reinterpret_cast<char*>(w.tile_off) - reinterpret_cast<char*>(w.tile_count)), st));
+  int max_n = 0;
+  for (int b = 0; b < batch; ++b) max_n = max(max_n, h_cloud_count[b]);
+  if (max_n > 0) {
+    dim3 grid(ceil_div(max_n, kBinPts), batch);
+    tile_count_kernel<<<grid, 256, 0, st>>>(d_pts, pt_stride, clouds, g, tg, w.tile_count);
+    LAVB_LAUNCH_OK();
+    tile_scatter_kernel<11><<<grid, 256, 0, st>>>(d_pts, pt_stride, clouds, g, tg, w.tile_count, w.tile_cursor, w.tile_off, w.recs);
+    LAVB_LAUNCH_OK();
+  } else {
+    LAVB_CUDA_OK(cudaMemsetAsync(w.tile_off, 0, ((size_t)batch * tg.tiles + batch) * 4, st));
+  }
+  LAVB_CUDA_OK(ensure_dyn_smem((const void*)pillar_tile_encode_kernel<11, false>, TileSmem::total));
+  LAVB_CUDA_OK(ensure_dyn_smem((const void*)pillar_tile_encode_kernel<11, true>, TileSmem::total));
+  const int grid4 = min(batch * tg.tiles, kNumSMs * 3);              // persistent: 3 resident CTAs per SM
+  if (out_mode == 0)
+    pillar_tile_encode_kernel<11, false><<<grid4, kRows, TileSmem::total, st>>>(w.recs, clouds, g, tg, w.tile_count, w.tile_off, d_w1, d_s1,
+                                                                               d_t1, d_w2, d_s2, d_t2, d_canvas);
+  else
+    pillar_tile_encode_kernel<11, true><<<grid4, kRows, TileSmem::total, st>>>(w.recs, clouds, g, tg, w.tile_count, w.tile_off, d_w1, d_s1,
+                                                                              d_t1, d_w2, d_s2, d_t2, d_canvas);
   LAVB_LAUNCH_OK();
   return 0;
 }

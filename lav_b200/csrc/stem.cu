@@ -25,21 +25,21 @@ constexpr int kStemSmem = (64 * kStemPitch + kStemInRows * kStemQW + 4 * 32 * kS
 
 struct StemArgs {
   const unsigned char* img; int batch, ncam, h, cam_w;     // logical image: h x (ncam*cam_w) x 3
-  const __nv_bfloat16* w; const float* bias;               // w [64][160], k = ky*22 + kx*3 + c
+  const h16* w; const float* bias;               // w [64][160], k = ky*22 + kx*3 + c
   float na[3], nb[3];                                       // normalised = u8 * na[c] + nb[c]
-  __nv_bfloat16* out; int ho, wo;                           // NHWC (batch, ho, wo, 64)
+  h16* out; int ho, wo;                           // NHWC (batch, ho, wo, 64)
 };
 
-__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+__device__ __forceinline__ void mma_h16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." LAVB_H16_PTX "." LAVB_H16_PTX ".f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 __global__ void __launch_bounds__(128) stem7x7_u8_kernel(const __grid_constant__ StemArgs a) {
   extern __shared__ __align__(16) uint8_t stem_sm[];
-  __nv_bfloat16* ws = reinterpret_cast<__nv_bfloat16*>(stem_sm);              // [64][kStemPitch]
-  __nv_bfloat16* S = ws + 64 * kStemPitch;                                    // [kStemInRows][kStemQW]
-  __nv_bfloat16* Ot = S + kStemInRows * kStemQW;                              // [4 warps][32 px][kStemOutPitch]
+  h16* ws = reinterpret_cast<h16*>(stem_sm);              // [64][kStemPitch]
+  h16* S = ws + 64 * kStemPitch;                                    // [kStemInRows][kStemQW]
+  h16* Ot = S + kStemInRows * kStemQW;                              // [4 warps][32 px][kStemOutPitch]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
   const int groups = (a.ho + kStemRows - 1) / kStemRows;
   const int b = blockIdx.x / groups, oy0 = (blockIdx.x - b * groups) * kStemRows;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) stem7x7_u8_kernel(const __grid_constant__
         if (q >= 0 && q < kStemQW) {
           const float u = (float)((word >> (8 * j)) & 0xffu);
           const float nrm = c == 0 ? fmaf(u, a.na[0], a.nb[0]) : (c == 1 ? fmaf(u, a.na[1], a.nb[1]) : fmaf(u, a.na[2], a.nb[2]));
-          S[r * kStemQW + q] = __float2bfloat16_rn(ok ? nrm : 0.f);
+          S[r * kStemQW + q] = float2h16(ok ? nrm : 0.f);
         }
         c = c == 2 ? 0 : c + 1;
       }
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128) stem7x7_u8_kernel(const __grid_constant__
     }
   const int pxw = warp * 32;                                // the warp's first pixel inside the block's 128 columns
   if (ox0 + pxw >= a.wo) return;
-  __nv_bfloat16* ot = Ot + warp * 32 * kStemOutPitch;
+  h16* ot = Ot + warp * 32 * kStemOutPitch;
   float bias2[8][2];
 #pragma unroll
   for (int nn = 0; nn < 8; ++nn) { bias2[nn][0] = __ldg(a.bias + nn * 8 + 2 * tq); bias2[nn][1] = __ldg(a.bias + nn * 8 + 2 * tq + 1); }
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128) stem7x7_u8_kernel(const __grid_constant__
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int nn = 0; nn < 8; ++nn) acc[mt][nn][0] = acc[mt][nn][1] = acc[mt][nn][2] = acc[mt][nn][3] = 0.f;
-    const __nv_bfloat16* srow = S + 2 * rr * kStemQW + 6 * (pxw + gq);
+    const h16* srow = S + 2 * rr * kStemQW + 6 * (pxw + gq);
 #pragma unroll
     for (int kk = 0; kk < kStemK / 16; ++kk) {
       uint32_t af[4][2];
@@ -113,10 +113,10 @@ __global__ void __launch_bounds__(128) stem7x7_u8_kernel(const __grid_constant__
         for (int h = 0; h < 2; ++h) af[r][h] = *reinterpret_cast<const uint32_t*>(srow + 48 * r + offs[kk][h]);   // pixel gq + 8r
 #pragma unroll
       for (int nn = 0; nn < 8; ++nn) {
-        const __nv_bfloat16* wp = ws + (nn * 8 + gq) * kStemPitch + kk * 16 + 2 * tq;
+        const h16* wp = ws + (nn * 8 + gq) * kStemPitch + kk * 16 + 2 * tq;
         const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wp), b1 = *reinterpret_cast<const uint32_t*>(wp + 8);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) mma_bf16(acc[mt][nn], af[mt * 2][0], af[mt * 2 + 1][0], af[mt * 2][1], af[mt * 2 + 1][1], b0, b1);
+        for (int mt = 0; mt < 2; ++mt) mma_h16(acc[mt][nn], af[mt * 2][0], af[mt * 2 + 1][0], af[mt * 2][1], af[mt * 2 + 1][1], b0, b1);
       }
     }
     // bias + ReLU -> bf16 into the warp's staging tile (C fragment: rows gq | gq+8 of each m-tile, cols 8nn + 2tq, +1)
@@ -126,10 +126,10 @@ __global__ void __launch_bounds__(128) stem7x7_u8_kernel(const __grid_constant__
 #pragma unroll
       for (int nn = 0; nn < 8; ++nn) {
         const float x0 = fmaxf(acc[r >> 1][nn][(r & 1) * 2] + bias2[nn][0], 0.f), x1 = fmaxf(acc[r >> 1][nn][(r & 1) * 2 + 1] + bias2[nn][1], 0.f);
-        store2<__nv_bfloat16>(ot + ((r >> 1) * 16 + (r & 1) * 8 + gq) * kStemOutPitch + nn * 8 + 2 * tq, x0, x1);
+        store2<h16>(ot + ((r >> 1) * 16 + (r & 1) * 8 + gq) * kStemOutPitch + nn * 8 + 2 * tq, x0, x1);
       }
     __syncwarp();
-    __nv_bfloat16* orow = a.out + (((long long)b * a.ho + oy) * a.wo + ox0 + pxw) * 64;
+    h16* orow = a.out + (((long long)b * a.ho + oy) * a.wo + ox0 + pxw) * 64;
     const int npx = min(32, a.wo - ox0 - pxw);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(128) stem7x7_u8_kernel(const __grid_constant__
 }
 
 // 3x3 stride-2 pad-1 max-pool on NHWC bf16 (lav/models/resnet.py:181,238): one thread = one output pixel x 8 channels.
-__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, int n, int h, int w, int c8,
-                                                           __nv_bfloat16* __restrict__ out, int ho, int wo) {
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const h16* __restrict__ in, int n, int h, int w, int c8,
+                                                           h16* __restrict__ out, int ho, int wo) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)n * ho * wo * c8;
   if (gid >= total) return;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
   const int oy = (int)(p % ho);
   const int b = (int)(p / ho);
   const uint4* src = reinterpret_cast<const uint4*>(in) + (long long)b * h * w * c8 + ch;
-  __nv_bfloat162 m[4];
+  h162 m[4];
   bool first = true;
 #pragma unroll
   for (int dy = -1; dy <= 1; ++dy) {
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
       const int ix = 2 * ox + dx;
       if (ix < 0 || ix >= w) continue;
       const uint4 v = __ldg(src + ((long long)iy * w + ix) * c8);
-      const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+      const h162* pv = reinterpret_cast<const h162*>(&v);
       if (first) { m[0] = pv[0]; m[1] = pv[1]; m[2] = pv[2]; m[3] = pv[3]; first = false; }
       else { m[0] = __hmax2(m[0], pv[0]); m[1] = __hmax2(m[1], pv[1]); m[2] = __hmax2(m[2], pv[2]); m[3] = __hmax2(m[3], pv[3]); }
     }
@@ -182,16 +182,12 @@ extern "C" int lavb_stem7x7s2_u8(const void* d_img, int batch, int ncam, int h, 
   LAVB_CHECK_ARG(batch >= 0 && ncam >= 1 && ncam <= 4 && h >= 7 && cam_w >= 8, "stem7x7s2_u8: bad shape");
   LAVB_CHECK_ARG(cam_w % 4 == 0, "stem7x7s2_u8: camera width must be a multiple of 4 (got %d)", cam_w);
   if (batch == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LAVB_CUDA_OK(cudaFuncSetAttribute(stem7x7_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem));
-    attr_set = true;
-  }
+  LAVB_CUDA_OK(ensure_dyn_smem((const void*)stem7x7_u8_kernel, kStemSmem));
   StemArgs a;
   a.img = reinterpret_cast<const unsigned char*>(d_img); a.batch = batch; a.ncam = ncam; a.h = h; a.cam_w = cam_w;
-  a.w = reinterpret_cast<const __nv_bfloat16*>(d_w); a.bias = d_bias;
+  a.w = reinterpret_cast<const h16*>(d_w); a.bias = d_bias;
   for (int c = 0; c < 3; ++c) { a.na[c] = 1.f / (255.f * h_std[c]); a.nb[c] = -h_mean[c] / h_std[c]; }
-  a.out = reinterpret_cast<__nv_bfloat16*>(d_out);
+  a.out = reinterpret_cast<h16*>(d_out);
   a.ho = (h + 6 - 7) / 2 + 1; a.wo = (ncam * cam_w + 6 - 7) / 2 + 1;
   dim3 grid(batch * ceil_div(a.ho, kStemRows), ceil_div(a.wo, 128));
   stem7x7_u8_kernel<<<grid, 128, kStemSmem, (cudaStream_t)stream>>>(a);
@@ -204,8 +200,8 @@ extern "C" int lavb_maxpool3x3s2_nhwc(const void* d_in, int n, int h, int w, int
   if (n == 0) return 0;
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
   const long long total = (long long)n * ho * wo * (c / 8);
-  maxpool3x3s2_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_in), n, h, w, c / 8,
-                                                                              reinterpret_cast<__nv_bfloat16*>(d_out), ho, wo);
+  maxpool3x3s2_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const h16*>(d_in), n, h, w, c / 8,
+                                                                              reinterpret_cast<h16*>(d_out), ho, wo);
   LAVB_LAUNCH_OK();
   return 0;
 }

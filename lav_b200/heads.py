@@ -18,6 +18,8 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
+from . import ops
+
 
 # ----------------------------------------------------------------------------- ResNet-18
 class BasicBlock(nn.Module):
@@ -64,9 +66,22 @@ class ResNet18(nn.Module):
 
     # ---- eval fast path: BatchNorm folded into the conv weights, conv+bias+ReLU and conv+bias+add+ReLU as single cuDNN
     # fused ops (no separate BN / ReLU / add passes over the activations).  Folded weights are cached per (dtype, device).
+    def _fold_sig(self):
+        """identity + in-place version of every tensor the folded weights derive from: optimizer steps, copy_ (any
+        load_state_dict, also a parent's), .to() and re-assignment all change it, so stale folds cannot survive."""
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _cache(self):
+        cache = self.__dict__.setdefault("_fold_cache", {})
+        sig = self._fold_sig()
+        if cache.get("sig") != sig:
+            cache.clear()
+            cache["sig"] = sig
+        return cache
+
     def _folded(self, dtype, device):
         key = (dtype, str(device))
-        cache = self.__dict__.setdefault("_fold_cache", {})
+        cache = self._cache()
         if key not in cache:
             def fold(conv, bn):
                 s = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
@@ -89,18 +104,16 @@ class ResNet18(nn.Module):
         f = self._folded(dt, x.device)
         w, b = f["stem"]
         x = torch.cudnn_convolution_relu(x, w, b, (2, 2), (3, 3), (1, 1), 1)
-        if dt == torch.bfloat16:                        # lav_b200 pool kernel on the channels-last memory (ATen's is ~5x slower)
-            from . import ops
+        if dt == ops.h16():                        # lav_b200 pool kernel on the channels-last memory (ATen's is ~5x slower)
             return self._trunk_folded(ops.maxpool3x3s2_nhwc(x.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2), f)
         return self._trunk_folded(self.maxpool(x), f)
 
     def forward_u8(self, img_u8, mean, std):
         """Eval fast path from raw camera bytes: img_u8 (B, ncam, H, cam_w, 3) uint8 (cameras side by side) -> layer4 map.
         Normalisation + conv1 + bn1 + ReLU run in the lav_b200 tensor-core stem kernel and the max-pool in its companion
-        (csrc/stem.cu): in cuDNN/ATen these two are 64 % of the brake model's GPU time (3 input channels).  bf16 only."""
-        from . import ops
+        (csrc/stem.cu): in cuDNN/ATen these two are 64 % of the brake model's GPU time (3 input channels).  f16 only."""
         dt = self.conv1.weight.dtype
-        assert dt == torch.bfloat16 and self.conv1.in_channels == 3, "forward_u8: bf16 3-channel stem only"
+        assert dt == ops.h16() and self.conv1.in_channels == 3, "forward_u8: f16 3-channel stem only"
         f = self._folded(dt, img_u8.device)
         if "stem_u8" not in f:
             w, b = self._folded(torch.float32, img_u8.device)["stem"]                  # fold in fp32, round once
@@ -111,10 +124,10 @@ class ResNet18(nn.Module):
 
     def _trunk_folded(self, x, f):
         dt = x.dtype
-        if getattr(self, "use_umma_trunk", False) and dt == torch.bfloat16:
+        if getattr(self, "use_umma_trunk", False) and dt == ops.h16():
             # layer1..4 on the lav_b200 tcgen05 conv kernel (BN / residual / ReLU fused in its epilogue)
             key = ("umma", str(x.device))
-            cache = self.__dict__.setdefault("_fold_cache", {})
+            cache = self._cache()
             if key not in cache:
                 from .resnet_umma import ResNetTrunkUMMA
                 cache[key] = ResNetTrunkUMMA(self)
@@ -140,12 +153,16 @@ class ResNet18(nn.Module):
         self.__dict__["_fold_cache"] = {}
         return super().load_state_dict(*a, **k)
 
+    def train(self, mode=True):
+        self.__dict__["_fold_cache"] = {}
+        return super().train(mode)
+
 
 def resnet18(pretrained=False, num_channels=3, **kw):
     return ResNet18(num_channels=num_channels)
 
 
-GRU_KERNEL = False    # experimental cluster-persistent plan GRU (csrc/gru_cluster.cu); off until validated and timed on the GPU
+GRU_KERNEL = True     # cluster-persistent plan GRU (csrc/gru_cluster.cu): validated on B200, roll-out 1.06 -> 0.71 ms @192 sequences
 
 
 # ----------------------------------------------------------------------------- planners
@@ -212,12 +229,11 @@ def _plan_rollout(plan_gru, plan_mlp, num_cmds, num_plan, num_plan_iter, embd, n
         u = torch.cat([u0[:, None, None].expand(B, num_cmds, num_plan, 2), plan_loc], dim=3)
         if GRU_KERNEL and u.is_cuda and not torch.is_grad_enabled() and plan_gru.hidden_size == 512 and plan_gru.input_size == 4:
             # experimental: the whole 20-step roll-out in one cluster-persistent kernel (csrc/gru_cluster.cu)
-            from . import ops
             whh = plan_gru.weight_hh_l0
             key = (whh.data_ptr(), whh._version, str(whh.device))
-            cached = plan_gru.__dict__.get("_whh_bf16")
+            cached = plan_gru.__dict__.get("_whh_h16")
             if cached is None or cached[0] != key:      # re-derive after load_state_dict / .to()
-                cached = plan_gru.__dict__["_whh_bf16"] = (key, whh.detach().to(torch.bfloat16).contiguous())
+                cached = plan_gru.__dict__["_whh_h16"] = (key, whh.detach().to(ops.h16()).contiguous())
             wb = cached[1]
             out = ops.gru_h512(u.reshape(B * num_cmds, num_plan, 4).float(), h0[0].float(), wb, plan_gru.weight_ih_l0.detach().float(),
                                plan_gru.bias_ih_l0.detach().float(), plan_gru.bias_hh_l0.detach().float())
@@ -277,7 +293,6 @@ class UniPlanner(nn.Module):
         B, C, H, W = features.size()
         theta = crop_theta(rel_locs, rel_oris, H, W, pixels_per_meter, crop_size, self.offset_x, self.offset_y)
         if features.is_cuda and not (torch.is_grad_enabled() and features.requires_grad):
-            from . import ops
             feats_nhwc = features.permute(0, 2, 3, 1)
             if feats_nhwc.is_contiguous():
                 if frame_idx is None:
@@ -508,7 +523,7 @@ class RGBBrakePredictionModel(nn.Module):
     def forward_u8(self, rgbs_u8, tel_u8):
         """Same as forward(wide, tel) (team_code_v2/lav_agent_fast.py:257-262,318-321) from the raw camera bytes:
         rgbs_u8 (B, 3, 288, 256, 3) — the three cameras, stitched side by side inside the stem kernel — and tel_u8
-        (B, 192, 480, 3).  bf16 eval only; the mean/std constants are read once (host) and cached."""
+        (B, 192, 480, 3).  f16 eval only; the mean/std constants are read once (host) and cached."""
         ms = self.__dict__.get("_ms")
         if ms is None:
             ms = self.__dict__["_ms"] = (self.normalize.mean.float().tolist(), self.normalize.std.float().tolist())

@@ -11,8 +11,6 @@ from . import ops
 
 USE_UMMA = True   # tests flip this to compare the tcgen05 path with the CUDA-core path
 UMMA_STRIDED = True   # stride-2 convs through the tensor map's element strides
-USE_HALO = False      # experimental halo-patch tcgen05 kernel (csrc/conv_halo_umma.cu) for stride-1 layers with cout <= 128
-USE_EPI16 = False     # experimental: narrow layers (cout <= 128) with 2 CTAs/SM x 8 epilogue warps (csrc/conv_umma16.cu)
 
 
 def bn_affine(bn, eps=None):
@@ -78,14 +76,14 @@ class TapConv:
                                             out_o=(oy, ox)))
         for ph in self.phases:
             assert len(ph["taps"]) <= 16, "tap list longer than the kernel's table"
-        # tcgen05 path (bf16 activations): weights [ntaps][cout][cin] bf16, K contiguous
+        # tcgen05 path (f16 activations): weights [ntaps][cout][cin] f16, K contiguous
         # (cout that is a multiple of 8 but not of 32 is zero-padded to the MMA width; only the real channels are stored)
         self.umma_ok = USE_UMMA and self.cin_k % 64 == 0 and self.cout % 8 == 0 and self.cout <= 256
         if self.umma_ok:
             cm = (self.cout + 31) // 32 * 32
             for ph in self.phases:
-                wu = torch.zeros((len(ph["taps"]), cm, self.cin_k), dtype=torch.bfloat16, device=ph["w"].device)
-                wu[:, :self.cout] = ph["w"][:, :, :self.cout].permute(0, 2, 1).to(torch.bfloat16)
+                wu = torch.zeros((len(ph["taps"]), cm, self.cin_k), dtype=ops.h16(), device=ph["w"].device)
+                wu[:, :self.cout] = ph["w"][:, :, :self.cout].permute(0, 2, 1).to(ops.h16())
                 ph["w_umma"] = wu.contiguous()
 
     def _block(self, w_ci_co):
@@ -112,12 +110,11 @@ class TapConv:
             osy, osx = ph["out_s"]
             ooy, oox = ph["out_o"]
             hog, wog = (hout - ooy + osy - 1) // osy, (wout - oox + osx - 1) // osx
-            umma = (self.umma_ok and x.dtype == torch.bfloat16 and (res is None or (res.dtype == torch.bfloat16 and self.cout % 32 == 0))
+            umma = (self.umma_ok and x.dtype == ops.h16() and (res is None or (res.dtype == ops.h16() and self.cout % 32 == 0))
                     and (UMMA_STRIDED or ph["in_s"] == (1, 1)))
             ops.conv_taps(x, self.cin_k, in_coff, out, self.cout, out_coff, hog, wog, ph["in_s"], ph["out_s"], ph["out_o"],
                           ph["taps"], ph["w_umma"] if umma else ph["w"], self.bias, self.scale, self.shift, res, res_coff,
-                          self.pre_relu, self.post_relu, self.sigmoid, umma=umma, halo=umma and USE_HALO and self.cout <= 128,
-                          epi16=umma and USE_EPI16 and self.cout <= 128)
+                          self.pre_relu, self.post_relu, self.sigmoid, umma=umma)
         return out
 
 

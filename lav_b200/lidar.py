@@ -2,17 +2,20 @@
 
 Same constructors, forward signatures and ``state_dict`` keys; every conv / transposed conv
 (+ReLU+BatchNorm epilogue) runs in hand-written CUDA (csrc/conv_taps.cu; csrc/conv_umma.cu on the
-bf16 path).  Tensors keep the reference's logical NCHW shapes but are stored channels-last.
-``precision`` = 'fp32' (exact path, default) or 'bf16' (tensor-core path).
+f16 path).  Tensors keep the reference's logical NCHW shapes but are stored channels-last.
+``precision`` = 'fp32' (exact path, default) or 'f16' (tensor-core path).
 """
 import torch
 from torch import nn
 
+from . import ops
 from .capi import LavbError
 from .layers import PlanMixin, TapConv, bn_affine
 from .point_pillar import PointPillarNet
 
-_DT = {"fp32": torch.float32, "bf16": torch.bfloat16}
+
+def _dt(precision):
+    return torch.float32 if precision == "fp32" else ops.h16()
 
 
 def _nhwc(x):
@@ -56,8 +59,8 @@ class ConvBackbone(PlanMixin, nn.Module):
         for name in ("upconv1", "upconv2", "upconv3"):
             seq = getattr(self, name)
             plan[name] = crb(seq[0], seq[2])
-        if self.precision == "bf16":
-            # first layer on tensor cores WITHOUT rounding the fp32 canvas to bf16: input = [hi | lo] split (2*cin channels),
+        if self.precision == "f16":
+            # first layer on tensor cores WITHOUT rounding the fp32 canvas to f16: input = [hi | lo] split (2*cin channels),
             # weights duplicated along cin, so conv(x_hi) + conv(x_lo) accumulate in TMEM (costs 1.9 extra GFLOP / frame)
             c0, b0 = self.conv1[0], self.conv1[2]
             s, t = bn_affine(b0)
@@ -70,13 +73,12 @@ class ConvBackbone(PlanMixin, nn.Module):
         if self.training:
             raise LavbError("ConvBackbone: training-mode forward goes through lav_b200.train (autograd path)")
         plan = self._plan_get(x.device, self._build)
-        dt = _DT[self.precision]
+        dt = _dt(self.precision)
         first = None
-        if dt == torch.bfloat16 and x.dtype == torch.float32:
-            from . import ops
-            first = plan["conv1_split"](ops.split_bf16(x), out_dtype=dt)
-        elif dt == torch.bfloat16 and x.shape[-1] == 2 * self.conv1[0].in_channels:
-            first = plan["conv1_split"](x, out_dtype=dt)       # canvas already arrives as the [hi | lo] bf16 split
+        if dt == ops.h16() and x.dtype == torch.float32:
+            first = plan["conv1_split"](ops.split_h16(x), out_dtype=dt)
+        elif dt == ops.h16() and x.shape[-1] == 2 * self.conv1[0].in_channels:
+            first = plan["conv1_split"](x, out_dtype=dt)       # canvas already arrives as the [hi | lo] f16 split
         xs = []
         for name in ("conv1", "conv2", "conv3"):
             for li, layer in enumerate(plan[name]):
@@ -129,7 +131,7 @@ class Head(PlanMixin, nn.Module):
         if self.training:
             raise LavbError("Head: training-mode forward goes through lav_b200.train (autograd path)")
         conv, up = self._plan_get(x.device, self._build)
-        return up(conv(x, out_dtype=_DT[self.precision]), out_dtype=torch.float32)
+        return up(conv(x, out_dtype=_dt(self.precision)), out_dtype=torch.float32)
 
     def forward(self, x):
         if self.training:
@@ -156,7 +158,7 @@ class LiDARModel(PlanMixin, nn.Module):
         self.precision = "fp32"
 
     def set_precision(self, precision):
-        assert precision in _DT
+        assert precision in ("fp32", "f16"), precision
         for m in self.modules():
             if hasattr(m, "precision"):
                 m.precision = precision
@@ -187,7 +189,7 @@ class LiDARModel(PlanMixin, nn.Module):
             wd[g, :, :, :no] = ct.weight.detach().float().permute(0, 2, 3, 1).reshape(nh, 9, no)   # (cin,cout,ky,kx)->(cin,tap,cout)
             bd[g, :no] = ct.bias.detach().float()
             n_outs.append(no)
-            # tensor-core form (bf16 path): a 2x2-tap GEMM over the input grid with 4*no (<=32) columns and a
+            # tensor-core form (f16 path): a 2x2-tap GEMM over the input grid with 4*no (<=32) columns and a
             # depth-to-space epilogue.  out(2y+a, 2x+b) gathers input pixel (y+dy, x+dx) through kernel tap (ky,kx):
             #   a=0 -> (dy=0,ky=1);  a=1 -> (dy=0,ky=2) and (dy=1,ky=0)      (same for b / dx / kx)
             w = ct.weight.detach().float()                                      # (cin, cout, ky, kx)
@@ -200,14 +202,13 @@ class LiDARModel(PlanMixin, nn.Module):
                             wu[dy * 2 + dx, (pa * 2 + pb) * no:(pa * 2 + pb) * no + no] = w[:, :, ky, kx].t()
             bias32 = torch.zeros(32, dtype=torch.float32, device=device)
             bias32[:4 * no] = ct.bias.detach().float().repeat(4)
-            d2s.append((wu.to(torch.bfloat16).contiguous(), bias32))
+            d2s.append((wu.to(ops.h16()).contiguous(), bias32))
         return conv, (wd.contiguous(), bd.contiguous(), n_outs, [h._is_sigmoid() for h in self._heads()], nh, d2s)
 
     def heads_nhwc(self, feats):
-        from . import ops
         conv, (wd, bd, n_outs, sig, nh, d2s) = self._plan_get(feats.device, self._build)
-        if self.precision == "bf16":
-            hid = conv(feats, out_dtype=torch.bfloat16)
+        if self.precision == "f16":
+            hid = conv(feats, out_dtype=ops.h16())
             n, h, w, _ = hid.shape
             outs = []
             for g, (wu, b32) in enumerate(d2s):
@@ -220,7 +221,7 @@ class LiDARModel(PlanMixin, nn.Module):
         return ops.deconv3x3s2_small(hid, 4, nh, wd, bd, n_outs, sig)
 
     def forward_nhwc(self, lidars, num_points):
-        canvas = self.point_pillar_net.forward_nhwc(lidars, num_points, split_out=(self.precision == "bf16"))
+        canvas = self.point_pillar_net.forward_nhwc(lidars, num_points, split_out=(self.precision == "f16"))
         feats = self.backbone.forward_nhwc(canvas)
         return (feats, *self.heads_nhwc(feats))
 

@@ -9,9 +9,16 @@ import numpy as np
 import torch
 
 from . import capi
-from .capi import BF16, F32, ConvDesc, check, lib
+from .capi import BF16, F16, F32, ConvDesc, check, lib
 
-_DT = {torch.float32: F32, torch.bfloat16: BF16}
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+
+
+def h16():
+    """torch dtype of the library's 16-bit storage type: float16 (fp32 accumulation, saturating stores) unless the library was
+    built with -DLAVB_H16_BF16."""
+    return torch.float16 if capi.h16_code() == F16 else torch.bfloat16
+
 
 
 def _stream():
@@ -86,6 +93,23 @@ def stack_sweep(src, R, dx, dy, time_idx, n_time, dst, roof_filter=False):
                                  time_idx, n_time, int(roof_filter), _ptr(dst), _stream()), "lavb_stack_sweep")
     _COUNT[0] += 1
     return dst
+
+
+def roof_filter(sweeps, pad_nan=False, out=None):
+    """LAVAgent.preprocess (lav_agent.py:448-457) on the device, order preserving.  sweeps: (n, cols) or (F, n, cols) fp32
+    contiguous -> (out like sweeps with the kept rows first, counts (F,) int32).  pad_nan fills rows past the count with NaN."""
+    _need_cuda(sweeps)
+    assert sweeps.dtype == torch.float32 and sweeps.is_contiguous() and sweeps.dim() in (2, 3)
+    x = sweeps if sweeps.dim() == 3 else sweeps[None]
+    f, n, cols = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.is_contiguous() and out.shape == x.shape and out.data_ptr() != x.data_ptr()
+    counts = torch.empty((f,), dtype=torch.int32, device=x.device)
+    check(lib().lavb_roof_filter(_ptr(x), f, n, cols, n * cols, _ptr(out), n * cols, _ptr(counts), int(pad_nan), _stream()),
+          "lavb_roof_filter")
+    _COUNT[0] += 1
+    return (out if sweeps.dim() == 3 else out[0]), counts
 
 
 # ----------------------------------------------------------------------------- pillars
@@ -163,10 +187,10 @@ def pillar_scatter_max_bwd(gcanvas, arg, cell, m):
 
 # ----------------------------------------------------------------------------- convolution
 def conv_taps(x, cin, in_coff, out, cout, out_coff, hog, wog, in_s, out_s, out_o, taps, w, bias=None, scale=None, shift=None,
-              res=None, res_coff=0, pre_relu=False, post_relu=False, sigmoid=False, umma=False, d2s_nout=0, halo=False, epi16=False):
+              res=None, res_coff=0, pre_relu=False, post_relu=False, sigmoid=False, umma=False, d2s_nout=0):
     """x, out, res: contiguous NHWC buffers (N,H,W,Ctot).  taps: list of (dy,dx).
     umma=False: CUDA-core kernel, w (ntaps,cin,cout_pad16) fp32.
-    umma=True : tcgen05 kernel, x bf16, w (ntaps,cout,cin) bf16."""
+    umma=True : tcgen05 kernel, x f16, w (ntaps,cout,cin) f16."""
     _need_cuda(x, out, w)
     assert x.is_contiguous() and out.is_contiguous() and w.is_contiguous()
     d = ConvDesc()
@@ -187,7 +211,7 @@ def conv_taps(x, cin, in_coff, out, cout, out_coff, hog, wog, in_s, out_s, out_o
     d.out_oy, d.out_ox = out_o
     d.ntaps = len(taps)
     if umma:
-        assert w.dtype == torch.bfloat16 and tuple(w.shape) == (len(taps), (cout + 31) // 32 * 32, cin) and x.dtype == torch.bfloat16
+        assert w.dtype == h16() and tuple(w.shape) == (len(taps), (cout + 31) // 32 * 32, cin) and x.dtype == h16()
     else:
         assert w.dtype == torch.float32 and tuple(w.shape) == (len(taps), cin, (cout + 15) // 16 * 16)
     for i, (dy, dx) in enumerate(taps):
@@ -202,17 +226,7 @@ def conv_taps(x, cin, in_coff, out, cout, out_coff, hog, wog, in_s, out_s, out_o
     d.pre_relu, d.post_relu, d.sigmoid = int(pre_relu), int(post_relu), int(sigmoid)
     if umma:
         e0 = _prof_begin()
-        rc = 4
-        if halo and out.dtype == torch.bfloat16 and tuple(in_s) == (1, 1) and tuple(out_s) == (1, 1) and not d2s_nout and not sigmoid:
-            rc = lib().lavb_conv_halo_umma(C.byref(d), _stream())       # experimental; 4 = "not covered / does not pay"
-            if rc not in (0, 4):
-                check(rc, "lavb_conv_halo_umma")
-        if rc == 4 and epi16:
-            rc = lib().lavb_conv_umma16(C.byref(d), _stream())          # experimental; 4 = "not covered"
-            if rc not in (0, 4):
-                check(rc, "lavb_conv_umma16")
-        if rc == 4:
-            check(lib().lavb_conv_umma(C.byref(d), _stream()), "lavb_conv_umma")
+        check(lib().lavb_conv_umma(C.byref(d), _stream()), "lavb_conv_umma")
         _prof_end(f"umma:{cin}->{cout}x{len(taps)}taps@{hog}x{wog}", 2.0 * x.shape[0] * hog * wog * cout * cin * len(taps), e0)
     else:
         check(lib().lavb_conv_taps(C.byref(d), _stream()), "lavb_conv_taps")
@@ -260,7 +274,7 @@ def convert(src, dtype):
 
 
 def crop_bilinear(feats_nhwc, frame_idx, theta, crop_size):
-    """feats_nhwc (B,H,W,C) contiguous fp32/bf16; frame_idx (K,) int32; theta (K,2,3) fp32 -> (K,crop,crop,C)."""
+    """feats_nhwc (B,H,W,C) contiguous fp32/f16; frame_idx (K,) int32; theta (K,2,3) fp32 -> (K,crop,crop,C)."""
     _need_cuda(feats_nhwc, frame_idx, theta)
     assert feats_nhwc.is_contiguous()
     b, h, w, c = feats_nhwc.shape
@@ -304,6 +318,35 @@ def paint_batched(points, sem, cams, mode, copy_cols, out):
     return out
 
 
+def pack_deconv2x2(weight, bias):
+    """ConvTranspose2d(16, C, 2, stride=2) parameters (weight (16,C,2,2), bias (C,)) -> the 264-float table
+    lavb_paint_deconv_batched reads: w[v%2][u%2][c_in][8] | bias[8]."""
+    cin, c, kh, kw = weight.shape
+    assert cin == 16 and kh == 2 and kw == 2 and c <= 8
+    w = torch.zeros((2, 2, 16, 8), dtype=torch.float32, device=weight.device)
+    w[:, :, :, :c] = weight.detach().float().permute(2, 3, 0, 1)
+    b = torch.zeros((8,), dtype=torch.float32, device=weight.device)
+    b[:c] = bias.detach().float()
+    return torch.cat([w.reshape(-1), b]).contiguous()
+
+
+def paint_deconv_batched(points, feat, n_classes, deconv, cams, copy_cols, out, image_hw):
+    """points (F,N,>=3) fp32; feat NHWC (F*ncam, H/2, W/2, 16) fp32 / h16 = ERFNet decoder output before output_conv;
+    deconv = pack_deconv2x2(...); out (F,N,copy_cols + n_classes-1)."""
+    _need_cuda(points, feat, out, deconv)
+    assert points.is_contiguous() and out.is_contiguous() and feat.is_contiguous() and points.dtype == torch.float32
+    f, n, ps = points.shape
+    h, w = image_hw
+    cams = np.ascontiguousarray(cams, dtype=np.float32)
+    ncam = cams.shape[0]
+    assert feat.shape == (f * ncam, h // 2, w // 2, 16) and deconv.numel() == 264
+    check(lib().lavb_paint_deconv_batched(_ptr(points), f, n, ps, n * ps, _ptr(feat), _DT[feat.dtype], ncam, n_classes, h, w,
+                                          _ptr(deconv), cams.ctypes.data_as(C.c_void_p), _ptr(out), out.shape[2], n * out.shape[2],
+                                          copy_cols, copy_cols, _stream()), "lavb_paint_deconv_batched")
+    _COUNT[0] += 1
+    return out
+
+
 STACK_JOB_DTYPE = np.dtype([("src", np.uint64), ("dst", np.uint64), ("n", np.int32), ("time_idx", np.int32), ("R", np.float32, 9),
                             ("dx", np.float32), ("dy", np.float32), ("pad", np.int32)])
 assert STACK_JOB_DTYPE.itemsize == 72
@@ -316,20 +359,23 @@ def stack_jobs(d_jobs, n_jobs, max_n, src_cols, n_time, roof_filter=False):
     _COUNT[0] += 1
 
 
-def split_bf16(x):
-    """fp32 (..., C) contiguous -> bf16 (..., 2C) = [hi | lo] error-free split (see lavb_split_bf16)."""
+def split_h16(x):
+    """fp32 (..., C) contiguous -> f16 (..., 2C) = [hi | lo] error-free split (see lavb_split_h16)."""
     _need_cuda(x)
     assert x.is_contiguous() and x.dtype == torch.float32
     c = x.shape[-1]
-    out = torch.empty((*x.shape[:-1], 2 * c), dtype=torch.bfloat16, device=x.device)
-    check(lib().lavb_split_bf16(_ptr(x), _ptr(out), x.numel() // c, c, _stream()), "lavb_split_bf16")
+    out = torch.empty((*x.shape[:-1], 2 * c), dtype=h16(), device=x.device)
+    check(lib().lavb_split_h16(_ptr(x), _ptr(out), x.numel() // c, c, _stream()), "lavb_split_h16")
     _COUNT[0] += 1
     return out
 
 
+PILLAR_ENCODER = "tiled"     # "tiled" (lavb_pillar_forward_tiled) | "sorted" (lavb_pillar_forward_sorted): tensor-core encoders
+
+
 def pillar_forward_sorted(pts, starts, counts, grid, w1, s1, t1, w2, s2, t2, split_out=False):
-    """sorted / tensor-core pillar encoder (lavb_pillar_forward_sorted).  Returns the NHWC canvas: fp32 (B,ny,nx,H2) or,
-    with split_out, bf16 (B,ny,nx,2*H2) = [hi | lo]."""
+    """tensor-core pillar encoder of the 16-bit pipeline (tile-binned or sorted kernel, see PILLAR_ENCODER).  Returns the NHWC
+    canvas: fp32 (B,ny,nx,H2) or, with split_out, f16 (B,ny,nx,2*H2) = [hi | lo]."""
     _need_cuda(pts, w1, w2)
     assert pts.dtype == torch.float32 and pts.dim() == 2 and pts.stride(1) == 1
     min_x, max_x, min_y, max_y, ppm, nx, ny = grid
@@ -337,14 +383,18 @@ def pillar_forward_sorted(pts, starts, counts, grid, w1, s1, t1, w2, s2, t2, spl
     b, st, ct = _clouds(starts, counts)
     total = int(sum(int(c) for c in counts))
     h2 = w2.shape[0]
-    canvas = torch.empty((b, ny, nx, 2 * h2 if split_out else h2), dtype=torch.bfloat16 if split_out else torch.float32, device=pts.device)
-    ws = _workspace(pts.device, lib().lavb_pillar_sorted_workspace_bytes(b, nx, ny, total))
+    canvas = torch.empty((b, ny, nx, 2 * h2 if split_out else h2), dtype=h16() if split_out else torch.float32, device=pts.device)
+    tiled = PILLAR_ENCODER == "tiled"
+    if tiled:      # every frame's records start at its exclusive point offset: size the record buffer for the clouds as given
+        total = int(sum(int(c) for c in counts))
+    ws = _workspace(pts.device, (lib().lavb_pillar_tiled_workspace_bytes if tiled else lib().lavb_pillar_sorted_workspace_bytes)(b, nx, ny, total))
     e0 = _prof_begin()
-    check(lib().lavb_pillar_forward_sorted(_ptr(pts), pts.stride(0), d, st, ct, b, min_x, max_x, min_y, max_y, ppm, nx, ny,
+    fn, name = (lib().lavb_pillar_forward_tiled, "lavb_pillar_forward_tiled") if tiled else (lib().lavb_pillar_forward_sorted, "lavb_pillar_forward_sorted")
+    check(fn(_ptr(pts), pts.stride(0), d, st, ct, b, min_x, max_x, min_y, max_y, ppm, nx, ny,
                                            _ptr(w1), _ptr(s1), _ptr(t1), w1.shape[0], _ptr(w2), _ptr(s2), _ptr(t2), h2,
-                                           _ptr(canvas), int(split_out), _ptr(ws), _stream()), "lavb_pillar_forward_sorted")
+                                           _ptr(canvas), int(split_out), _ptr(ws), _stream()), name)
     _prof_end("pillar", float(total) * d * 4 + float(b) * ny * nx * h2 * 4, e0)
-    _COUNT[0] += 6
+    _COUNT[0] += 3 if tiled else 6
     return canvas
 
 
@@ -361,37 +411,37 @@ def det_peaks(center, box, ori, min_score=0.2, max_det=15):
     return packed
 
 
-def stem7x7s2_u8(img_u8, w_bf16, bias, mean, std):
-    """img_u8 (B, ncam, H, cam_w, 3) uint8 contiguous; w_bf16 (64,160) packed by pack_stem_weights; bias (64,)
-    -> bf16 NHWC (B, H/2, ncam*cam_w/2, 64)."""
-    _need_cuda(img_u8, w_bf16, bias)
+def stem7x7s2_u8(img_u8, w_h16, bias, mean, std):
+    """img_u8 (B, ncam, H, cam_w, 3) uint8 contiguous; w_h16 (64,160) packed by pack_stem_weights; bias (64,)
+    -> f16 NHWC (B, H/2, ncam*cam_w/2, 64)."""
+    _need_cuda(img_u8, w_h16, bias)
     assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous() and img_u8.dim() == 5 and img_u8.shape[4] == 3
-    assert w_bf16.dtype == torch.bfloat16 and tuple(w_bf16.shape) == (64, 160) and w_bf16.is_contiguous()
+    assert w_h16.dtype == h16() and tuple(w_h16.shape) == (64, 160) and w_h16.is_contiguous()
     b, ncam, h, cw, _ = img_u8.shape
-    out = torch.empty((b, (h - 1) // 2 + 1, (ncam * cw - 1) // 2 + 1, 64), dtype=torch.bfloat16, device=img_u8.device)
+    out = torch.empty((b, (h - 1) // 2 + 1, (ncam * cw - 1) // 2 + 1, 64), dtype=h16(), device=img_u8.device)
     m = (C.c_float * 3)(*[float(v) for v in mean])
     sd = (C.c_float * 3)(*[float(v) for v in std])
-    check(lib().lavb_stem7x7s2_u8(_ptr(img_u8), b, ncam, h, cw, _ptr(w_bf16), _ptr(bias), m, sd, _ptr(out), _stream()),
+    check(lib().lavb_stem7x7s2_u8(_ptr(img_u8), b, ncam, h, cw, _ptr(w_h16), _ptr(bias), m, sd, _ptr(out), _stream()),
           "lavb_stem7x7s2_u8")
     _COUNT[0] += 1
     return out
 
 
 def pack_stem_weights(w):
-    """(64, 3, 7, 7) conv weights -> (64, 160) bf16 in the stem kernel's K order k = ky*22 + kx*3 + c (zero elsewhere)."""
+    """(64, 3, 7, 7) conv weights -> (64, 160) f16 in the stem kernel's K order k = ky*22 + kx*3 + c (zero elsewhere)."""
     wk = torch.zeros((64, 7, 22), dtype=torch.float32, device=w.device)
     wk[:, :, :21] = w.float().permute(0, 2, 3, 1).reshape(64, 7, 21)
     out = torch.zeros((64, 160), dtype=torch.float32, device=w.device)
     out[:, :154] = wk.reshape(64, 154)
-    return out.to(torch.bfloat16).contiguous()
+    return out.to(h16()).contiguous()
 
 
 def maxpool3x3s2_nhwc(x):
-    """MaxPool2d(3, 2, 1) on a contiguous bf16 NHWC tensor."""
+    """MaxPool2d(3, 2, 1) on a contiguous f16 NHWC tensor."""
     _need_cuda(x)
-    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4 and x.shape[3] % 8 == 0
+    assert x.dtype == h16() and x.is_contiguous() and x.dim() == 4 and x.shape[3] % 8 == 0
     n, h, w, c = x.shape
-    out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=h16(), device=x.device)
     check(lib().lavb_maxpool3x3s2_nhwc(_ptr(x), n, h, w, c, _ptr(out), _stream()), "lavb_maxpool3x3s2_nhwc")
     _COUNT[0] += 1
     return out
@@ -399,12 +449,12 @@ def maxpool3x3s2_nhwc(x):
 
 def conv_pair_umma(x, w1, bias1, w2, bias2, scale2, shift2, dil, res=None, post_relu=True):
     """EXPERIMENTAL fused pair: relu(conv3x1_dil(x) + bias1) -> conv1x3_dil -> (+bias2) * scale2 + shift2 [+ res] [-> relu].
-    x / res: contiguous bf16 NHWC (n, h, w, c), c in {64, 128}, w in {32, 64, 128}; w1 / w2: (3, c, c) bf16 [tap][cout][cin]."""
+    x / res: contiguous f16 NHWC (n, h, w, c), c in {64, 128}, w in {32, 64, 128}; w1 / w2: (3, c, c) f16 [tap][cout][cin]."""
     from .capi import ConvPairDesc
     _need_cuda(x, w1, w2)
     n, h, w, c = x.shape
-    assert x.dtype == torch.bfloat16 and x.is_contiguous() and w1.is_contiguous() and w2.is_contiguous()
-    assert tuple(w1.shape) == (3, c, c) and tuple(w2.shape) == (3, c, c) and w1.dtype == w2.dtype == torch.bfloat16
+    assert x.dtype == h16() and x.is_contiguous() and w1.is_contiguous() and w2.is_contiguous()
+    assert tuple(w1.shape) == (3, c, c) and tuple(w2.shape) == (3, c, c) and w1.dtype == w2.dtype == h16()
     out = torch.empty_like(x)
     d = ConvPairDesc()
     d.inp, d.out = x.data_ptr(), out.data_ptr()
@@ -415,7 +465,7 @@ def conv_pair_umma(x, w1, bias1, w2, bias2, scale2, shift2, dil, res=None, post_
     d.scale2 = scale2.data_ptr() if scale2 is not None else None
     d.shift2 = shift2.data_ptr() if shift2 is not None else None
     if res is not None:
-        assert res.is_contiguous() and res.shape == x.shape and res.dtype == torch.bfloat16
+        assert res.is_contiguous() and res.shape == x.shape and res.dtype == h16()
         d.res = res.data_ptr()
     e0 = _prof_begin()
     check(lib().lavb_conv_pair_umma(C.byref(d), _stream()), "lavb_conv_pair_umma")
@@ -424,17 +474,31 @@ def conv_pair_umma(x, w1, bias1, w2, bias2, scale2, shift2, dil, res=None, post_
     return out
 
 
-def gru_h512(u, h0, whh_bf16, wih, bih, bhh):
-    """EXPERIMENTAL cluster-persistent GRU(4 -> 512) roll-out.  u (N, T, 4) fp32, h0 (N, 512) fp32, whh_bf16 (1536, 512) bf16,
+def erf_nb16(x, w4, st, out=None):
+    """fused non_bottleneck_1d(16, dilation 1) block: x h16 NHWC (n,h,w,16) -> same shape (lavb_erf_nb16)."""
+    _need_cuda(x, w4, st)
+    assert x.dtype == h16() and x.is_contiguous() and x.dim() == 4 and x.shape[3] == 16
+    assert w4.dtype == torch.float32 and tuple(w4.shape) == (4, 3, 16, 16) and w4.is_contiguous()
+    assert st.dtype == torch.float32 and tuple(st.shape) == (4, 16, 2) and st.is_contiguous()
+    n, h, w, _ = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().lavb_erf_nb16(_ptr(x), _ptr(out), n, h, w, _ptr(w4), _ptr(st), _stream()), "lavb_erf_nb16")
+    _COUNT[0] += 1
+    return out
+
+
+def gru_h512(u, h0, whh_h16, wih, bih, bhh):
+    """EXPERIMENTAL cluster-persistent GRU(4 -> 512) roll-out.  u (N, T, 4) fp32, h0 (N, 512) fp32, whh_h16 (1536, 512) f16,
     wih (1536, 4), bih / bhh (1536,) fp32 -> out (N, T, 512) fp32 (the output sequence of nn.GRU(batch_first=True))."""
-    _need_cuda(u, h0, whh_bf16)
+    _need_cuda(u, h0, whh_h16)
     n, t, k = u.shape
-    assert k == 4 and tuple(h0.shape) == (n, 512) and tuple(whh_bf16.shape) == (1536, 512) and whh_bf16.dtype == torch.bfloat16
+    assert k == 4 and tuple(h0.shape) == (n, 512) and tuple(whh_h16.shape) == (1536, 512) and whh_h16.dtype == h16()
     assert u.dtype == h0.dtype == wih.dtype == bih.dtype == bhh.dtype == torch.float32
     u, h0 = u.contiguous(), h0.contiguous()
-    assert whh_bf16.is_contiguous() and wih.is_contiguous()
+    assert whh_h16.is_contiguous() and wih.is_contiguous()
     out = torch.empty((n, t, 512), dtype=torch.float32, device=u.device)
-    check(lib().lavb_gru_h512(_ptr(u), _ptr(h0), _ptr(whh_bf16), _ptr(wih), _ptr(bih), _ptr(bhh), _ptr(out), n, t, _stream()),
+    check(lib().lavb_gru_h512(_ptr(u), _ptr(h0), _ptr(whh_h16), _ptr(wih), _ptr(bih), _ptr(bhh), _ptr(out), n, t, _stream()),
           "lavb_gru_h512")
     _COUNT[0] += 1
     return out

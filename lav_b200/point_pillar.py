@@ -33,7 +33,7 @@ class _PillarScatterMax(torch.autograd.Function):
     """scatter_max over canvas cells with arg-routed backward (torch_scatter.scatter_max semantics)."""
 
     @staticmethod
-    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)     # under autocast the point MLP hands over bf16
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)     # under autocast the point MLP hands over f16
     def forward(ctx, h, cell, n_cells):
         canvas, arg = ops.pillar_scatter_max(h, cell, n_cells, want_argmax=True)
         ctx.save_for_backward(arg, cell)
@@ -56,7 +56,7 @@ class PointPillarNet(PlanMixin, nn.Module):
         self.min_x, self.min_y, self.max_x, self.max_y = min_x, min_y, max_x, max_y
         self.pixels_per_meter = pixels_per_meter
         self.num_point_dims = num_input - 5
-        self.precision = "fp32"      # 'bf16' selects the sorted / tensor-core encoder (set by LiDARModel.set_precision)
+        self.precision = "fp32"      # 'f16' selects the sorted / tensor-core encoder (set by LiDARModel.set_precision)
 
     def _grid(self):
         return (float(self.min_x), float(self.max_x), float(self.min_y), float(self.max_y), float(self.pixels_per_meter),
@@ -114,12 +114,12 @@ class PointPillarNet(PlanMixin, nn.Module):
 
     def forward_nhwc(self, lidar_list, num_points, split_out=False, _buf=None):
         """eval forward returning the raw NHWC canvas buffer.  fp32 precision: exact kernel (fp32 FFMA + atomicMax).
-        bf16 precision: sorted / tensor-core kernel; with split_out the canvas comes as bf16 [hi | lo] (B,ny,nx,2C),
+        f16 precision: sorted / tensor-core kernel; with split_out the canvas comes as f16 [hi | lo] (B,ny,nx,2C),
         which is what ConvBackbone's first tensor-core conv consumes."""
         buf, starts, counts = _buf if _buf is not None else self._as_buffer(lidar_list, num_points)
         if not buf.is_cuda:
             raise LavbError("lav_b200.PointPillarNet needs CUDA tensors (no CPU fallback)")
         w1, s1, t1, w2, s2, t2 = self._plan_get(buf.device, self._build)
-        if self.precision == "bf16":
+        if self.precision == "f16":
             return ops.pillar_forward_sorted(buf, starts, counts, self._grid(), w1, s1, t1, w2, s2, t2, split_out=split_out)
         return ops.pillar_forward(buf, starts, counts, self._grid(), w1, s1, t1, w2, s2, t2)

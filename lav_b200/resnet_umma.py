@@ -1,5 +1,5 @@
 """ResNet-18 trunk (layer1..layer4) on the lav_b200 tensor-core conv kernel — used by the brake predictor on the
-bf16 path ("brake model on the same conv kernels").
+f16 path ("brake model on the same conv kernels").
 
 Each BasicBlock (lav/models/resnet.py:41-84) becomes two (three with a downsample branch) tap-list convolutions whose
 epilogue carries the eval-mode BatchNorm as scale/shift, the residual add and the ReLU — no separate BN / add / ReLU
@@ -8,6 +8,7 @@ passes over the activations.  The 7x7/2 stem on 3 input channels and the 3x3/2 m
 """
 import torch
 
+from . import ops
 from .layers import TapConv, bn_affine
 
 
@@ -49,7 +50,7 @@ class ResNetTrunkUMMA:
                 self.blocks.append((c1, c2, ds))
 
     def __call__(self, x):
-        """x: NHWC bf16 (N,H,W,64) = stem + max-pool output -> NHWC bf16 (N,H/8,W/8,512)."""
+        """x: NHWC f16 (N,H,W,64) = stem + max-pool output -> NHWC f16 (N,H/8,W/8,512)."""
         for c1, c2, ds in self.blocks:
             idt = x if ds is None else ds(x)
             x = c2(c1(x), res=idt)

@@ -9,7 +9,7 @@ from torch import nn
 
 from . import ops
 from .capi import LavbError
-from .erfnet import ERFNet, _DT
+from .erfnet import ERFNet, _dt
 
 
 class RGBSegmentationModel(nn.Module):
@@ -27,8 +27,16 @@ class RGBSegmentationModel(nn.Module):
         """rgb: uint8 (N,H,W,3) or float (N,3,H,W), 0..255 -> logits NHWC fp32 (N,H,W,C)."""
         if not rgb.is_cuda:
             raise LavbError("lav_b200.RGBSegmentationModel needs CUDA tensors (no CPU fallback)")
-        x = ops.rgb_normalize(rgb, _DT[self.erfnet.precision])
+        x = ops.rgb_normalize(rgb, _dt(self.erfnet.precision))
         return self.erfnet.forward_nhwc(x)
+
+    def forward_features_nhwc(self, rgb):
+        """-> (decoder features NHWC (N,H/2,W/2,16), output_conv table, n_classes): see ERFNet.forward_features_nhwc."""
+        if not rgb.is_cuda:
+            raise LavbError("lav_b200.RGBSegmentationModel needs CUDA tensors (no CPU fallback)")
+        x = ops.rgb_normalize(rgb, _dt(self.erfnet.precision))
+        feat, table = self.erfnet.forward_features_nhwc(x)
+        return feat, table, self.erfnet.decoder.output_conv.out_channels
 
     def forward_u8(self, rgb_u8_nhwc):
         return self.forward_nhwc(rgb_u8_nhwc).permute(0, 3, 1, 2)

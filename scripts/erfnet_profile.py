@@ -1,4 +1,4 @@
-"""torch.profiler kernel table of one ERFNet forward (3B images, bf16)."""
+"""torch.profiler kernel table of one ERFNet forward (3B images, f16)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,7 +8,7 @@ from tests import util
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 dev = torch.device("cuda:0")
 seg, _ = util.seg_model(dev)
-seg.set_precision("bf16")
+seg.set_precision("f16")
 rgb = synth.rgb_frames().to(dev).repeat(B, 1, 1, 1)
 with torch.no_grad():
     for _ in range(3):

@@ -10,7 +10,7 @@ Run each selector in its own process under `timeout` (scripts/round2_first_call.
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from lav_b200 import erfnet, heads, layers, synth
+from lav_b200 import erfnet, heads, layers, ops, synth
 from tests import util
 
 args = sys.argv[1:]
@@ -50,11 +50,11 @@ def compare(label, module, flag, fn):
 with torch.no_grad():
     if WHICH & {"pairs", "halo", "epi16"}:
         seg, _ = util.seg_model(dev)
-        seg.set_precision("bf16")
+        seg.set_precision("f16")
         rgb = synth.rgb_frames().to(dev).repeat(B, 1, 1, 1)
         lid, _ = util.lidar_model(dev)
-        lid.set_precision("bf16")
-        canvas = (torch.randn(B, 320, 320, 128, device=dev) * 0.3).to(torch.bfloat16)       # [hi | lo] split canvas
+        lid.set_precision("f16")
+        canvas = (torch.randn(B, 320, 320, 128, device=dev) * 0.3).to(ops.h16())       # [hi | lo] split canvas
         run_seg, run_bb = (lambda: seg.forward_nhwc(rgb)), (lambda: lid.backbone.forward_nhwc(canvas))
         if "epi16" in WHICH:
             compare(f"ERFNet {3 * B} images", layers, "USE_EPI16", run_seg)
@@ -68,8 +68,8 @@ with torch.no_grad():
         import bench
         (_, _, _, bra), _ = bench.build_models()
         bra = bra.to(dev).eval()
-        bra.conv_backbone.to(torch.bfloat16).to(memory_format=torch.channels_last)
-        bra.attn1.to(torch.bfloat16); bra.attn2.to(torch.bfloat16)
+        bra.conv_backbone.to(ops.h16()).to(memory_format=torch.channels_last)
+        bra.attn1.to(ops.h16()); bra.attn2.to(ops.h16())
         g = torch.Generator().manual_seed(1)
         rgbs = torch.randint(0, 256, (B, 3, 288, 256, 3), generator=g, dtype=torch.uint8).to(dev)
         tel = torch.randint(0, 256, (B, 192, 480, 3), generator=g, dtype=torch.uint8).to(dev)

@@ -1,4 +1,4 @@
-"""Print error metrics of the bf16 path (and fp32 path) against the oracle for each LiDARModel output."""
+"""Print error metrics of the f16 path (and fp32 path) against the oracle for each LiDARModel output."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,7 +12,7 @@ npts = [len(c) for c in clouds]
 with torch.no_grad():
     want = O.lidar_model(sd, clouds, npts, **util.GRID)
     want = list(want[:4]) + [torch.logit(want[4].clamp(1e-7, 1 - 1e-7))]
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "f16"):
         m.set_precision(prec)
         got = m([c.to(dev) for c in clouds], npts)
         got = [g.float().cpu() for g in got]

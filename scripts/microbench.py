@@ -44,7 +44,7 @@ for B in (1, 32):
 st = synth.stacked_lidar().to(dev)
 with torch.no_grad():
     res["pillar_B1_120k_ms"] = timeit(lambda: m.point_pillar_net([st], [len(st)]))
-for prec in ("fp32", "bf16"):
+for prec in ("fp32", "f16"):
     m.set_precision(prec)
     for B in (1, 4):
         canvas = torch.randn(B, 320, 320, 64, device=dev).relu()
@@ -58,7 +58,7 @@ for prec in ("fp32", "bf16"):
         res[f"heads_{prec}_B{B}_TFs"] = B * 45.564e9 / th / 1e9
 seg, _ = util.seg_model(dev)
 rgb = synth.rgb_frames().to(dev)
-for prec in ("fp32", "bf16"):
+for prec in ("fp32", "f16"):
     seg.set_precision(prec)
     with torch.no_grad():
         t = timeit(lambda: seg.forward_nhwc(rgb), iters=5)

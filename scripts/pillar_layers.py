@@ -7,7 +7,7 @@ from tests import util
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 dev = torch.device("cuda:0")
 m, _ = util.lidar_model(dev)
-m.set_precision("bf16")
+m.set_precision("f16")
 pts = synth.stacked_lidar().to(dev)[None].repeat(B, 1, 1).contiguous()
 with torch.no_grad():
     for _ in range(2):

@@ -9,7 +9,7 @@ from lav_b200.agent import StaticFramePipeline
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 dev = torch.device("cuda:0")
 (seg, lid, uni, bra), _ = bench.build_models()
-pipe = StaticFramePipeline(seg, lid, uni, bra, B, synth.SWEEP_POINTS, device=dev, precision="bf16", use_graphs=True)
+pipe = StaticFramePipeline(seg, lid, uni, bra, B, synth.SWEEP_POINTS, device=dev, precision="f16", use_graphs=True)
 rgbs, tels, lidars, prev, poses = bench.synth_frames(B)
 pipe.tick = 10
 for b in range(B):

@@ -10,7 +10,7 @@ from lav_b200.agent import StaticFramePipeline
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 dev = torch.device("cuda:0")
 (seg, lid, uni, bra), _ = bench.build_models()
-pipe = StaticFramePipeline(seg, lid, uni, bra, B, synth.SWEEP_POINTS, device=dev, precision="bf16", use_graphs=False)
+pipe = StaticFramePipeline(seg, lid, uni, bra, B, synth.SWEEP_POINTS, device=dev, precision="f16", use_graphs=False)
 rgbs, tels, lidars, prev, poses = bench.synth_frames(B)
 nxps = torch.tensor([[0.0, -20.0]] * B); cmds = torch.tensor([3] * B)
 for _ in range(2):

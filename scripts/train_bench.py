@@ -6,7 +6,7 @@ import torch, torch.distributed as dist
 import bench
 from lav_b200.train import LAVTrainer, synthetic_train_batch
 
-ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=32); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--amp", action="store_true", help="bf16 autocast forwards (opt-in)")
+ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=32); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--amp", action="store_true", help="f16 autocast forwards (opt-in)")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)

@@ -2,6 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from lav_b200 import ops
 from lav_b200.layers import TapConv
 
 dev = torch.device("cuda:0")
@@ -13,8 +14,8 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for name, n, h, w, cin, cout, k, p in cfgs:
     wgt = torch.randn(cout, cin, *k, device=dev) * 0.05
     layer = TapConv(wgt, False, 1, p, 1, 0, None, pre_relu=True, scale=torch.ones(cout, device=dev), shift=torch.zeros(cout, device=dev))
-    x = torch.randn(n, h, w, cin, device=dev).bfloat16()
-    out = torch.empty(n, h, w, cout, device=dev, dtype=torch.bfloat16)
+    x = torch.randn(n, h, w, cin, device=dev).to(ops.h16())
+    out = torch.empty(n, h, w, cout, device=dev, dtype=ops.h16())
     for _ in range(3):
         layer(x, out=out)
     ts = []

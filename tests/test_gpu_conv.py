@@ -6,7 +6,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from lav_b200 import synth
+from lav_b200 import ops, synth
 from oracle import lav_ref as O
 from tests import util
 
@@ -25,7 +25,7 @@ pytestmark = pytest.mark.gpu
     dict(cin=16, cout=5, k=(2, 2), s=2, p=(0, 0), d=(1, 1), t=True, op=0),
     dict(cin=64, cout=128, k=(1, 1), s=1, p=(0, 0), d=(1, 1), t=True, op=0),
 ])
-@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("dtype", ["fp32", "f16"])
 def test_tapconv_vs_torch(cuda, cfg, dtype):
     from lav_b200.layers import TapConv
     g = synth._gen(9, str(cfg))
@@ -43,11 +43,11 @@ def test_tapconv_vs_torch(cuda, cfg, dtype):
     want = F.relu(F.relu(y) * sc[None, :, None, None] + sh[None, :, None, None] + res)
     layer = TapConv(w.to(cuda), t, cfg["s"], cfg["p"], cfg["d"], cfg.get("op", 0), bias=b.to(cuda), pre_relu=True,
                     scale=sc.to(cuda), shift=sh.to(cuda), post_relu=True)
-    tdt = torch.float32 if dtype == "fp32" else torch.bfloat16
+    tdt = torch.float32 if dtype == "fp32" else ops.h16()
     xin = x.permute(0, 2, 3, 1).contiguous().to(cuda).to(tdt)
     rin = res.permute(0, 2, 3, 1).contiguous().to(cuda).to(tdt)
     got = layer(xin, res=rin).float().cpu().permute(0, 3, 1, 2)
-    tol = 1e-5 if dtype == "fp32" else 2e-2
+    tol = 1e-5 if dtype == "fp32" else 5e-3
     assert got.shape == want.shape
     assert util.rel_err(got, want) < tol
 
@@ -75,9 +75,9 @@ def test_lidar_model_matches_oracle_fp32(cuda, golden_dir):
         assert util.rel_err(m.center_head(feats), want[1]) < 1e-3
 
 
-def test_lidar_model_bf16(cuda):
+def test_lidar_model_f16(cuda):
     m, sd = util.lidar_model(cuda)
-    m.set_precision("bf16")
+    m.set_precision("f16")
     clouds = util.pillar_clouds()
     npts = [len(c) for c in clouds]
     with torch.no_grad():
@@ -85,13 +85,12 @@ def test_lidar_model_bf16(cuda):
         got = m([c.to(cuda) for c in clouds], npts)
     for n, a, b in zip(["features", "center", "box", "ori", "seg"], got, want):
         a, b = a.float().cpu(), b
-        # north_star tolerance for bf16 is 1e-2.  Measured on B200 with seeded (untrained, non-contractive) weights:
-        # max-norm error 0.8-1.2e-2, RMS 0.8-1.2e-2 after 12 chained bf16 layers (bf16 canvas, activations, weights;
-        # fp32 accumulate) — the storage-rounding floor.  Gate at 1.5e-2 on both; DESIGN.md §5 records the numbers.
+        # north_star tolerance of the 16-bit tensor-core path: 1e-2 (max-norm AND rms, of the tensor scale).  With IEEE-half
+        # storage + fp32 accumulation the 12 chained layers measure 1-2e-3 on these seeded, non-contractive weights
+        # (bfloat16 storage measured 1.0-1.7e-2, which is why the path is half — DESIGN.md §5).
         rms = float(((a - b) ** 2).mean().sqrt() / (b ** 2).mean().sqrt())
-        assert rms < 1.5e-2, (n, rms)
-        if n != "seg":     # sigmoid of O(30) random-weight logits amplifies bf16 rounding; RMS bound covers it
-            assert util.rel_err(a, b) < 1.5e-2, (n, util.rel_err(a, b))
+        assert rms < 1e-2, (n, rms)
+        assert util.rel_err(a, b) < 1e-2, (n, util.rel_err(a, b))
 
 
 @pytest.mark.parametrize("weights", ["seeded", "real"])
@@ -131,23 +130,23 @@ def test_erfnet_matches_oracle(cuda, weights, golden_dir):
     dict(cin=64, cout=128, k=(3, 3), p=(1, 1), d=(1, 1), hw=(40, 36), cs=2),
 ])
 def test_umma_conv_vs_torch(cuda, cfg):
-    """tcgen05 implicit-GEMM conv against fp32 torch on bf16-rounded operands (so only accumulation order differs)."""
+    """tcgen05 implicit-GEMM conv against fp32 torch on f16-rounded operands (so only accumulation order differs)."""
     from lav_b200 import layers
     from lav_b200.layers import TapConv
     g = synth._gen(21, str(cfg))
     t = cfg.get("t", False)
     s = cfg.get("s", 1)
     cin, cout, (kh, kw) = cfg["cin"], cfg["cout"], cfg["k"]
-    w = (torch.randn((cin, cout, kh, kw) if t else (cout, cin, kh, kw), generator=g) / (cin * kh * kw) ** 0.5).bfloat16().float()
+    w = (torch.randn((cin, cout, kh, kw) if t else (cout, cin, kh, kw), generator=g) / (cin * kh * kw) ** 0.5).to(ops.h16()).float()
     b = torch.randn(cout, generator=g)
     sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
-    x = torch.randn(3, cin, *cfg["hw"], generator=g).bfloat16().float()
+    x = torch.randn(3, cin, *cfg["hw"], generator=g).to(ops.h16()).float()
     if t:
         y = F.conv_transpose2d(x, w, b, s, cfg["p"], cfg["op"], 1, cfg["d"])
     else:
         s = cfg.get("cs", 1)
         y = F.conv2d(x, w, b, s, cfg["p"], cfg["d"])
-    res = torch.randn(y.shape, generator=g).bfloat16().float()
+    res = torch.randn(y.shape, generator=g).to(ops.h16()).float()
     if cfg.get("nores"):
         res = torch.zeros_like(res)
     want = F.relu(F.relu(y) * sc[None, :, None, None] + sh[None, :, None, None] + res)
@@ -155,25 +154,25 @@ def test_umma_conv_vs_torch(cuda, cfg):
     layer = TapConv(w.to(cuda), t, s, cfg["p"], cfg["d"], cfg.get("op", 0), bias=b.to(cuda), pre_relu=True,
                     scale=sc.to(cuda), shift=sh.to(cuda), post_relu=True)
     assert layer.umma_ok
-    xin = x.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16()
-    rin = None if cfg.get("nores") else res.permute(0, 2, 3, 1).contiguous().to(cuda).bfloat16()
+    xin = x.permute(0, 2, 3, 1).contiguous().to(cuda).to(ops.h16())
+    rin = None if cfg.get("nores") else res.permute(0, 2, 3, 1).contiguous().to(cuda).to(ops.h16())
     got32 = layer(xin, res=rin, out_dtype=torch.float32).cpu().permute(0, 3, 1, 2)
     assert util.rel_err(got32, want) < 2e-5          # fp32 output: only accumulation-order noise
     got16 = layer(xin, res=rin).float().cpu().permute(0, 3, 1, 2)
-    assert util.rel_err(got16, want) < 6e-3          # bf16 output rounding
+    assert util.rel_err(got16, want) < 1e-3          # f16 output rounding (2^-11)
     # linearity in the input batch: concatenating images must not mix them (tile scheduler / TMA image coordinate)
     one = layer(xin[1:2].contiguous(), res=None if rin is None else rin[1:2].contiguous(), out_dtype=torch.float32).cpu()
     assert torch.equal(one, layer(xin, res=rin, out_dtype=torch.float32).cpu()[1:2])
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", ["fp32", "h16"])
 def test_grouped_head_deconv_vs_torch(cuda, dtype):
     """the four Head.net[3] ConvTranspose2d(64->2/2/2/3,k3,s2,p1,op1) as one grouped launch"""
-    from lav_b200 import ops
+    dtype = torch.float32 if dtype == "fp32" else ops.h16()
     g = synth._gen(31, "deconv")
     hid = torch.randn(2, 256, 13, 17, generator=g)
-    if dtype == torch.bfloat16:
-        hid = hid.bfloat16().float()
+    if dtype == ops.h16():
+        hid = hid.to(ops.h16()).float()
     n_outs, sig = [2, 2, 2, 3], [False, False, False, True]
     ws = [torch.randn(64, no, 3, 3, generator=g) * 0.1 for no in n_outs]
     bs = [torch.randn(no, generator=g) for no in n_outs]
@@ -196,8 +195,7 @@ def test_grouped_head_deconv_vs_torch(cuda, dtype):
 @pytest.mark.parametrize("shape", [(2, 3, 32, 24), (1, 1, 31, 52), (1, 3, 9, 88), (1, 3, 288, 256), (2, 1, 192, 480)])
 def test_stem_u8_vs_torch(cuda, shape):
     """lavb_stem7x7s2_u8 == Normalize + conv 7x7/s2/p3 (3->64) + bias + ReLU on the side-by-side camera image
-    (team_code_v2/models/rgb.py:66-70, lav/models/resnet.py:235-238); operands rounded to bf16 on both sides, tol 1e-2."""
-    from lav_b200 import ops
+    (team_code_v2/models/rgb.py:66-70, lav/models/resnet.py:235-238); operands rounded to f16 on both sides, tol 1e-2."""
     b, ncam, h, cw = shape
     g = torch.Generator().manual_seed(5)
     img = torch.randint(0, 256, (b, ncam, h, cw, 3), generator=g, dtype=torch.uint8)
@@ -207,7 +205,7 @@ def test_stem_u8_vs_torch(cuda, shape):
     out = ops.stem7x7s2_u8(img.cuda(), ops.pack_stem_weights(w.cuda()), bias.cuda(), mean, std).float().cpu()
     wide = img.permute(0, 2, 1, 3, 4).reshape(b, h, ncam * cw, 3).permute(0, 3, 1, 2).float()
     x = (wide / 255. - torch.tensor(mean)[None, :, None, None]) / torch.tensor(std)[None, :, None, None]
-    ref = F.relu(F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias, stride=2, padding=3))
+    ref = F.relu(F.conv2d(x.to(ops.h16()).float(), w.to(ops.h16()).float(), bias, stride=2, padding=3))
     ref = ref.permute(0, 2, 3, 1)
     assert out.shape == ref.shape
     err = (out - ref).abs().max().item() / ref.abs().max().item()
@@ -218,23 +216,22 @@ def test_stem_u8_vs_torch(cuda, shape):
 @pytest.mark.parametrize("shape", [(2, 7, 9, 64), (3, 144, 384, 64), (1, 1, 1, 8), (2, 96, 240, 64)])
 def test_maxpool_nhwc_vs_torch(cuda, shape):
     """lavb_maxpool3x3s2_nhwc == MaxPool2d(3, 2, 1) (lav/models/resnet.py:181), bit-exact (values include negatives)."""
-    from lav_b200 import ops
-    x = torch.randn(shape, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16).cuda()
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(2)).to(ops.h16()).cuda()
     out = ops.maxpool3x3s2_nhwc(x)
-    ref = F.max_pool2d(x.permute(0, 3, 1, 2).float(), 3, 2, 1).permute(0, 2, 3, 1).to(torch.bfloat16)
+    ref = F.max_pool2d(x.permute(0, 3, 1, 2).float(), 3, 2, 1).permute(0, 2, 3, 1).to(ops.h16())
     assert out.shape == ref.shape and torch.equal(out, ref)
 
 
 @pytest.mark.gpu
 def test_brake_forward_u8_matches_forward(cuda):
-    """RGBBrakePredictionModel.forward_u8 (stem kernel on raw bytes) == forward(wide, tel) in bf16."""
+    """RGBBrakePredictionModel.forward_u8 (stem kernel on raw bytes) == forward(wide, tel) in f16."""
     from lav_b200.heads import RGBBrakePredictionModel
     torch.manual_seed(3)
     m = RGBBrakePredictionModel([4, 6, 7, 10]).eval()
     m.load_state_dict(synth.fill_state_dict_(m.state_dict(), seed=11))
-    m = m.cuda()                                   # as FramePipeline.set_precision('bf16'): trunk + attention in bf16
-    m.conv_backbone.to(torch.bfloat16).to(memory_format=torch.channels_last)
-    m.attn1.to(torch.bfloat16); m.attn2.to(torch.bfloat16)
+    m = m.cuda()                                   # as FramePipeline.set_precision('f16'): trunk + attention in f16
+    m.conv_backbone.to(ops.h16()).to(memory_format=torch.channels_last)
+    m.attn1.to(ops.h16()); m.attn2.to(ops.h16())
     g = torch.Generator().manual_seed(9)
     rgbs = torch.randint(0, 256, (3, 3, 288, 256, 3), generator=g, dtype=torch.uint8).cuda()
     tel = torch.randint(0, 256, (3, 192, 480, 3), generator=g, dtype=torch.uint8).cuda()
@@ -242,16 +239,14 @@ def test_brake_forward_u8_matches_forward(cuda):
         wide = rgbs.permute(0, 2, 1, 3, 4).reshape(3, 288, 768, 3).permute(0, 3, 1, 2).float()
         a = m(wide, tel.permute(0, 3, 1, 2).float()).float()
         b = m.forward_u8(rgbs, tel).float()
-    assert (a - b).abs().max().item() < 2e-2, (a, b)
+    assert (a - b).abs().max().item() < 1e-2, (a, b)
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("LAVB_EXPERIMENTAL"), reason="experimental fused-pair kernel: set LAVB_EXPERIMENTAL=1")
 @pytest.mark.parametrize("cfg", [(3, 72, 64, 64, 1, True), (2, 36, 32, 128, 2, True), (2, 36, 32, 128, 16, True), (1, 7, 64, 64, 1, False),
                                  (24, 72, 64, 64, 1, True), (96, 36, 32, 128, 4, True)])   # last two: several tiles per CTA (persistent loop)
 def test_conv_pair_umma_vs_torch(cuda, cfg):
-    """lavb_conv_pair_umma == relu(conv3x1) -> conv1x3 -> affine (+res) -> relu of erfnet.py:37-63, bf16 operands, tol 1e-2."""
-    from lav_b200 import ops
+    """lavb_conv_pair_umma == relu(conv3x1) -> conv1x3 -> affine (+res) -> relu of erfnet.py:37-63, f16 operands, tol 1e-2."""
     n, h, w, c, dil, use_res = cfg
     g = torch.Generator().manual_seed(4)
     x = torch.randn(n, c, h, w, generator=g)
@@ -259,91 +254,53 @@ def test_conv_pair_umma_vs_torch(cuda, cfg):
     w2 = torch.randn(c, c, 1, 3, generator=g) * (1.0 / (3 * c) ** 0.5)
     b1, b2 = torch.randn(c, generator=g) * 0.1, torch.randn(c, generator=g) * 0.1
     s2, t2 = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
-    bf = lambda t: t.to(torch.bfloat16).float()
+    bf = lambda t: t.to(ops.h16()).float()
     mid = bf(F.relu(F.conv2d(bf(x), bf(w1), b1, padding=(dil, 0), dilation=(dil, 1))))
     ref = F.conv2d(mid, bf(w2), b2, padding=(0, dil), dilation=(1, dil)) * s2[None, :, None, None] + t2[None, :, None, None]
     if use_res:
         ref = ref + bf(x)
     ref = F.relu(ref).permute(0, 2, 3, 1)
-    xd = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
-    w1u = w1[:, :, :, 0].permute(2, 0, 1).contiguous().to(torch.bfloat16).cuda()       # [tap][cout][cin]
-    w2u = w2[:, :, 0, :].permute(2, 0, 1).contiguous().to(torch.bfloat16).cuda()
+    xd = x.permute(0, 2, 3, 1).contiguous().to(ops.h16()).cuda()
+    w1u = w1[:, :, :, 0].permute(2, 0, 1).contiguous().to(ops.h16()).cuda()       # [tap][cout][cin]
+    w2u = w2[:, :, 0, :].permute(2, 0, 1).contiguous().to(ops.h16()).cuda()
     out = ops.conv_pair_umma(xd, w1u, b1.cuda(), w2u, b2.cuda(), s2.cuda(), t2.cuda(), dil, res=xd if use_res else None).float().cpu()
     err = (out - ref).abs().max().item() / ref.abs().max().item()
     assert err < 1e-2, err
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("LAVB_EXPERIMENTAL"), reason="experimental cluster GRU kernel: set LAVB_EXPERIMENTAL=1")
 @pytest.mark.parametrize("nseq", [192, 48, 7])
 def test_gru_cluster_vs_torch(cuda, nseq):
-    """lavb_gru_h512 == nn.GRU(4, 512, batch_first=True) output sequence (uniplanner.py:45,247-259); bf16 recurrent weights and
-    hidden-state copy on the tensor cores, fp32 state: tol 2e-2 of the output scale over 20 steps."""
-    from lav_b200 import ops
+    """lavb_gru_h512 == nn.GRU(4, 512, batch_first=True) output sequence (uniplanner.py:45,247-259); f16 recurrent weights and
+    hidden-state copy on the tensor cores, fp32 state: tol 5e-3 of the output scale over 20 steps."""
     torch.manual_seed(0)
     gru = torch.nn.GRU(4, 512, batch_first=True).cuda()
     u = torch.randn(nseq, 20, 4, device="cuda")
     h0 = torch.randn(nseq, 512, device="cuda") * 0.5
     with torch.no_grad():
         ref, _ = gru(u, h0[None])
-        out = ops.gru_h512(u, h0, gru.weight_hh_l0.to(torch.bfloat16).contiguous(), gru.weight_ih_l0.contiguous(),
+        out = ops.gru_h512(u, h0, gru.weight_hh_l0.to(ops.h16()).contiguous(), gru.weight_ih_l0.contiguous(),
                            gru.bias_ih_l0.contiguous(), gru.bias_hh_l0.contiguous())
     err = (out - ref).abs().max().item() / ref.abs().max().item()
-    assert err < 2e-2, err
+    assert err < 5e-3, err
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("LAVB_EXPERIMENTAL"), reason="experimental halo-patch conv kernel: set LAVB_EXPERIMENTAL=1")
-@pytest.mark.parametrize("cfg", [
-    # (n, h, w, cin, cout, kh, kw, dil, pre_relu_affine, residual)
-    (2, 40, 24, 64, 64, 3, 3, 1, True, False),        # backbone-style Conv -> ReLU -> BN, partial tiles in both directions
-    (3, 72, 64, 64, 64, 3, 1, 1, False, False),       # ERFNet 3x1
-    (2, 36, 32, 128, 128, 3, 1, 4, False, True),      # dilated 3x1 + residual, streamed weights do not apply (resident)
-    (2, 80, 80, 128, 128, 3, 3, 1, True, False),      # weights streamed through their own ring
-    (32, 160, 160, 64, 64, 3, 3, 1, True, False),     # many tiles per CTA
-])
-def test_conv_halo_umma_vs_umma(cuda, cfg, monkeypatch):
-    """lavb_conv_halo_umma == lavb_conv_umma (same descriptor, same bf16 operands): results must agree to accumulation-order noise."""
-    from lav_b200 import layers
-    n, h, w, cin, cout, kh, kw, dil, pre, use_res = cfg
-    g = torch.Generator().manual_seed(11)
-    x = (torch.randn(n, h, w, cin, generator=g)).to(torch.bfloat16).cuda()
-    wt = torch.randn(cout, cin, kh, kw, generator=g) * (1.0 / (kh * kw * cin) ** 0.5)
-    bias = torch.randn(cout, generator=g) * 0.1
-    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
-    pad = (dil * (kh // 2), dil * (kw // 2))
-    conv = layers.TapConv(wt.cuda(), False, 1, pad, (dil if kh > 1 else 1, dil if kw > 1 else 1), bias=None if pre else bias.cuda(),
-                          pre_relu=pre, scale=scale.cuda(), shift=shift.cuda(), post_relu=not pre)
-    res = x if use_res else None
-    monkeypatch.setattr(layers, "USE_HALO", False)
-    ref = conv(x, res=res).float()
-    monkeypatch.setattr(layers, "USE_HALO", True)
-    out = conv(x, res=res).float()
-    torch.cuda.synchronize()
-    err = (out - ref).abs().max().item() / ref.abs().max().item()
-    assert err < 4e-3, err          # both paths round the output to bf16; only the accumulation order differs
-
-
-@pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("LAVB_EXPERIMENTAL"), reason="experimental 2-CTA x 8-epilogue-warp variant: set LAVB_EXPERIMENTAL=1")
-@pytest.mark.parametrize("cfg", [(3, 72, 64, 64, 64, 3, 1, 1, False, True), (2, 36, 32, 128, 128, 1, 3, 8, False, True),
-                                 (2, 80, 80, 128, 128, 3, 3, 1, True, False), (16, 160, 160, 64, 64, 3, 3, 1, True, False)])
-def test_conv_umma16_vs_umma(cuda, cfg, monkeypatch):
-    """lavb_conv_umma16 (same source, 8 epilogue warps + 2 CTAs/SM) == lavb_conv_umma bit for bit (same MMA order, same epilogue math)."""
-    from lav_b200 import layers
-    n, h, w, cin, cout, kh, kw, dil, pre, use_res = cfg
-    g = torch.Generator().manual_seed(12)
-    x = (torch.randn(n, h, w, cin, generator=g)).to(torch.bfloat16).cuda()
-    wt = torch.randn(cout, cin, kh, kw, generator=g) * (1.0 / (kh * kw * cin) ** 0.5)
-    bias = torch.randn(cout, generator=g) * 0.1
-    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
-    pad = (dil * (kh // 2), dil * (kw // 2))
-    conv = layers.TapConv(wt.cuda(), False, 1, pad, (dil if kh > 1 else 1, dil if kw > 1 else 1), bias=None if pre else bias.cuda(),
-                          pre_relu=pre, scale=scale.cuda(), shift=shift.cuda(), post_relu=not pre)
-    res = x if use_res else None
-    monkeypatch.setattr(layers, "USE_EPI16", False)
-    ref = conv(x, res=res)
-    monkeypatch.setattr(layers, "USE_EPI16", True)
-    out = conv(x, res=res)
-    torch.cuda.synchronize()
-    assert torch.equal(out, ref)
+@pytest.mark.parametrize("shape", [(3, 144, 128), (2, 20, 32), (1, 7, 16), (5, 33, 64)])
+def test_erf_nb16_block_vs_torch(cuda, shape):
+    """lavb_erf_nb16 == non_bottleneck_1d(16, dilated=1) in eval mode (lav/models/erfnet.py:37-63), h16 operands: ragged
+    heights (tiles of 8 rows, halo rows above/below the image) and every supported width."""
+    from lav_b200.erfnet import _NB1D, non_bottleneck_1d
+    n, h, w = shape
+    torch.manual_seed(5)
+    blk = non_bottleneck_1d(16, 0.0, 1).eval()
+    sd = synth.fill_state_dict_(blk.state_dict())
+    blk.load_state_dict(sd)
+    x = torch.randn(n, 16, h, w)
+    with torch.no_grad():
+        want = O._erf_nb1d(x.to(ops.h16()).float(), {k: v.clone() for k, v in sd.items()}, "", 1).permute(0, 2, 3, 1)
+    plan = _NB1D(blk.to(cuda))
+    assert plan.nb16 is not None
+    got = ops.erf_nb16(x.permute(0, 2, 3, 1).contiguous().to(cuda).to(ops.h16()), *plan.nb16).float().cpu()
+    err = (got - want).abs().max().item() / want.abs().max().item()
+    assert err < 5e-3, err

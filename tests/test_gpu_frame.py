@@ -4,7 +4,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from lav_b200 import synth
+from lav_b200 import ops, synth
 from oracle import lav_ref as O
 from tests import util
 from tests.test_heads_cpu import uniplanner
@@ -14,9 +14,9 @@ pytestmark = pytest.mark.gpu
 DETS = [(150.0, 200.0, 8.0, 4.0, 0.9, 0.3), (170.0, 240.0, 8.0, 4.0, -0.2, 0.95), (161.0, 281.0, 8., 4., 1., 0.)]
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", ["fp32", "h16"])
 def test_crop_kernel_vs_grid_sample(cuda, dtype):
-    from lav_b200 import ops
+    dtype = torch.float32 if dtype == "fp32" else ops.h16()
     from lav_b200.heads import crop_theta
     g = synth._gen(4, "crop")
     feats = torch.randn(3, 64, 40, 48, generator=g)
@@ -121,9 +121,9 @@ def test_frame_pipeline_fp32_matches_oracle(cuda):
         assert abs(float(out["pred_bra"][b]) - float(want["bra"][0])) < 1e-3
 
 
-def test_frame_pipeline_bf16_close_to_oracle(cuda):
+def test_frame_pipeline_f16_close_to_oracle(cuda):
     from lav_b200.agent import SweepHistory
-    pipe, sds = _pipeline(cuda, "bf16")
+    pipe, sds = _pipeline(cuda, "f16")
     rgbs = synth.rgb_frames(tag="g0", smooth=True)[None]
     tels = synth.rgb_frames(tag="gt", smooth=True, n_cam=1, h=192, w=480)
     lidar = synth.lidar_sweep(8000, tag="gl")
@@ -137,10 +137,11 @@ def test_frame_pipeline_bf16_close_to_oracle(cuda):
     want = _oracle_frame(sds, rgbs[0], tels[0], lidar, prev, loc, ori, None)
     f_got, f_want = out["features"][0].float().cpu().permute(2, 0, 1), want["features"][0]
     rms = float(((f_got - f_want) ** 2).mean().sqrt() / (f_want ** 2).mean().sqrt())
-    assert rms < 2e-2, rms                                   # ERFNet(bf16) -> paint -> 17 bf16 conv layers
+    assert rms < 1e-2, rms                                   # ERFNet(f16) -> paint -> 17 f16 conv layers: north_star 1e-2
+    assert util.rel_err(f_got, f_want) < 1e-2
     sc = float(want["plan"][1].abs().max()) + 1
-    assert float((out["ego_plan_locs"][0].float().cpu() - want["plan"][1]).abs().max()) < 5e-2 * sc
-    assert abs(float(out["pred_bra"][0]) - float(want["bra"][0])) < 2e-2
+    assert float((out["ego_plan_locs"][0].float().cpu() - want["plan"][1]).abs().max()) < 1e-2 * sc
+    assert abs(float(out["pred_bra"][0]) - float(want["bra"][0])) < 1e-2
 
 
 @pytest.mark.parametrize("graphs", [False, True])
@@ -191,7 +192,7 @@ def test_resnet_trunk_on_umma_matches_cudnn(cuda):
     from lav_b200.heads import resnet18
     m = resnet18(num_channels=3).eval()
     m.load_state_dict(synth.fill_state_dict_(m.state_dict()))
-    m = m.to(cuda).to(torch.bfloat16).to(memory_format=torch.channels_last)
+    m = m.to(cuda).to(ops.h16()).to(memory_format=torch.channels_last)
     x = synth.rgb_frames(smooth=True, tag="rt", n_cam=2, h=192, w=480).permute(0, 3, 1, 2).float().to(cuda) / 255.
     with torch.no_grad():
         m.use_umma_trunk = False
@@ -200,13 +201,12 @@ def test_resnet_trunk_on_umma_matches_cudnn(cuda):
         got = m(x).float()
     assert got.shape == want.shape == (2, 512, 6, 15)
     rms = float(((got - want) ** 2).mean().sqrt() / (want ** 2).mean().sqrt())
-    assert rms < 2e-2, rms            # both paths are bf16 with different rounding points (cuDNN keeps BN folded in the weights)
+    assert rms < 5e-3, rms            # both paths are f16 with different rounding points (cuDNN keeps BN folded in the weights)
 
 
 @pytest.mark.parametrize("kind", ["blobs", "noise", "flat"])
 def test_det_peaks_kernel_matches_reference_decode(cuda, kind):
     """CUDA decode (sigmoid + 7x7 NMS + top-15 + map reads) vs the torch restatement of extract_peak / det_inference."""
-    from lav_b200 import ops
     from lav_b200.model_inference import InferModel
     g = synth._gen(17, kind)
     B = 3
@@ -233,3 +233,58 @@ def test_det_peaks_kernel_matches_reference_decode(cuda, kind):
             assert sorted(got[b][c]) == sorted(want[b][c]), (kind, b, c)
             if kind == "blobs":
                 assert got[b][c] == want[b][c]            # distinct scores: same (descending) order as torch.topk
+
+
+def test_brake_real_weights_match_reference_golden(cuda, golden_dir):
+    """a19 with the RELEASED weights (weights/bra_v2_9.pt, staged by oracle/pin_against_reference.py): the CUDA paths — fp32
+    forward, and the 16-bit forward_u8 path with the lav_b200 stem / pool kernels — against the reference module's own output
+    (tests/golden/brake.npz["real"]) on the same frames."""
+    import os
+    from lav_b200.heads import RGBBrakePredictionModel
+    path = os.path.join(util.ROOT, "oracle", "_ref", "bra_v2_9.state_dict.pt")
+    gold = np.load(os.path.join(golden_dir, "brake.npz"))
+    if not os.path.exists(path) or "real" not in gold:
+        pytest.skip("oracle/_ref/bra_v2_9.state_dict.pt not staged")
+    sd = torch.load(path, map_location="cpu")
+    n_lab = sd["seg_head.upconv.9.weight"].shape[0]
+    m = RGBBrakePredictionModel(list(range(n_lab - 1))).eval()
+    m.load_state_dict(sd, strict=True)
+    wide_u8 = synth.rgb_frames(smooth=True, tag="wide", n_cam=1, h=288, w=768)         # (1,288,768,3) — the pin script's frames
+    tel_u8 = synth.rgb_frames(smooth=True, tag="tele", n_cam=1, h=192, w=480)
+    m = m.to(cuda)
+    with torch.no_grad():
+        got32 = m(wide_u8.permute(0, 3, 1, 2).float().to(cuda), tel_u8.permute(0, 3, 1, 2).float().to(cuda)).float().cpu()
+    np.testing.assert_allclose(got32.numpy(), gold["real"], atol=1e-4)
+    # 16-bit product path: the three 256-wide cameras side by side ARE the 768-wide image
+    rgbs = wide_u8.view(1, 288, 3, 256, 3).permute(0, 2, 1, 3, 4).contiguous()
+    m.conv_backbone.to(ops.h16()).to(memory_format=torch.channels_last)
+    m.attn1.to(ops.h16()); m.attn2.to(ops.h16())
+    with torch.no_grad():
+        got16 = m.forward_u8(rgbs.to(cuda), tel_u8.to(cuda)).float().cpu()
+    assert abs(float(got16[0]) - float(gold["real"][0])) < 1e-2, (got16, gold["real"])
+
+
+def test_resnet18_folded_weights_follow_the_parameters(cuda):
+    """The BN-folded eval weights are a cache: an optimizer step, a parent's load_state_dict or train()/eval() must never leave
+    a stale fold behind (the reference's per-step pattern: eval() -> infer under no_grad -> train(), lav_final_v2.py:228-236)."""
+    up, usd = uniplanner()
+    up = up.to(cuda)
+    emb = up.lidar_conv_emb
+    x = torch.randn(2, 384, 96, 96, generator=torch.Generator().manual_seed(3)).to(cuda)
+    with torch.no_grad():
+        a = emb(x).clone()
+    opt = torch.optim.SGD(emb.parameters(), lr=0.5)
+    emb.train()
+    emb(x).sum().backward()
+    opt.step()
+    emb.eval()
+    with torch.no_grad():
+        b = emb(x).clone()
+        want = emb[0].maxpool(emb[0].relu(emb[0].bn1(emb[0].conv1(x))))
+        want = emb[1:](emb[0].layer4(emb[0].layer3(emb[0].layer2(emb[0].layer1(want)))))
+    assert not torch.allclose(a, b), "fold cache survived an optimizer step"
+    assert util.rel_err(b, want) < 1e-3
+    up.load_state_dict({k: v.to(cuda) for k, v in usd.items()})              # PARENT load: nn.Module recursion never calls the child's
+    with torch.no_grad():
+        c = emb(x)
+    assert util.rel_err(c, a) < 1e-5, "fold cache survived a parent load_state_dict"

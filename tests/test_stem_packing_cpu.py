@@ -63,12 +63,12 @@ def test_stem_k_order_and_staging(shape):
     img = rng.integers(0, 256, (b, ncam, h, cam_w, 3), dtype=np.uint8)
     w = torch.from_numpy(rng.standard_normal((64, 3, 7, 7)).astype(np.float32) * 0.1)
     wk = ops.pack_stem_weights(w)
-    assert wk.shape == (64, 160) and wk.dtype == torch.bfloat16
+    assert wk.shape == (64, 160) and wk.dtype == ops.h16()
     wq = wk.float().numpy()
     assert np.all(wq.reshape(64, -1)[:, 154:] == 0) and np.all(wq[:, :154].reshape(64, 7, 22)[:, :, 21] == 0)
     got = emulate(img, wq)
     wide = torch.from_numpy(img).permute(0, 2, 1, 3, 4).reshape(b, h, ncam * cam_w, 3).permute(0, 3, 1, 2).float()
     x = (wide / 255. - torch.tensor(MEAN)[None, :, None, None]) / torch.tensor(STD)[None, :, None, None]
-    ref = F.conv2d(x, w.to(torch.bfloat16).float(), None, 2, 3).permute(0, 2, 3, 1).numpy()
+    ref = F.conv2d(x, w.to(ops.h16()).float(), None, 2, 3).permute(0, 2, 3, 1).numpy()
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
