@@ -156,6 +156,85 @@ def workload_config(B, precision, P=1):
             "execution": "two CUDA graphs per step (perception+heads+brake; planner), host decode of detections in between"}
 
 
+def run_train_leg(args, dev, rank, world, lid, uni):
+    """BASELINE config 4: one `train_lidar` step (lav/lav_final_v2.py:140-259: LiDAR model + UniPlanner student vs the frozen
+    teacher, 8 losses, Adam) on `--train-batch` samples per rank, gradients of 18 293 329 parameters averaged over the ranks with
+    a bucketed NCCL all-reduce that overlaps backward.  Every step's batch (lidar 32 x 120 000 x 11 fp32 = 169 MB, maps, BEV) is
+    copied from pinned host memory on a side stream one step ahead (the staging must not be synchronous).
+    Returns the `train` object of the JSON line (rank 0) — timed like the inference legs: events on the device, barrier on both
+    sides, max over ranks."""
+    import copy
+    import torch.distributed as dist
+    from lav_b200.train import LAVTrainer, synthetic_train_batch
+    Bt = args.train_batch
+    tr = LAVTrainer(copy.deepcopy(lid).to(dev), copy.deepcopy(uni).to(dev), device=dev, amp=args.train_amp)
+    host = synthetic_train_batch(Bt, torch.device("cpu"), seed=2021 + rank)
+    host = tuple(t.pin_memory() if torch.is_tensor(t) and t.dim() > 0 else t for t in host)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host if torch.is_tensor(t))
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [None, None]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def stage(i):
+        with torch.cuda.stream(copy_stream):
+            # num_points (index 1) stays on the host: the voxeliser reads it there (no D2H sync in the step)
+            slots[i % 2] = tuple(t.to(dev, non_blocking=True) if torch.is_tensor(t) and k != 1 else t for k, t in enumerate(host))
+            ready[i % 2].record(copy_stream)
+
+    ev_bwd, ev_red = [], []
+    orig_finish = tr.reducer.finish
+
+    def timed_finish():
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        orig_finish()
+        b.record()
+        ev_bwd.append(a); ev_red.append(b)
+    tr.reducer.finish = timed_finish
+
+    def step(i):
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        batch = slots[i % 2]
+        stage(i + 1)                                   # next step's H2D overlaps this step's compute
+        return tr.train_lidar(*batch)
+
+    stage(0)
+    for i in range(args.train_warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    del ev_bwd[:], ev_red[:]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.train_steps):
+        loss, parts = step(args.train_warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    red = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(ev_bwd, ev_red)) / max(1, len(ev_bwd))], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    n_par = sum(p.numel() for p in tr.params if p.requires_grad)
+    out = {"metric": "train_lidar_samples_per_s", "value": world * Bt * args.train_steps / (float(ms) * 1e-3), "unit": "samples/s",
+           "ms_per_step": float(ms) / args.train_steps, "per_rank_batch": Bt, "global_batch": world * Bt, "steps": args.train_steps,
+           "warmup": args.train_warmup, "allreduce_params": n_par, "allreduce_bytes": 4 * n_par,
+           "collective": ("NCCL all-reduce (sum, fp32), %d buckets of <= 25 MB launched from grad hooks in fixed order" % len(tr.reducer.buckets))
+           if world > 1 else "none (1 rank)",
+           "exposed_after_backward_ms": float(red), "h2d_bytes_per_step": int(h2d_bytes), "h2d": "pinned, side stream, one step ahead",
+           "precision": "bf16 autocast forward/backward (cuDNN), fp32 master weights, losses and Adam" if args.train_amp else "fp32 (cuDNN, TF32 off)",
+           "conv_backend": "cuDNN (pillar decorate / scatter-max fwd+bwd: lav_b200 CUDA kernels)",
+           "loss": float(loss), "max_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+    tr.reducer.close()
+    del tr, slots
+    torch.cuda.empty_cache()
+    return out
+
+
 def _dbg(msg):
     if os.environ.get("BENCH_DEBUG"):
         print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
@@ -178,6 +257,11 @@ def main():
     ap.add_argument("--pipelines", type=int, default=2, help="agent groups per GPU that overlap host decode with GPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="run the static pipeline eagerly (debug / ncu launch lists)")
+    ap.add_argument("--no-train", action="store_true", help="skip the train_lidar leg (BASELINE config 4)")
+    ap.add_argument("--train-batch", type=int, default=32, help="train_lidar samples per rank (reference default 32; 8 ranks = 256)")
+    ap.add_argument("--train-steps", type=int, default=6)
+    ap.add_argument("--train-warmup", type=int, default=3)
+    ap.add_argument("--train-amp", action="store_true", default=False, help="bf16 autocast for the training leg (opt-in)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 
@@ -343,6 +427,13 @@ def main():
         roof["pillar"] = entry(pil, "hbm", "GB/s", peaks.get("hbm_gbs", 6650.0), 1e9)
         roof["pillar"]["kernel"] = "pillar encoder (count, scan+zero-fill, fill, encode)"
         roof["pillar"]["traffic"] = 662e6 / 16 * Bp                          # profiles/r01_kernels.md §6 (v3 encoder)
+    train = None
+    if not args.no_train:
+        for pp in pipes:                      # free the inference graphs' pools before the 22 GB training step
+            pp._g1 = None; pp._g2 = {}
+        torch.cuda.empty_cache()
+        train = run_train_leg(args, dev, rank, world, lid, uni)
+        _dbg(f"train leg done: {train['ms_per_step']:.1f} ms/step")
     if rank == 0:
         frames = world * B * args.steps
         line = {"metric": "agent_frames_per_s", "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -352,7 +443,8 @@ def main():
                         "h2d_bytes_per_step": int(h_rgbs.numel() + h_tels.numel() + h_lidar.numel() * 4),
                         "d2h_bytes_per_step": int(B * 20 * 2 * 4 + B * 4)},
                 "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": roof.get("umma"), "roofline_heads_conv": roof.get("umma_all"), "roofline_pillar": roof.get("pillar")}
+                "roofline": roof.get("umma"), "roofline_heads_conv": roof.get("umma_all"), "roofline_pillar": roof.get("pillar"),
+                "train": train}
         if not args.no_cpu_baseline and world == 1:      # bounded sample (~10-15 s of host work), rank 0 at N=1 only
             a2 = argparse.Namespace(**vars(args))
             a2.steps, a2.warmup = 24, 2

@@ -167,3 +167,27 @@ def fill_state_dict_(sd, seed=SEED):
 def _is_transposed_key(k):
     # Head.net.3 (lidar.py:155), ERFNet UpsamplerBlock.conv / decoder.output_conv (erfnet.py:102,122)
     return k.endswith("_head.net.3.weight") or ("decoder.layers.0.conv" in k) or ("decoder.layers.3.conv" in k)
+
+
+def loss_block_inputs(B=4, K=5, seed=SEED, num_cmds=6, num_plan=20, num_plan_iter=5):
+    """Seeded stand-ins for everything the loss block of LAV.train_lidar consumes (lav/lav_final_v2.py:177-225): the five
+    LiDARModel outputs, the eleven UniPlanner outputs and the targets.  Used by oracle/pin_against_reference.py (which feeds
+    them to the REFERENCE's own train_lidar through stub sub-models) and by the tests (which feed lav_b200.train)."""
+    g = _gen(seed, f"lossblock{B}")
+    r = lambda *s: torch.randn(*s, generator=g)
+    u = lambda *s: torch.rand(*s, generator=g)
+    outs = (r(B, 384, 8, 8), r(B, 2, 320, 320) * 2, u(B, 2, 320, 320) * 3, r(B, 2, 320, 320), torch.sigmoid(r(B, 3, 320, 320)))
+    planner = (r(K, num_plan, 2), r(K, num_cmds, num_plan, 2), torch.sigmoid(r(K, num_cmds)), r(K, num_cmds, num_plan, 2),
+               torch.sigmoid(r(K, num_cmds)), r(B, num_plan, 2), r(B, num_plan_iter, num_cmds, num_plan, 2),
+               r(B, num_cmds, num_plan, 2), torch.sigmoid(r(B, num_cmds)), r(B, num_cmds, num_plan, 2),
+               r(B, num_plan_iter, num_cmds, num_plan, 2))
+    yy, xx = torch.meshgrid(torch.arange(320.), torch.arange(320.), indexing="ij")
+    heat = torch.zeros(B, 2, 320, 320)
+    for b in range(B):
+        for k in range(5):
+            cx, cy = (u(2) * 320).tolist()
+            heat[b, k % 2] = torch.maximum(heat[b, k % 2], torch.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / 18.0))
+    targets = dict(heatmaps=heat, sizemaps=u(B, 2, 320, 320) * 3, orimaps=r(B, 2, 320, 320),
+                   bev=(u(B, 9, 320, 320) > 0.7).to(torch.uint8), ego_locs=r(B, num_plan + 1, 2),
+                   cmds=torch.randint(0, num_cmds, (B,), generator=g), bras=torch.tensor([0, 1, 0, 0][:B] + [0] * max(0, B - 4)))
+    return outs, planner, targets

@@ -15,6 +15,7 @@ frozen BEVPlanner teacher under no_grad (lav_b200/heads.py, pinned bit-exact aga
 motion losses of lav_final_v2.py:190-225.
 """
 import contextlib
+import dataclasses
 
 import torch
 import torch.distributed as dist
@@ -39,34 +40,103 @@ def lidar_model_train_forward(model, lidars, num_points):
 
 
 # --------------------------------------------------------------------------- losses
+# The eight loss terms of LAV.train_lidar (lav/lav_final_v2.py:177-225 + lav/models/loss.py:5-27), written as pure functions
+# of the model outputs so they can be pinned against the reference's own train_lidar (oracle/pin_against_reference.py runs
+# it on stub sub-models -> tests/golden/train_losses.npz).
+@dataclasses.dataclass
+class LossConfig:
+    """config_v2.yaml:14-18,48,57-62 (`distill` is read by train_lidar but absent from the released configs: explicit here)."""
+    box_weight: float = 1.0
+    ori_weight: float = 1.0
+    seg_weight: float = 2.0
+    perception_weight: float = 4.0
+    other_weight: float = 0.5
+    cmd_weight: float = 0.1
+    cmd_smooth: float = 0.2
+    branch_weights: tuple = (5, 5, 5, 1, 1, 1)
+    distill: bool = True
+    perceive_only: bool = False
+    motion_only: bool = False
+
+
+def _weighted_ratio(values, weights):
+    """mean(values * weights) / mean(weights): the focal-style normalisation of loss.py:21-24 (the weights broadcast over
+    channels, so the two means run over different element counts — kept as two means on purpose)."""
+    return (values * weights).mean() / weights.mean()
+
+
+def detection_losses(pred_heat, heat, pred_size, size, pred_ori, ori):
+    """DetLoss.forward (lav/models/loss.py:14-27) -> (heat-map, box, orientation) losses.
+    Heat-map: per-pixel BCE-with-logits weighted by the probability of being WRONG, sigmoid(logit * (1 - 2 target));
+    box / orientation: smooth-L1 weighted by the per-pixel peak of the target heat-maps."""
+    wrong = torch.sigmoid(pred_heat * (1.0 - 2.0 * heat))
+    peak = heat.amax(dim=1, keepdim=True)
+    hm = _weighted_ratio(F.binary_cross_entropy_with_logits(pred_heat, heat, reduction="none"), wrong)
+    box = _weighted_ratio(F.smooth_l1_loss(pred_size, size, reduction="none"), peak)
+    ang = _weighted_ratio(F.smooth_l1_loss(pred_ori, ori, reduction="none"), peak)
+    return hm, box, ang
+
+
 class DetLoss(nn.Module):
-    """CenterNet-style detection loss, lav/models/loss.py:5-27."""
+    """module form with the reference's name and call signature (lav/models/loss.py:5)."""
 
     def forward(self, pred_heatmaps, heatmaps, pred_sizemaps, sizemaps, pred_orimaps, orimaps):
-        size_w, _ = heatmaps.max(dim=1, keepdim=True)
-        p_det = torch.sigmoid(pred_heatmaps * (1 - 2 * heatmaps))
-        det_loss = (F.binary_cross_entropy_with_logits(pred_heatmaps, heatmaps, reduction='none') * p_det).mean() / p_det.mean()
-        box_loss = (size_w * F.smooth_l1_loss(pred_sizemaps, sizemaps, reduction='none')).mean() / size_w.mean()
-        ori_loss = (size_w * F.smooth_l1_loss(pred_orimaps, orimaps, reduction='none')).mean() / size_w.mean()
-        return det_loss, box_loss, ori_loss
+        return detection_losses(pred_heatmaps, heatmaps, pred_sizemaps, sizemaps, pred_orimaps, orimaps)
 
 
 def build_seg_mask(w=320, h=320, cx=160, cy=280, radius_x=240, radius_y=240):
-    """lav_final_v2.py:261-271."""
-    x, y = torch.arange(w), torch.arange(h)
-    gx = (-((x[:, None] - cx) / radius_x) ** 2).exp()
-    gy = (-((y[:, None] - cy) / radius_y) ** 2).exp()
-    gaussian, _ = (gx[None] * gy[:, None]).max(dim=-1)
-    return gaussian
+    """LAV.build_seg_mask (lav_final_v2.py:261-271): an (h, w) Gaussian bump centred on the ego (the reference builds it as a
+    max over a trailing singleton axis of the outer product of the two 1-D profiles)."""
+    gx = torch.exp(-((torch.arange(w, dtype=torch.float32) - cx) / radius_x) ** 2)
+    gy = torch.exp(-((torch.arange(h, dtype=torch.float32) - cy) / radius_y) ** 2)
+    return gy[:, None] * gx[None, :]
+
+
+def train_losses(outs, planner_out, heatmaps, sizemaps, orimaps, bev, ego_locs, cmds, bras, seg_mask, cfg=None, branch_weights=None):
+    """-> (total loss, dict of the 8 terms).  outs = LiDARModel outputs (features, heat logits, sizes, orientations, sigmoid BEV);
+    planner_out = the 11 UniPlanner.forward outputs; targets as LAV.train_lidar receives them."""
+    cfg = cfg or LossConfig()
+    _, pred_heat, pred_size, pred_ori, pred_bev = outs
+    (other_next, other_cast, other_cmds, other_cast_teacher, other_cmds_teacher, _ego_next, ego_plan, ego_cast, ego_cmds,
+     ego_cast_teacher, ego_plan_teacher) = planner_out
+    cmds = cmds.long()
+    rows = torch.arange(cmds.shape[0], device=cmds.device)
+    hm, box, ang = detection_losses(pred_heat, heatmaps, pred_size, sizemaps, pred_ori, orimaps)
+    det = hm + cfg.box_weight * box + cfg.ori_weight * ang
+    seg = (F.binary_cross_entropy(pred_bev, bev.float()[:, :3], reduction="none") * seg_mask).mean() * cfg.seg_weight
+    # plan: every refinement iteration and every command branch regresses the teacher's LAST-iteration plan of the COMMANDED
+    # branch; per-sample mean, weighted by the branch weight of that sample's command
+    bw = branch_weights if branch_weights is not None else torch.tensor(cfg.branch_weights, dtype=torch.float32, device=ego_plan.device)
+    goal = ego_plan_teacher[rows, -1, cmds]                                                   # (B, T, 2)
+    plan = ((ego_plan - goal[:, None, None]).abs().flatten(1).mean(1) * bw[cmds]).mean()
+    if cfg.distill:
+        ego_c = (ego_cast - ego_cast_teacher).abs().mean()
+        other_c = (other_cast - other_cast_teacher).abs().mean()
+        cmd = F.binary_cross_entropy(other_cmds, other_cmds_teacher)
+    else:
+        moving = (1 - bras).bool().to(cmds.device)                                             # samples without a brake label
+        ego_c = (ego_cast[rows, cmds] - ego_locs[:, 1:].float()).abs().flatten(1).mean(1)[moving].mean()
+        other_c = (other_cast - other_next[:, None]).abs().mean(dim=(2, 3)).amin(dim=1).mean()   # best branch per vehicle
+        k = ego_cmds.shape[1]
+        cmd = F.binary_cross_entropy(ego_cmds, (1.0 - cfg.cmd_smooth) * F.one_hot(cmds, k) + cfg.cmd_smooth / k)
+    motion = plan + ego_c + cfg.other_weight * other_c + cfg.cmd_weight * cmd
+    if cfg.perceive_only:
+        total = det + seg
+    elif cfg.motion_only:
+        total = motion
+    else:
+        total = motion + cfg.perception_weight * (det + seg)
+    return total, dict(hm_loss=hm, box_loss=box, ori_loss=ang, seg_loss=seg, plan_loss=plan, ego_cast_loss=ego_c,
+                       other_cast_loss=other_c, cmd_loss=cmd)
 
 
 def perception_loss(outs, heatmaps, sizemaps, orimaps, seg_bev, seg_mask, box_weight=1.0, ori_weight=1.0, seg_weight=2.0):
-    """det_loss + seg_loss of train_lidar (lav_final_v2.py:177-188,249-250)."""
+    """det_loss + seg_loss only (the --perceive-only branch, lav_final_v2.py:177-188,249-250)."""
     _, ph, ps, po, pb = outs
-    hm, box, ori = DetLoss()(ph, heatmaps, ps, sizemaps, po, orimaps)
-    det = hm + box_weight * box + ori_weight * ori
-    seg = torch.mean(F.binary_cross_entropy(pb, seg_bev, reduction='none') * seg_mask) * seg_weight
-    return det + seg, dict(hm_loss=hm.detach(), box_loss=box.detach(), ori_loss=ori.detach(), seg_loss=seg.detach())
+    hm, box, ang = detection_losses(ph, heatmaps, ps, sizemaps, po, orimaps)
+    seg = (F.binary_cross_entropy(pb, seg_bev, reduction="none") * seg_mask).mean() * seg_weight
+    return hm + box_weight * box + ori_weight * ang + seg, dict(hm_loss=hm.detach(), box_loss=box.detach(), ori_loss=ang.detach(),
+                                                                seg_loss=seg.detach())
 
 
 # --------------------------------------------------------------------------- data-parallel gradient exchange
@@ -74,8 +144,14 @@ class GradAllReducer:
     """Bucketed, overlapped gradient all-reduce (mean) for one-process-per-GPU data parallelism.
 
     Parameters are packed into flat buckets in reverse registration order (the order autograd finishes them);
-    when the last gradient of a bucket has been accumulated its all-reduce starts asynchronously (NCCL on GPUs,
-    gloo in the CPU tests) and ``finish()`` waits for all buckets and scatters the averaged values back.
+    when the last gradient of a bucket has been accumulated — and every earlier bucket has been launched — its all-reduce
+    starts asynchronously (NCCL on GPUs, gloo in the CPU tests); ``finish()`` waits for all buckets and scatters the averaged
+    values back.
+
+    Normalisation note: the reference trains under nn.DataParallel, whose losses see the GATHERED full batch, so its ratio terms
+    (``(...).mean() / p_det.mean()``, ``/ size_w.mean()``, ``[idxs].mean()``, lav/models/loss.py:14-24, lav_final_v2.py:205) are
+    normalised over all samples.  Here every rank normalises over its own sub-batch and the gradients are averaged: identical
+    when the per-rank normalisers are equal, a per-rank re-weighting of those loss terms otherwise (standard DDP behaviour).
     """
 
     def __init__(self, params, bucket_bytes=25 << 20, group=None):
@@ -106,24 +182,36 @@ class GradAllReducer:
     def reset(self):
         self._pending = [len(b) for b in self.buckets]
         self._works = [None] * len(self.buckets)
+        self._next = 0            # buckets are reduced STRICTLY in index order: every rank issues the same collectives in the
+                                  # same order even when the set of parameters that received a gradient differs between ranks
+
+    def _launch_ready(self):
+        while self._next < len(self.buckets) and self._pending[self._next] == 0:
+            bi = self._next
+            if self.world > 1:
+                self._works[bi] = dist.all_reduce(self._flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._next += 1
 
     def _on_grad(self, p):
         bi, off = self._where[p]
         self._flat[bi][off:off + p.numel()].copy_(p.grad.reshape(-1))
         self._pending[bi] -= 1
-        if self._pending[bi] == 0 and self.world > 1:
-            self._works[bi] = dist.all_reduce(self._flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        if self._pending[bi] == 0:
+            self._launch_ready()
 
     def finish(self):
-        """wait for the exchanges and write the averaged gradients back into ``p.grad``; call before optimizer.step()."""
+        """wait for the exchanges and write the averaged gradients back into ``p.grad``; call before optimizer.step().
+        Buckets with a parameter that received no gradient this step are completed with zeros and reduced here, still in
+        index order."""
         for bi, b in enumerate(self.buckets):
-            if self._pending[bi] != 0:      # a parameter received no gradient this step: reduce what is there
+            if self._pending[bi] != 0:
                 for p in b:
                     if p.grad is None:
                         _, off = self._where[p]
                         self._flat[bi][off:off + p.numel()].zero_()
-                if self.world > 1:
-                    self._works[bi] = dist.all_reduce(self._flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                self._pending[bi] = 0
+        self._launch_ready()
+        for bi, b in enumerate(self.buckets):
             if self._works[bi] is not None:
                 self._works[bi].wait()
             if self.world > 1:
@@ -188,8 +276,8 @@ class LAVTrainer:
         self.reducer = GradAllReducer(params, bucket_bytes)
         self.seg_mask = build_seg_mask().to(self.device)
         self.branch_weights = torch.tensor(branch_weights).float().to(self.device)
-        self.w = dict(box=box_weight, ori=ori_weight, seg=seg_weight, perc=perception_weight, other=other_weight, cmd=cmd_weight)
-        self.distill, self.cmd_smooth = distill, cmd_smooth
+        self.cfg = LossConfig(box_weight, ori_weight, seg_weight, perception_weight, other_weight, cmd_weight, cmd_smooth,
+                              tuple(branch_weights), distill, perceive_only, motion_only)
         self.perceive_only, self.motion_only = perceive_only, motion_only
         # amp=True: model forwards under bf16 autocast (fp32 master weights, losses and Adam in fp32).  The reference trains in
         # fp32 (cuDNN TF32); this is an opt-in throughput mode, off by default and not yet measured.
@@ -198,43 +286,15 @@ class LAVTrainer:
     def losses(self, lidars, num_points, heatmaps, sizemaps, orimaps, bev, ego_locs, cmds, nxps, bras, locs, oris, typs):
         up = self.uniplanner
         bev = bev.float()
-        seg_bev = bev[:, [0, 1, 2]]
-        cmds = cmds.long()
-        idxs = (1 - bras).bool()
         ctx = torch.autocast("cuda", dtype=torch.bfloat16) if self.amp else contextlib.nullcontext()
         with ctx:
             outs = self.lidar_model(lidars, num_points)
-            features, ph, ps, po, pb = outs
-            planner_out = up(features, bev, ego_locs.float(), locs.float(), oris.float(), nxps.float(), typs)
+            planner_out = up(outs[0], bev, ego_locs.float(), locs.float(), oris.float(), nxps.float(), typs)
         if self.amp:       # losses in fp32
-            ph, ps, po, pb = ph.float(), ps.float(), po.float(), pb.float()
+            outs = tuple(t.float() for t in outs)
             planner_out = tuple(t.float() if torch.is_floating_point(t) else t for t in planner_out)
-        (other_next_locs, other_cast_locs, other_cast_cmds, other_cast_locs_expert, other_cast_cmds_expert, ego_next_locs,
-         ego_plan_locs, ego_cast_locs, ego_cast_cmds, ego_cast_locs_expert, ego_plan_locs_expert) = planner_out
-        hm, box, ori = DetLoss()(ph, heatmaps, ps, sizemaps, po, orimaps)
-        det_loss = hm + self.w["box"] * box + self.w["ori"] * ori
-        seg_loss = torch.mean(F.binary_cross_entropy(pb, seg_bev, reduction='none') * self.seg_mask) * self.w["seg"]
-        T = up.num_plan
-        gather_idx = cmds.expand(T, 2, 1, -1).permute(3, 2, 0, 1)
-        target = ego_plan_locs_expert[:, -1].gather(1, gather_idx).unsqueeze(1).repeat(1, up.num_plan_iter, up.num_cmds, 1, 1)
-        plan_loss = torch.mean(F.l1_loss(ego_plan_locs, target, reduction='none').mean(dim=[1, 2, 3, 4]) * self.branch_weights[cmds])
-        if self.distill:
-            ego_cast_loss = F.l1_loss(ego_cast_locs, ego_cast_locs_expert)
-            other_cast_loss = F.l1_loss(other_cast_locs, other_cast_locs_expert)
-            cmd_loss = F.binary_cross_entropy(other_cast_cmds, other_cast_cmds_expert)
-        else:
-            ego_cast_loss = F.l1_loss(ego_cast_locs.gather(1, gather_idx).squeeze(1), ego_locs[:, 1:].float(), reduction='none').mean(dim=[1, 2])[idxs].mean()
-            other_cast_loss = F.l1_loss(other_cast_locs, other_next_locs.unsqueeze(1).repeat(1, up.num_cmds, 1, 1), reduction='none').mean(dim=[2, 3]).min(1)[0].mean()
-            cmd_loss = F.binary_cross_entropy(ego_cast_cmds, (1. - self.cmd_smooth) * F.one_hot(cmds, up.num_cmds) + self.cmd_smooth / up.num_cmds)
-        mot_loss = plan_loss + ego_cast_loss + other_cast_loss * self.w["other"] + cmd_loss * self.w["cmd"]
-        if self.perceive_only:
-            loss = det_loss + seg_loss
-        elif self.motion_only:
-            loss = mot_loss
-        else:
-            loss = mot_loss + (det_loss + seg_loss) * self.w["perc"]
-        parts = dict(hm_loss=hm, box_loss=box, ori_loss=ori, seg_loss=seg_loss, plan_loss=plan_loss, ego_cast_loss=ego_cast_loss,
-                     other_cast_loss=other_cast_loss, cmd_loss=cmd_loss)
+        loss, parts = train_losses(outs, planner_out, heatmaps, sizemaps, orimaps, bev, ego_locs, cmds, bras, self.seg_mask, self.cfg,
+                                   self.branch_weights)
         return loss, {k: v.detach() for k, v in parts.items()}
 
     def train_lidar(self, *batch):

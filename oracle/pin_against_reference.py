@@ -261,6 +261,51 @@ def main():
     torch.set_grad_enabled(False)
     np.savez_compressed(os.path.join(GOLD, "uniplanner_train.npz"), **{n: a_.detach().numpy() for n, a_ in zip(names_t, r_out)})
 
+    # ---- train_lidar loss block (a18): the REFERENCE's own LAV.train_lidar, sub-models stubbed ------------------------------
+    print("[train_lidar losses]")
+    import yaml
+    from lav.lav_final_v2 import LAV
+    from lav.models.loss import DetLoss as RefDetLoss
+    from lav_b200 import train as T
+    cfg = yaml.safe_load(open(os.path.join(REF, "config_v2.yaml")))
+    outs_l, planner_l, tg = synth.loss_block_inputs()
+    gold_l = {}
+    for distill in (True, False):
+        for mode in ("full", "perceive_only", "motion_only"):
+            torch.set_grad_enabled(True)
+            leaf = torch.zeros((), requires_grad=True)                      # so that the reference's backward()/step() have a graph
+            obj = object.__new__(LAV)                                       # LAV.__init__ loads checkpoints: set what train_lidar reads
+            for k in ("box_weight", "ori_weight", "seg_weight", "other_weight", "cmd_weight", "perception_weight", "cmd_smooth",
+                      "num_plan", "num_plan_iter", "num_cmds", "pixels_per_meter"):
+                setattr(obj, k, cfg[k])
+            obj.device, obj.distill = torch.device("cpu"), distill
+            obj.perceive_only, obj.motion_only = mode == "perceive_only", mode == "motion_only"
+            obj.branch_weights = torch.tensor(cfg["branch_weights"]).float()
+            obj.det_criterion = RefDetLoss()
+            obj.bev_center = [160.0, 280.0]
+            obj.seg_mask = LAV.build_seg_mask(obj, h=320, w=320, cx=160, cy=280)
+            obj.lidar_model = lambda lidars, num_points: tuple(t + leaf for t in outs_l[:4]) + (outs_l[4],)
+            obj.uniplanner = lambda *a: tuple(t + leaf for t in planner_l)
+            obj.lidar_optim = torch.optim.SGD([leaf], lr=0.0)
+            obj.det_inference = lambda *a, **k: [[], []]
+            obj.mot_inference = lambda *a, **k: (torch.zeros(20, 2), torch.zeros(0, 6, 20, 2), torch.zeros(0, 6))
+            B_ = tg["cmds"].shape[0]
+            res = LAV.train_lidar(obj, torch.zeros(B_, 4, 11), torch.tensor([4] * B_), tg["heatmaps"], tg["sizemaps"], tg["orimaps"], tg["bev"],
+                                  tg["ego_locs"], tg["cmds"], torch.zeros(B_, 2), tg["bras"], torch.zeros(B_, 6, 21, 2), torch.zeros(B_, 6),
+                                  torch.zeros(B_, 6).long(), torch.tensor([6] * B_))
+            torch.set_grad_enabled(False)
+            names_l = ["hm_loss", "box_loss", "ori_loss", "seg_loss", "plan_loss", "ego_cast_loss", "other_cast_loss", "cmd_loss"]
+            ref_l = np.array([res[k] for k in names_l], dtype=np.float64)
+            mine, parts = T.train_losses(outs_l, planner_l, tg["heatmaps"], tg["sizemaps"], tg["orimaps"], tg["bev"], tg["ego_locs"],
+                                         tg["cmds"], tg["bras"], T.build_seg_mask(), T.LossConfig(distill=distill, perceive_only=obj.perceive_only,
+                                                                                             motion_only=obj.motion_only))
+            my_l = np.array([float(parts[k]) for k in names_l])
+            d = float(np.abs(ref_l - my_l).max() / (np.abs(ref_l).max()))
+            print(f"  distill={distill} {mode:14s} max rel |ref-mine| over the 8 losses = {d:.2e}")
+            assert d < 1e-5
+            gold_l[f"{'distill' if distill else 'nodistill'}_{mode}"] = ref_l
+    np.savez_compressed(os.path.join(GOLD, "train_losses.npz"), names=np.array(names_l), **gold_l)
+
     # ---- brake model (a19) -------------------------------------------------------------------------
     print("[brake]")
     bra = RGBBrakePredictionModel([4, 6, 7, 10], pretrained=False).eval()
