@@ -96,22 +96,21 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(args, rank, world):
-    """the reference's own CPU implementation of the frame path (oracle port of its PyTorch modules) on the host cores."""
-    if rank != 0:
-        return
-    if os.environ.get("BENCH_DEBUG"):
-        import faulthandler
-        faulthandler.dump_traceback_later(int(os.environ["BENCH_DEBUG"]), exit=True)
+def _reference_frame_fn(device, cores=None):
+    """-> (frame(), kind, description): one whole agent frame through the reference's own implementation.  kind "reference" =
+    the UNMODIFIED reference modules staged in baseline/_ref (oracle/ref_runner.py); "port" = the oracle restatement
+    (oracle/lav_ref.py) when the staged sources are absent."""
+    from oracle import ref_runner as RR
+    rgbs, tels, lidars, prev, poses = synth_frames(1)
+    if RR.available():
+        rf = RR.ReferenceFrame(device, FIXED_DETS)
+
+        def frame():
+            return rf(rgbs[0], tels[0], lidars[0], prev[0], poses[0][0], poses[0][1], [0.0, -20.0], 3)[:2]
+        return frame, "reference", "unmodified reference modules (baseline/_ref: team_code_v2 InferModel with jit-scripted backbone/heads, RGBSegmentationModel, RGBBrakePredictionModel) + torch_scatter/carla stand-ins"
     from oracle import lav_ref as O
-    # all the host threads the path can USE: on the 2-socket 128-thread box oneDNN's small convs (ResNet-18 on 3x3..6x6
-    # maps) collapse under 128-way fork-join (measured: one 7x7 conv 0.02 s @32 threads, 0.28 s @128, the whole frame
-    # never finished in 100 s), so the port is timed at min(cpu_count, 32) threads and says so in `cores`.
-    cores = min(os.cpu_count() or 1, int(os.environ.get("LAVB_CPU_THREADS", 32)))
-    torch.set_num_threads(cores)
     _, sds = build_models()
     sd_seg, sd_lid, sd_uni, sd_bra = sds
-    rgbs, tels, lidars, prev, poses = synth_frames(1)
     convs = O.default_converters()
     grid = dict(min_x=-10, max_x=70, min_y=-40, max_y=40)
 
@@ -127,23 +126,70 @@ def run_reference(args, rank, world):
             out = O.uniplanner_infer(sd_uni, f[0], FIXED_DETS, 3, torch.tensor([0.0, -20.0]))
             wide = rgbs[0].permute(1, 0, 2, 3).reshape(288, 768, 3).permute(2, 0, 1)[None].float()
             bra = O.brake_model(sd_bra, wide, tels[:1].permute(0, 3, 1, 2).float())
-            return out[1], bra
+            return out[1], float(bra)
+    return frame, "port", "oracle/lav_ref.py restatement of the reference modules"
+
+
+def run_reference(args, rank, world, return_outputs=False):
+    """the reference's own CPU implementation of the frame path on the host cores (one whole frame per step)."""
+    if rank != 0:
+        return
+    if os.environ.get("BENCH_DEBUG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_DEBUG"]), exit=True)
+    # all the host threads the path can USE: on the 2-socket 128-thread box oneDNN's small convs (ResNet-18 on 3x3..6x6
+    # maps) collapse under 128-way fork-join (measured: one 7x7 conv 0.02 s @32 threads, 0.28 s @128, the whole frame
+    # never finished in 100 s), so the path is timed at min(cpu_count, 32) threads and says so in `cores`.
+    cores = min(os.cpu_count() or 1, int(os.environ.get("LAVB_CPU_THREADS", 32)))
+    torch.set_num_threads(cores)
+    frame, kind, what = _reference_frame_fn("cpu")
     for _ in range(args.warmup):
         tw = time.perf_counter()
-        frame()
+        out = frame()
         _dbg(f"reference warm-up frame {time.perf_counter() - tw:.2f} s on {cores} threads")
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        frame()
+        out = frame()
     dt = time.perf_counter() - t0
     v = args.steps / dt
     line = {"impl": "reference", "metric": "agent_frames_per_s", "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32", "data": "synthetic", "config": workload_config(1, "fp32"),
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} whole frames (1 frame per step) through oracle/lav_ref.py on {cores} host threads"},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
+                             "sample": f"{args.steps} whole frames (1 frame per step, batch 1 like the agent) through the {what} on {cores} host threads"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+    if return_outputs:
+        return out
+
+
+def run_gpu_reference(dev, steps=10, warmup=3):
+    """The north_star's denominator: the reference's own PyTorch-CUDA frame path (team_code_v2 InferModel + seg + brake modules,
+    driven like lav_agent_fast.run_step, batch 1, host sensor tensors in, waypoints + brake read back) on the SAME B200."""
+    from oracle import ref_runner as RR
+    if not RR.available():
+        return {"unavailable": "baseline/_ref not staged (run __graft_entry__.build() where /root/reference exists)"}
+    prev_tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    frame, kind, what = _reference_frame_fn(dev)
+    try:
+        for _ in range(warmup):
+            frame()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            out = frame()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": 1e3 / ms, "unit": "frames/s", "ms_per_frame": ms, "wall_ms_per_frame": 1e3 * wall / steps, "batch": 1, "steps": steps,
+            "warmup": warmup, "dtype": "fp32 (PyTorch defaults: cuDNN TF32 convs allowed)", "what": what,
+            "driven_like": "team_code_v2/lav_agent_fast.py:run_step model calls (seg -> paint -> stack -> InferModel pieces -> brake), host tensors in, results read back",
+            "outputs": {"plan0": [float(x) for x in out[0][0]], "brake": float(out[1])}}
 
 
 def workload_config(B, precision, P=1):
@@ -226,7 +272,7 @@ def run_train_leg(args, dev, rank, world, lid, uni):
            "collective": ("NCCL all-reduce (sum, fp32), %d buckets of <= 25 MB launched from grad hooks in fixed order" % len(tr.reducer.buckets))
            if world > 1 else "none (1 rank)",
            "exposed_after_backward_ms": float(red), "h2d_bytes_per_step": int(h2d_bytes), "h2d": "pinned, side stream, one step ahead",
-           "precision": "bf16 autocast forward/backward (cuDNN), fp32 master weights, losses and Adam" if args.train_amp else "fp32 (cuDNN, TF32 off)",
+           "precision": "bf16 autocast forward/backward (cuDNN), fp32 master weights, losses and Adam" if args.train_amp else "fp32 tensors, PyTorch defaults (cuDNN convolutions may use TF32, as in the reference trainer)",
            "conv_backend": "cuDNN (pillar decorate / scatter-max fwd+bwd: lav_b200 CUDA kernels)",
            "loss": float(loss), "max_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
     tr.reducer.close()
@@ -257,6 +303,8 @@ def main():
     ap.add_argument("--pipelines", type=int, default=2, help="agent groups per GPU that overlap host decode with GPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="run the static pipeline eagerly (debug / ncu launch lists)")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference-modules-on-this-GPU leg and the batch-1 latency leg")
+    ap.add_argument("--vary-k", action="store_true", help="planner fed a different number of vehicles every step (0..15 per frame) instead of the fixed K=3")
     ap.add_argument("--no-train", action="store_true", help="skip the train_lidar leg (BASELINE config 4)")
     ap.add_argument("--train-batch", type=int, default=32, help="train_lidar samples per rank (reference default 32; 8 ranks = 256)")
     ap.add_argument("--train-steps", type=int, default=6)
@@ -307,7 +355,13 @@ def main():
         # decoded on the host while the other groups' GPU work is still running
         for pi, pp in enumerate(pipes):
             pp.begin(r[sl[pi]], t[sl[pi]], l[sl[pi]], nxps[sl[pi]], cmds[sl[pi]], poses=step_poses[sl[pi]])
+        if args.vary_k:        # K differs per step (bucketed G2 graphs, agent.py): the cost of real, varying detection counts
+            k = vary_k_state[0] = (vary_k_state[0] * 5 + 3) % 16
+            dets = [(100.0 + 7 * j, 120.0 + 9 * j, 8.0, 4.0, 0.9, 0.3) for j in range(k)]
+            return [pp.finish(fixed_dets=dets) for pp in pipes]
         return [pp.finish(fixed_dets=FIXED_DETS) for pp in pipes]
+
+    vary_k_state = [0]
 
     def step_resident(i):
         return run(*d_sets[i % 2])
@@ -375,6 +429,9 @@ def main():
     _dbg("first step done")
     sampler = ClockSampler(local) if rank == 0 else None
     ms, t0, t1 = timed(step_resident, args.steps, args.warmup)
+    o_last = step_resident(0)
+    torch.cuda.synchronize()
+    ours0 = (o_last[0]["ego_plan_locs"][0].float().cpu(), float(o_last[0]["pred_bra"][0]))       # agent 0 of group 0 = the reference arm's frame
     # lav_b200 kernels per step = those recorded in the two graphs (replays do not pass through ops.py) + the FIFO copy
     launches = args.steps * sum(sum(pp._launches[:2]) for pp in pipes)
     _dbg(f"timed resident loop done: {ms / args.steps:.2f} ms/step")
@@ -396,6 +453,11 @@ def main():
     except OSError:
         pass
     src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    traffic = {}      # dram__bytes_read+write per launch from committed ncu captures AT THE BENCH BATCH (scripts/ncu_traffic.sh);
+    try:              # used only when the capture's frames-per-launch equals this run's, else `traffic` stays null
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    except OSError:
+        pass
 
     def entry(rows, bound, unit, peak, scale):
         work, tms = sum(r[0] for r in rows), sum(r[1] for r in rows)
@@ -420,13 +482,19 @@ def main():
             roof["umma_all"] = entry(umma[hk[0]], "tensor", "TFLOP/s", peaks.get("bf16_tflops", 1700.0), 1e12)
             roof["umma_all"]["peak_kind"] = "burst (bf16_tflops)"
             roof["umma_all"]["kernel"] = "conv_umma_kernel " + hk[0]
-            roof["umma_all"]["traffic"] = 225.5e6 / 8 * Bp
-            roof["umma_all"]["ncu_tensor_pipe_pct"] = 83.7
+            tr_ = traffic.get("heads_conv", {})
+            if tr_.get("frames") == Bp:          # DRAM bytes of THIS launch shape from the stored `ncu --set full` capture
+                roof["umma_all"]["traffic"] = tr_["dram_bytes"]
+                roof["umma_all"]["ncu_tensor_pipe_pct"] = tr_.get("tensor_pipe_pct")
+                roof["umma_all"]["traffic_source"] = tr_.get("source")
     pil = [(w, a.elapsed_time(b)) for k, w, a, b in prof if k == "pillar"]
     if pil:
         roof["pillar"] = entry(pil, "hbm", "GB/s", peaks.get("hbm_gbs", 6650.0), 1e9)
-        roof["pillar"]["kernel"] = "pillar encoder (count, scan+zero-fill, fill, encode)"
-        roof["pillar"]["traffic"] = 662e6 / 16 * Bp                          # profiles/r01_kernels.md §6 (v3 encoder)
+        roof["pillar"]["kernel"] = "pillar encoder (%s: all its launches)" % ops.PILLAR_ENCODER
+        tr_ = traffic.get("pillar_" + ops.PILLAR_ENCODER, {})
+        if tr_.get("frames") == Bp:
+            roof["pillar"]["traffic"] = tr_["dram_bytes"]
+            roof["pillar"]["traffic_source"] = tr_.get("source")
     train = None
     if not args.no_train:
         for pp in pipes:                      # free the inference graphs' pools before the 22 GB training step
@@ -434,6 +502,37 @@ def main():
         torch.cuda.empty_cache()
         train = run_train_leg(args, dev, rank, world, lid, uni)
         _dbg(f"train leg done: {train['ms_per_step']:.1f} ms/step")
+    latency, gpu_ref = None, None
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        # batch-1 latency of one agent tick (the CARLA agent runs batch 1 at 20 Hz, lav_agent.py:32): host sensors in, waypoints +
+        # brake back on the host, synchronised every tick
+        p1 = StaticFramePipeline(seg, lid, uni, bra, 1, N, device=dev, precision=args.precision)
+        p1.tick = 10
+        loc, ori = poses[0]
+        p1.preload_history(0, [(prev[0][k % 2].to(dev), loc[1 + (k % 2)], ori[1 + (k % 2)]) for k in range(10)])
+        hp, hb = torch.empty((1, 20, 2)).pin_memory(), torch.empty((1,)).pin_memory()
+
+        def tick():
+            o = p1.step(h_rgbs[:1], h_tels[:1], h_lidar[:1], nxps[:1], cmds[:1], poses=step_poses[:1], fixed_dets=FIXED_DETS)
+            hp.copy_(o["ego_plan_locs"], non_blocking=True)
+            hb.copy_(o["pred_bra"].float(), non_blocking=True)
+            torch.cuda.synchronize()
+        for _ in range(5):
+            tick()
+        tl0 = time.perf_counter()
+        nl = 30
+        for _ in range(nl):
+            tick()
+        lat_ms = 1e3 * (time.perf_counter() - tl0) / nl
+        latency = {"ms_per_frame": lat_ms, "frames_per_s": 1e3 / lat_ms, "batch": 1, "ticks": nl, "timing": "host wall clock, torch.cuda.synchronize() every tick",
+                   "path": "StaticFramePipeline(batch=1): pinned host sensors -> 2 CUDA graphs + host decode -> waypoints + brake on the host"}
+        del p1
+        torch.cuda.empty_cache()
+        gpu_ref = run_gpu_reference(dev)
+        if "value" in gpu_ref:
+            gpu_ref["ratio_ours_b1_over_reference"] = latency["frames_per_s"] / gpu_ref["value"]
+            gpu_ref["ratio_ours_throughput_over_reference"] = (world * B * args.steps / (ms_e2e * 1e-3)) / gpu_ref["value"]
+        _dbg("latency + gpu reference legs done")
     if rank == 0:
         frames = world * B * args.steps
         line = {"metric": "agent_frames_per_s", "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -444,16 +543,21 @@ def main():
                         "d2h_bytes_per_step": int(B * 20 * 2 * 4 + B * 4)},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": roof.get("umma"), "roofline_heads_conv": roof.get("umma_all"), "roofline_pillar": roof.get("pillar"),
-                "train": train}
+                "train": train, "latency_b1": latency, "gpu_reference": gpu_ref}
+        line["dtype"] = "fp16 storage, fp32 accumulate (tcgen05 kind::f16 / mma.sync f16; saturating stores)" if args.precision == "f16" else args.precision
         if not args.no_cpu_baseline and world == 1:      # bounded sample (~10-15 s of host work), rank 0 at N=1 only
             a2 = argparse.Namespace(**vars(args))
-            a2.steps, a2.warmup = 24, 2
+            a2.steps, a2.warmup = 16, 2
             import io
             import contextlib
             buf = io.StringIO()
             with contextlib.redirect_stdout(buf):
-                run_reference(a2, 0, 1)
+                ref_out = run_reference(a2, 0, 1, return_outputs=True)
             line["cpu_baseline"] = json.loads(buf.getvalue())["cpu_baseline"]
+            # measured error of THIS run's agent-0 outputs against the reference arm's outputs for the same frame
+            sc = float(ref_out[0].abs().max()) + 1
+            line["parity"] = {"against": line["cpu_baseline"]["kind"], "ego_plan_locs_max_abs_err_over_scale": float((ours0[0] - ref_out[0]).abs().max()) / sc,
+                              "brake_abs_err": abs(ours0[1] - float(ref_out[1])), "tolerance": 1e-2 if args.precision == "f16" else 1e-3}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -65,7 +65,7 @@ int lavb_paint_batched(const float* d_pts, int frames, int n, int pt_stride, lon
  * replaces: Decoder.output_conv = ConvTranspose2d(16, c_cls, 2, stride 2) (lav/models/erfnet.py:122-124,132) + torch.softmax
  *           (lav_agent_fast.py:264) + the background suppression and gather of forward_paint (model_inference.py:44-50,75-93),
  * evaluated for the hit pixel only, so the (h x w x c_cls) logit maps are never materialised.
- * d_feat: NHWC (frames*ncam, h/2, w/2, 16) fp32 or h16 = input of output_conv; d_deconv: 2*2*16*8 + 8 floats =
+ * d_feat: NHWC (frames*ncam, h/2, w/2, 16) fp32 or h16 = input of output_conv; d_deconv: 2*2*16*8 + 8 = 520 floats =
  * w[v%2][u%2][c_in][k] (k >= c_cls zero) | bias[8].  Output row as lavb_paint mode 2: copy_cols point columns, then c_cls-1
  * painted channels at out_col0. */
 int lavb_paint_deconv_batched(const float* d_pts, int frames, int n, int pt_stride, long long pts_frame_stride,

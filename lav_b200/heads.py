@@ -167,9 +167,11 @@ GRU_KERNEL = True     # cluster-persistent plan GRU (csrc/gru_cluster.cu): valid
 
 # ----------------------------------------------------------------------------- planners
 def transform_points(locs, oris):
-    cos, sin = torch.cos(oris), torch.sin(oris)
-    R = torch.stack([torch.stack([cos, sin], dim=-1), torch.stack([-sin, cos], dim=-1)], dim=-2)
-    return locs @ R
+    """rotate row-vector points by `oris` (right-multiplication by [[c, s], [-s, c]], uniplanner.py:319-326):
+    locs (..., T, 2), oris (...)."""
+    c, s_ = torch.cos(oris), torch.sin(oris)
+    rot = torch.stack([c, s_, -s_, c], dim=-1).unflatten(-1, (2, 2))
+    return torch.matmul(locs, rot)
 
 
 def crop_theta(rel_locs, rel_oris, H, W, pixels_per_meter, crop_size, offset_x, offset_y):
@@ -218,7 +220,7 @@ class BEVPlanner(nn.Module):
                              (self.cast(embd) if cast_locs is None else cast_locs).detach(), pixels_per_meter, crop_size)
 
 
-def _plan_rollout(plan_gru, plan_mlp, num_cmds, num_plan, num_plan_iter, embd, nxp, plan_loc, pixels_per_meter, crop_size):
+def _plan_rollout(plan_gru, plan_mlp, num_cmds, num_plan, num_plan_iter, embd, nxp, plan_loc, pixels_per_meter, crop_size, h16_ok=False):
     """plan/_plan of both planners (uniplanner.py:227-259): the six command branches share the GRU, so one call rolls
     6*B sequences; repeated num_plan_iter times feeding its own output."""
     B = embd.size(0)
@@ -227,8 +229,9 @@ def _plan_rollout(plan_gru, plan_mlp, num_cmds, num_plan, num_plan_iter, embd, n
     outs = []
     for _ in range(num_plan_iter):
         u = torch.cat([u0[:, None, None].expand(B, num_cmds, num_plan, 2), plan_loc], dim=3)
-        if GRU_KERNEL and u.is_cuda and not torch.is_grad_enabled() and plan_gru.hidden_size == 512 and plan_gru.input_size == 4:
-            # experimental: the whole 20-step roll-out in one cluster-persistent kernel (csrc/gru_cluster.cu)
+        if GRU_KERNEL and h16_ok and u.is_cuda and not torch.is_grad_enabled() and plan_gru.hidden_size == 512 and plan_gru.input_size == 4:
+            # 16-bit path only (W_hh and the exchanged hidden state are h16 there): the whole 20-step roll-out in one
+            # cluster-persistent kernel (csrc/gru_cluster.cu); the fp32 path keeps cuDNN's fp32 GRU
             whh = plan_gru.weight_hh_l0
             key = (whh.data_ptr(), whh._version, str(whh.device))
             cached = plan_gru.__dict__.get("_whh_h16")
@@ -244,24 +247,25 @@ def _plan_rollout(plan_gru, plan_mlp, num_cmds, num_plan, num_plan_iter, embd, n
     return torch.stack(outs, dim=1)
 
 
-def filter_cars(ego_locs, locs, typs):
-    """uniplanner.py:329-333: only vehicles ahead of the ego."""
-    rel_locs = locs[:, :, 0] - ego_locs[:, 0:1]
-    return typs & (rel_locs[..., 1] < 0)
+def vehicles_ahead(ego_locs, locs, is_vehicle):
+    """mask of the actors a sample may forecast: vehicles whose current position lies ahead of the ego (negative y in the ego
+    frame) — the selection rule of lav/models/uniplanner.py:329-333.  ego_locs (B,T,2), locs (B,N,T,2), is_vehicle (B,N) bool."""
+    ahead = (locs[:, :, 0, 1] - ego_locs[:, None, 0, 1]) < 0
+    return is_vehicle & ahead
 
 
-def random_sample(binaries, size):
-    """uniplanner.py:336-347: keep at most `size` vehicles per sample (same RNG consumption as the reference)."""
-    cut = torch.zeros_like(binaries)
-    for i in range(binaries.size(0)):
-        if binaries[i].sum() <= size:
-            cut[i] = binaries[i]
-        else:
-            nonzero = torch.nonzero(binaries[i]).squeeze(1)
-            idx = torch.multinomial(torch.ones_like(nonzero).float(), size)
-            nonzero = nonzero[idx]
-            cut[i, nonzero] = binaries[i, nonzero]
-    return cut
+def cap_per_sample(mask, limit):
+    """at most `limit` True entries per row of a (B,N) bool mask; rows over the limit keep a uniformly random subset.  One
+    torch.multinomial draw per over-full row, in row order — the random stream consumption of uniplanner.py:336-347, so a
+    seeded run selects the same actors as the reference."""
+    out = mask.clone()
+    for b in range(mask.shape[0]):
+        on = mask[b].nonzero().flatten()
+        if on.numel() > limit:
+            keep = on[torch.multinomial(torch.ones(on.numel()), limit).to(on.device)]
+            out[b] = False
+            out[b, keep] = True
+    return out
 
 
 class UniPlanner(nn.Module):
@@ -313,69 +317,68 @@ class UniPlanner(nn.Module):
         return torch.stack(locs, dim=1)
 
     def plan(self, embd, nxp, cast_locs=None, pixels_per_meter=4, crop_size=96):
+        h16_ok = self.lidar_conv_emb[0].conv1.weight.dtype != torch.float32          # the pipeline cast the embedder: 16-bit path
         return _plan_rollout(self.plan_gru, self.plan_mlp, self.num_cmds, self.num_plan, self.num_plan_iter, embd, nxp,
-                             (self.cast(embd) if cast_locs is None else cast_locs).detach(), pixels_per_meter, crop_size)
+                             (self.cast(embd) if cast_locs is None else cast_locs).detach(), pixels_per_meter, crop_size, h16_ok)
+
+    # ---- training forward ------------------------------------------------------------------------------------------------
+    def _jitter(self, n, device):
+        """augmentation of a crop's pose: lateral offset U(-jx, jx) metres (no longitudinal part) and heading U(-ja, ja).
+        Drawn on the CPU generator as rand(n,2) then rand(n): the reference's stream order (uniplanner.py:83-86,118-121)."""
+        shift = (torch.rand(n, 2) * 2 - 1) * self.feature_x_jitter
+        shift[:, 1] = 0
+        turn = (torch.rand(n) * 2 - 1) * self.feature_angle_jitter
+        return shift.to(device), turn.to(device)
+
+    def _student(self, crops):
+        """crops (n,C,crop,crop) -> (embedding, cast (n,cmds,T,2), command scores (n,cmds)); one call = one BatchNorm batch."""
+        embd = self.lidar_conv_emb(crops)
+        return embd, self.cast(embd), self.cast_cmd_pred(embd)
 
     def forward(self, features, bev, ego_locs, locs, oris, nxps, typs):
-        """Training forward of the student with its frozen teacher (lav/models/uniplanner.py:56-151).  Random jitter
-        is drawn on the CPU in the reference's order, so a seeded run reproduces the reference exactly."""
-        self.bev_planner.eval()
-        ego_oris = oris[:, :1]
-        locs, oris = locs[:, 1:], oris[:, 1:]
-        typs = (typs[:, 1:] == 1)
-        N = locs.size(1)
-        typs = filter_cars(ego_locs, locs, typs)
-        bp = self.bev_planner
-        if int(typs.float().sum()) > 0:
-            typs = random_sample(typs, size=self.max_num_cars)
-            flat_features = features.expand(N, *features.size()).permute(1, 0, 2, 3, 4)[typs]
-            flat_bev = bev.expand(N, *bev.size()).permute(1, 0, 2, 3, 4)[typs]
-            flat_locs = (locs[:, :, 1:] - locs[:, :, :1])[typs]
-            flat_rel_loc0 = (locs[:, :, 0] - ego_locs[:, None, 0])[typs]
-            flat_rel_ori0 = (oris - ego_oris)[typs]
-            K = flat_locs.size(0)
-            locs_jitter = (torch.rand((K, 2)) * 2 - 1).float().to(locs.device) * self.feature_x_jitter
-            locs_jitter[:, 1] = 0
-            oris_jitter = (torch.rand((K,)) * 2 - 1).float().to(oris.device) * self.feature_angle_jitter
-            cropped_other_features = self.crop_feature(flat_features, flat_rel_loc0 + locs_jitter, flat_rel_ori0 + oris_jitter,
-                                                       pixels_per_meter=self.pixels_per_meter / 2, crop_size=self.crop_size)
-            cropped_other_bev = bp.crop_feature(flat_bev, flat_rel_loc0 + locs_jitter, flat_rel_ori0 + oris_jitter,
-                                                pixels_per_meter=self.pixels_per_meter, crop_size=self.crop_size * 2)
-            other_locs = transform_points(flat_locs - locs_jitter[:, None], -flat_rel_ori0 - oris_jitter)
-            other_embd = self.lidar_conv_emb(cropped_other_features)
-            other_cast_locs = self.cast(other_embd, mode='other')
-            other_cast_cmds = self.cast_cmd_pred(other_embd)
+        """Distillation forward of train_lidar (lav/models/uniplanner.py:56-151): the student forecasts the selected other
+        vehicles and plans for the ego from jittered crops of the LiDAR features; the frozen BEVPlanner teacher does the same
+        from crops of the ground-truth BEV, under no_grad.  Returns the reference's 11-tuple
+            (other_locs, other_cast_locs, other_cast_cmds, other_cast_locs_expert, other_cast_cmds_expert,
+             ego_locs, ego_plan_locs, ego_cast_locs, ego_cast_cmds, ego_cast_locs_expert, ego_plan_locs_expert).
+        Others and egos go through the embedder in two separate calls (two BatchNorm batches) and the random draws keep the
+        reference's order, so a seeded run is bit-identical to the reference module (tests/golden/uniplanner_train.npz)."""
+        teacher = self.bev_planner.eval()
+        dev = features.device
+        ppm, crop = self.pixels_per_meter, self.crop_size
+        ego_now, ego_heading = ego_locs[:, 0], oris[:, :1]
+        act_locs, act_oris = locs[:, 1:], oris[:, 1:]                       # slot 0 of locs / oris / typs is the ego itself
+        slots = act_locs.shape[1]
+        chosen = vehicles_ahead(ego_locs, act_locs, typs[:, 1:] == 1)
+        if bool(chosen.any()):
+            chosen = cap_per_sample(chosen, self.max_num_cars)
+            frame, slot = chosen.nonzero(as_tuple=True)                     # row-major = the order of a boolean-mask gather
+            start = act_locs[frame, slot, 0] - ego_now[frame]               # actor pose in the ego frame
+            heading = act_oris[frame, slot] - ego_heading[frame, 0]
+            future = act_locs[frame, slot, 1:] - act_locs[frame, slot, :1]
+            shift, turn = self._jitter(frame.numel(), dev)
+            at, facing = start + shift, heading + turn
+            other_locs = transform_points(future - shift[:, None], -facing)
+            _, other_cast, other_cmds = self._student(self.crop_feature(features[frame], at, facing, pixels_per_meter=ppm / 2, crop_size=crop))
             with torch.no_grad():
-                other_bev_embd = bp.bev_conv_emb(cropped_other_bev)
-                other_cast_locs_expert = bp.cast(other_bev_embd)
-                other_cast_cmds_expert = bp.cast_cmd_pred(other_bev_embd)
-        else:
-            z = dict(dtype=features.dtype, device=features.device)
-            other_locs = torch.zeros((N, self.num_plan, 2), **z)
-            other_cast_locs = torch.zeros((N, self.num_cmds, self.num_plan, 2), **z)
-            other_cast_cmds = torch.zeros((N, self.num_cmds), **z)
-            other_cast_locs_expert = torch.zeros((N, self.num_cmds, self.num_plan, 2), **z)
-            other_cast_cmds_expert = torch.zeros((N, self.num_cmds), **z)
-        B = features.size(0)
-        locs_jitter = (torch.rand((B, 2)) * 2 - 1).float().to(locs.device) * self.feature_x_jitter
-        locs_jitter[:, 1] = 0
-        oris_jitter = (torch.rand((B,)) * 2 - 1).float().to(oris.device) * self.feature_angle_jitter
-        ego_locs = transform_points(ego_locs[:, 1:] - locs_jitter[:, None], -oris_jitter)
-        nxps = transform_points(nxps[:, None] - locs_jitter[:, None], -oris_jitter)[:, 0]
-        cropped_ego_features = self.crop_feature(features, locs_jitter, oris_jitter, pixels_per_meter=self.pixels_per_meter / 2,
-                                                 crop_size=self.crop_size)
-        cropped_ego_bev = bp.crop_feature(bev, locs_jitter, oris_jitter, pixels_per_meter=self.pixels_per_meter, crop_size=self.crop_size * 2)
-        ego_embd = self.lidar_conv_emb(cropped_ego_features)
+                t_embd = teacher.bev_conv_emb(teacher.crop_feature(bev[frame], at, facing, pixels_per_meter=ppm, crop_size=2 * crop))
+                other_cast_t, other_cmds_t = teacher.cast(t_embd), teacher.cast_cmd_pred(t_embd)
+        else:                                                               # no actor to forecast: zero placeholders, one per slot
+            blank = lambda *shape: torch.zeros(shape, dtype=features.dtype, device=dev)
+            other_locs = blank(slots, self.num_plan, 2)
+            other_cast, other_cast_t = blank(slots, self.num_cmds, self.num_plan, 2), blank(slots, self.num_cmds, self.num_plan, 2)
+            other_cmds, other_cmds_t = blank(slots, self.num_cmds), blank(slots, self.num_cmds)
+        shift, turn = self._jitter(features.shape[0], dev)
+        ego_future = transform_points(ego_locs[:, 1:] - shift[:, None], -turn)
+        goal = transform_points(nxps[:, None] - shift[:, None], -turn)[:, 0]
+        ego_embd, ego_cast, ego_cmds = self._student(self.crop_feature(features, shift, turn, pixels_per_meter=ppm / 2, crop_size=crop))
         with torch.no_grad():
-            ego_bev_embd = bp.bev_conv_emb(cropped_ego_bev)
-            ego_cast_locs_expert = bp.cast(ego_bev_embd)
-            ego_plan_locs_expert = bp.plan(ego_bev_embd, nxps, cast_locs=ego_cast_locs_expert, pixels_per_meter=self.pixels_per_meter,
-                                           crop_size=self.crop_size * 2)
-        ego_cast_locs = self.cast(ego_embd, mode='ego')
-        ego_plan_locs = self.plan(ego_embd, nxps, cast_locs=ego_cast_locs, pixels_per_meter=self.pixels_per_meter, crop_size=self.crop_size * 2)
-        ego_cast_cmds = self.cast_cmd_pred(ego_embd)
-        return (other_locs, other_cast_locs, other_cast_cmds, other_cast_locs_expert, other_cast_cmds_expert,
-                ego_locs, ego_plan_locs, ego_cast_locs, ego_cast_cmds, ego_cast_locs_expert, ego_plan_locs_expert)
+            t_embd = teacher.bev_conv_emb(teacher.crop_feature(bev, shift, turn, pixels_per_meter=ppm, crop_size=2 * crop))
+            ego_cast_t = teacher.cast(t_embd)
+            ego_plan_t = teacher.plan(t_embd, goal, cast_locs=ego_cast_t, pixels_per_meter=ppm, crop_size=2 * crop)
+        ego_plan = self.plan(ego_embd, goal, cast_locs=ego_cast, pixels_per_meter=ppm, crop_size=2 * crop)
+        return (other_locs, other_cast, other_cmds, other_cast_t, other_cmds_t,
+                ego_future, ego_plan, ego_cast, ego_cmds, ego_cast_t, ego_plan_t)
 
     def det_to_locs(self, det, H, W):
         """detections -> (locs list, oris list) in ego metres (uniplanner.py:195-214)."""
@@ -447,12 +450,10 @@ class UniPlanner(nn.Module):
 
 # ----------------------------------------------------------------------------- brake predictor
 def positionalencoding1d(d_model, length):
-    pe = torch.zeros(length, d_model)
-    position = torch.arange(0, length).unsqueeze(1)
-    div_term = torch.exp((torch.arange(0, d_model, 2, dtype=torch.float) * -(math.log(10000.0) / d_model)))
-    pe[:, 0::2] = torch.sin(position.float() * div_term)
-    pe[:, 1::2] = torch.cos(position.float() * div_term)
-    return pe
+    """sinusoidal table (length, d_model): even columns sin, odd columns cos of position / 10000^(2i/d_model) — the
+    positional-encodings package formula the reference's attention pool uses (lav/models/attention.py:41-56)."""
+    phase = torch.arange(length, dtype=torch.float32)[:, None] * torch.exp(torch.arange(0, d_model, 2, dtype=torch.float) * -(math.log(10000.0) / d_model))
+    return torch.stack([torch.sin(phase), torch.cos(phase)], dim=-1).flatten(1)
 
 
 class Attention(nn.Module):

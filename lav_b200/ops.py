@@ -319,7 +319,7 @@ def paint_batched(points, sem, cams, mode, copy_cols, out):
 
 
 def pack_deconv2x2(weight, bias):
-    """ConvTranspose2d(16, C, 2, stride=2) parameters (weight (16,C,2,2), bias (C,)) -> the 264-float table
+    """ConvTranspose2d(16, C, 2, stride=2) parameters (weight (16,C,2,2), bias (C,)) -> the 520-float table
     lavb_paint_deconv_batched reads: w[v%2][u%2][c_in][8] | bias[8]."""
     cin, c, kh, kw = weight.shape
     assert cin == 16 and kh == 2 and kw == 2 and c <= 8
@@ -339,7 +339,7 @@ def paint_deconv_batched(points, feat, n_classes, deconv, cams, copy_cols, out, 
     h, w = image_hw
     cams = np.ascontiguousarray(cams, dtype=np.float32)
     ncam = cams.shape[0]
-    assert feat.shape == (f * ncam, h // 2, w // 2, 16) and deconv.numel() == 264
+    assert feat.shape == (f * ncam, h // 2, w // 2, 16) and deconv.numel() == 520
     check(lib().lavb_paint_deconv_batched(_ptr(points), f, n, ps, n * ps, _ptr(feat), _DT[feat.dtype], ncam, n_classes, h, w,
                                           _ptr(deconv), cams.ctypes.data_as(C.c_void_p), _ptr(out), out.shape[2], n * out.shape[2],
                                           copy_cols, copy_cols, _stream()), "lavb_paint_deconv_batched")
@@ -370,7 +370,7 @@ def split_h16(x):
     return out
 
 
-PILLAR_ENCODER = "tiled"     # "tiled" (lavb_pillar_forward_tiled) | "sorted" (lavb_pillar_forward_sorted): tensor-core encoders
+PILLAR_ENCODER = "sorted"    # "sorted" (lavb_pillar_forward_sorted) | "tiled" (lavb_pillar_forward_tiled): tensor-core encoders; B200 @B=32 x 120k pts: sorted 23.4, tiled 27.6 us/frame
 
 
 def pillar_forward_sorted(pts, starts, counts, grid, w1, s1, t1, w2, s2, t2, split_out=False):

