@@ -14,6 +14,9 @@ from .layers import PlanMixin, TapConv, bn_affine
 from .point_pillar import PointPillarNet
 
 
+CANVAS16 = True       # 16-bit path: single h16 canvas (tile-binned encoder, out_mode 2) instead of the [hi | lo] split
+
+
 def _dt(precision):
     return torch.float32 if precision == "fp32" else ops.h16()
 
@@ -221,7 +224,11 @@ class LiDARModel(PlanMixin, nn.Module):
         return ops.deconv3x3s2_small(hid, 4, nh, wd, bd, n_outs, sig)
 
     def forward_nhwc(self, lidars, num_points):
-        canvas = self.point_pillar_net.forward_nhwc(lidars, num_points, split_out=(self.precision == "f16"))
+        f16 = self.precision == "f16"
+        # 16-bit path: the canvas is an h16 activation like every other layer's input (64 ch, 128 B per cell).  With half storage
+        # its rounding (2^-12) is the same as everywhere else in the stack; the [hi | lo] split canvas (CANVAS16 = False) is the
+        # legacy form that kept the first conv at fp32 input precision when the storage type was bfloat16.
+        canvas = self.point_pillar_net.forward_nhwc(lidars, num_points, split_out=f16 and not CANVAS16, canvas16=f16 and CANVAS16)
         feats = self.backbone.forward_nhwc(canvas)
         return (feats, *self.heads_nhwc(feats))
 

@@ -370,12 +370,13 @@ def split_h16(x):
     return out
 
 
-PILLAR_ENCODER = "sorted"    # "sorted" (lavb_pillar_forward_sorted) | "tiled" (lavb_pillar_forward_tiled): tensor-core encoders; B200 @B=32 x 120k pts: sorted 23.4, tiled 27.6 us/frame
+PILLAR_ENCODER = "tiled"     # "tiled" (lavb_pillar_forward_tiled: tile-binned, tcgen05 MLP) | "sorted" (lavb_pillar_forward_sorted: cell-sorted, mma.sync MLP)
 
 
-def pillar_forward_sorted(pts, starts, counts, grid, w1, s1, t1, w2, s2, t2, split_out=False):
+def pillar_forward_sorted(pts, starts, counts, grid, w1, s1, t1, w2, s2, t2, split_out=False, canvas16=False):
     """tensor-core pillar encoder of the 16-bit pipeline (tile-binned or sorted kernel, see PILLAR_ENCODER).  Returns the NHWC
-    canvas: fp32 (B,ny,nx,H2) or, with split_out, f16 (B,ny,nx,2*H2) = [hi | lo]."""
+    canvas: fp32 (B,ny,nx,H2); with split_out, h16 (B,ny,nx,2*H2) = [hi | lo]; with canvas16 (tile-binned encoder only), h16
+    (B,ny,nx,H2) — what the 16-bit pipeline feeds the backbone."""
     _need_cuda(pts, w1, w2)
     assert pts.dtype == torch.float32 and pts.dim() == 2 and pts.stride(1) == 1
     min_x, max_x, min_y, max_y, ppm, nx, ny = grid
@@ -383,8 +384,9 @@ def pillar_forward_sorted(pts, starts, counts, grid, w1, s1, t1, w2, s2, t2, spl
     b, st, ct = _clouds(starts, counts)
     total = int(sum(int(c) for c in counts))
     h2 = w2.shape[0]
-    canvas = torch.empty((b, ny, nx, 2 * h2 if split_out else h2), dtype=h16() if split_out else torch.float32, device=pts.device)
-    tiled = PILLAR_ENCODER == "tiled"
+    assert not (split_out and canvas16)
+    canvas = torch.empty((b, ny, nx, 2 * h2 if split_out else h2), dtype=h16() if (split_out or canvas16) else torch.float32, device=pts.device)
+    tiled = PILLAR_ENCODER == "tiled" or canvas16
     if tiled:      # every frame's records start at its exclusive point offset: size the record buffer for the clouds as given
         total = int(sum(int(c) for c in counts))
     ws = _workspace(pts.device, (lib().lavb_pillar_tiled_workspace_bytes if tiled else lib().lavb_pillar_sorted_workspace_bytes)(b, nx, ny, total))
@@ -392,8 +394,8 @@ def pillar_forward_sorted(pts, starts, counts, grid, w1, s1, t1, w2, s2, t2, spl
     fn, name = (lib().lavb_pillar_forward_tiled, "lavb_pillar_forward_tiled") if tiled else (lib().lavb_pillar_forward_sorted, "lavb_pillar_forward_sorted")
     check(fn(_ptr(pts), pts.stride(0), d, st, ct, b, min_x, max_x, min_y, max_y, ppm, nx, ny,
                                            _ptr(w1), _ptr(s1), _ptr(t1), w1.shape[0], _ptr(w2), _ptr(s2), _ptr(t2), h2,
-                                           _ptr(canvas), int(split_out), _ptr(ws), _stream()), name)
-    _prof_end("pillar", float(total) * d * 4 + float(b) * ny * nx * h2 * 4, e0)
+                                           _ptr(canvas), 2 if canvas16 else int(split_out), _ptr(ws), _stream()), name)
+    _prof_end("pillar", float(total) * d * 4 + float(b) * ny * nx * h2 * (2 if canvas16 else 4), e0)
     _COUNT[0] += 3 if tiled else 6
     return canvas
 

@@ -132,6 +132,8 @@ def test_config3_backbone_heads_planner_b64_f16(cuda):
                                 ("ori", ori[b], wo[0]), ("seg", seg[b], ws[0])):
             g = got.float().cpu().permute(2, 0, 1)
             e, r = util.rel_err(g, want), _rms(g, want)
+            if name == "seg":          # sigmoid output: max-norm on the logits over the logit scale (util.seg_logit_err)
+                e = util.seg_logit_err(g[None], wf, lsd)
             worst[name] = max(worst.get(name, 0.0), e, r)
             assert e < 1e-2 and r < 1e-2, (b, name, e, r)
         sc = float(wplan[1].abs().max()) + 1

@@ -50,3 +50,17 @@ def paint_inputs():
 def rel_err(a, b):
     a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def seg_logit_err(got_prob, ref_feats, sd):
+    """error of the seg head measured BEFORE its sigmoid, as a fraction of the logit scale: the reference module returns
+    sigmoid(logits) with logits of O(30-90) on seeded weights, so a probability-space max-norm would measure the sigmoid's slope.
+    ref_feats: oracle features (B,384,h,w); got_prob: our sigmoid output (B,3,H,W).  Compared where our sigmoid is invertible
+    (|reference logit| < 10), normalised by max |reference logit|."""
+    from oracle import lav_ref as O
+    with torch.no_grad():
+        ref_logit = O.head(sd, ref_feats, "seg_head.", sigmoid=False)
+    got_logit = torch.logit(got_prob.double().cpu().clamp(1e-9, 1 - 1e-9))
+    live = ref_logit.abs() < 10
+    assert float(live.float().mean()) > 0.05
+    return float((got_logit - ref_logit.double())[live].abs().max() / ref_logit.abs().max())
