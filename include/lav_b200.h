@@ -254,6 +254,15 @@ typedef struct lavb_conv_pair_desc {
 } lavb_conv_pair_desc;
 int lavb_conv_pair_umma(const lavb_conv_pair_desc* h_desc, void* stream);
 
+/* ---------------------------------------------------------------- fused ERFNet entry block on the raw camera bytes
+ * replaces: RGBSegmentationModel.normalize ((x/255 - .5) * 2, lav/models/rgb.py:41-45) + Encoder.initial_block =
+ * DownsamplerBlock(3, 16): relu(bn(cat[conv3x3 s2 p1 (13 ch), maxpool2x2 (3 ch)])) (lav/models/erfnet.py:12-23,67).
+ * d_rgb_u8: uint8 NHWC (n, h, w, 3); h_w27x16: host fp32 [(ky*3+kx)*3+c][16] conv weights (columns >= 13 zero); h_scale16 /
+ * h_shift16: host fp32 [16], epi(a) = relu(a * scale + shift) with the conv bias folded into the first 13 shifts; d_out: NHWC
+ * (n, h/2, w/2, 16) fp32 or h16. */
+int lavb_erf_stem(const void* d_rgb_u8, int n, int h, int w, const float* h_w27x16, const float* h_scale16,
+                  const float* h_shift16, void* d_out, int out_dtype, void* stream);
+
 /* ---------------------------------------------------------------- fused 16-channel non_bottleneck_1d block
  * replaces: non_bottleneck_1d(16, dropprob, dilated=1) of the ERFNet decoder (lav/models/erfnet.py:37-63, Decoder layers 4 and 5) —
  * conv3x1 -> ReLU -> conv1x3 -> bn1 -> ReLU -> conv3x1 -> ReLU -> conv1x3 -> bn2 -> (+ input) -> ReLU — in one kernel, all four

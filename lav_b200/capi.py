@@ -91,6 +91,7 @@ _SIGS = {
                                     C.c_void_p, C.c_void_p]),
     "lavb_gru_h512": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                 C.c_void_p]),
+    "lavb_erf_stem": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "lavb_erf_nb16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lavb_conv_pair_umma": (C.c_int, [C.c_void_p, C.c_void_p]),
     "lavb_maxpool3x3s2_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -1,4 +1,4 @@
-// EXPERIMENTAL (round-2 work item, not on the default path; enabled by lav_b200.erfnet.FUSE_PAIRS):
+// Fused ERFNet pair kernel (lav_b200.erfnet.FUSE_PAIRS, on by default; B200: ERFNet of 96 images 2.85 -> 2.72 ms):
 // one kernel for a (3x1 -> 1x3) convolution pair of ERFNet's non_bottleneck_1d (lav/models/erfnet.py:37-63):
 //     mid = relu(conv3x1(x) + b1)                      (vertical taps, dilation d)
 //     out = [relu]( (conv1x3(mid) + b2) * s + t [+ res] )   (horizontal taps, dilation d; BN affine; residual)
@@ -6,11 +6,11 @@
 // fused, `mid` never leaves the SM.  A tile is 128 pixels made of FULL-WIDTH image rows (W = 64 -> 2 rows, W = 32 -> 4 rows),
 // so the horizontal conv needs no halo: its zero padding is the image border.
 //   stage 1: tcgen05.mma over 3 vertical taps (A = 4-D TMA boxes shifted by the tap, B = W1 blocks) -> TMEM acc1 (2 buffers)
-//   epilogue 1: acc1 -> relu(+b1) -> bf16 -> shared memory, written three times in the SWIZZLE_128B K-major operand layout:
+//   epilogue 1: acc1 -> relu(+b1) -> h16 -> shared memory, written three times in the SWIZZLE_128B K-major operand layout:
 //               shifted by +d, 0, -d pixels inside each image row (rows that fall off the image border stay zero), i.e. the
 //               three A operands of the horizontal taps
 //   stage 2: tcgen05.mma over the 3 horizontal taps (A = those copies, B = W2 blocks through the same TMA ring) -> TMEM acc2
-//   epilogue 2: affine / residual / ReLU -> bf16 NHWC.
+//   epilogue 2: affine / residual / ReLU -> h16 NHWC.
 // Warp roles as conv_umma.cu (warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue), one CTA per SM, persistent.
 // MMA issue order S1(0), S1(1), S2(0), S1(2), S2(1), ... — the producer feeds the ring in exactly that order — so the
 // stage-1 MMAs of the next tile run while the epilogue warps write `mid` of the current one.
@@ -99,7 +99,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_pair_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
+template <int kMinBlocks>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                                const __grid_constant__ CUtensorMap tmap_w1,
                                                                                const __grid_constant__ CUtensorMap tmap_w2,
                                                                                const __grid_constant__ PairArgs p) {
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_pair_umma_kernel(
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, K-major both, N = c, M = 128 (bit layout in conv_umma.cu)
+      // instruction descriptor: D=f32, A=B=h16, K-major both, N = c, M = 128 (bit layout in conv_umma.cu)
       const uint32_t idesc = (1u << 4) | (kH16Fmt << 7) | (kH16Fmt << 10) | ((uint32_t)(p.c >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
       int slot = 0; uint32_t phase = 0;
       uint32_t te_phase[2] = {0, 0};                 // parity of tempty1[buf] expected next
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_pair_umma_kernel(
       const int img = tile / p.tiles_per_img, y = (tile - img * p.tiles_per_img) * p.tile_h + py;
       const bool valid = y < p.h;
       const long long pix = ((long long)img * p.h + y) * p.w + px;
-      // ---- epilogue 1: acc1 -> relu(+b1) -> bf16 -> three shifted K-major copies in shared memory
+      // ---- epilogue 1: acc1 -> relu(+b1) -> h16 -> three shifted K-major copies in shared memory
       mbar_wait(tfull1 + 8 * buf, (uint32_t)((i >> 1) & 1));
       tc_fence_after();
       for (int c0 = half * 32; c0 < p.c; c0 += 64) {
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_pair_umma_kernel(
       mbar_arrive(tempty1 + 8 * buf);                // acc1[buf] may be overwritten by the stage-1 MMAs of tile i+2
       proxy_fence_async();                           // generic-proxy stores -> visible to the tensor core's async-proxy reads
       mbar_arrive(mid_full);
-      // ---- epilogue 2: acc2 -> affine (+ residual) -> ReLU -> bf16 NHWC
+      // ---- epilogue 2: acc2 -> affine (+ residual) -> ReLU -> h16 NHWC
       uint4 rr[4];
       auto load_res = [&](int c0) {
         const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.c + c0);
@@ -359,7 +360,12 @@ extern "C" int lavb_conv_pair_umma(const lavb_conv_pair_desc* d, void* stream) {
   a.bias1 = d->bias1; a.bias2 = d->bias2; a.scale2 = d->scale2; a.shift2 = d->shift2;
   const int slot_bytes = kABytes + d->c * kBlockK * 2;
   const int mid_bytes = 3 * a.kchunks * kABytes;
-  a.stages = min(kMaxStages, (200 * 1024 - mid_bytes) / slot_bytes);
+  // C = 64: TWO co-resident CTAs per SM (3 x 64 TMEM columns -> 256 each, ~100 KB of shared memory each): two independent tile
+  // pipelines hide the per-tile serial chain (TMA -> MMA -> epilogue 1 -> MMA -> epilogue 2) that bounds this kernel.
+  static int two_mode = -1;
+  if (two_mode < 0) { const char* e = getenv("LAVB_PAIR_TWO"); two_mode = e ? atoi(e) : 1; }
+  const bool two = two_mode && d->c == 64;
+  a.stages = min(kMaxStages, ((two ? 100 : 200) * 1024 - mid_bytes) / slot_bytes);
   a.tmem_cols = d->c == 64 ? 256 : 512;          // acc1 x 2 + acc2 = 3c columns, power of two
   CUtensorMap tmap_a, tmap_w1, tmap_w2;
   {
@@ -383,9 +389,13 @@ extern "C" int lavb_conv_pair_umma(const lavb_conv_pair_desc* d, void* stream) {
     LAVB_CHECK_ARG(r == CUDA_SUCCESS, "conv_pair_umma: cuTensorMapEncodeTiled(W%d) failed with %d", which + 1, (int)r);
   }
   const size_t smem = (size_t)a.stages * slot_bytes + mid_bytes + 1024 /*align*/ + 16 * kMaxStages + 96 + 3 * 128 * sizeof(float);
-  LAVB_CUDA_OK(ensure_dyn_smem((const void*)conv_pair_umma_kernel, 227 * 1024));
-  const int grid = min(a.num_tiles, kNumSMs);
-  conv_pair_umma_kernel<<<grid, 64 + 32 * kEpiWarps, smem, (cudaStream_t)stream>>>(tmap_a, tmap_w1, tmap_w2, a);
+  if (two) {
+    LAVB_CUDA_OK(ensure_dyn_smem((const void*)conv_pair_umma_kernel<2>, 113 * 1024));
+    conv_pair_umma_kernel<2><<<min(a.num_tiles, 2 * kNumSMs), 64 + 32 * kEpiWarps, smem, (cudaStream_t)stream>>>(tmap_a, tmap_w1, tmap_w2, a);
+  } else {
+    LAVB_CUDA_OK(ensure_dyn_smem((const void*)conv_pair_umma_kernel<1>, 227 * 1024));
+    conv_pair_umma_kernel<1><<<min(a.num_tiles, kNumSMs), 64 + 32 * kEpiWarps, smem, (cudaStream_t)stream>>>(tmap_a, tmap_w1, tmap_w2, a);
+  }
   LAVB_LAUNCH_OK();
   return 0;
 }

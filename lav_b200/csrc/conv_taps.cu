@@ -7,7 +7,7 @@
 // N = cout, K = ntaps*cin; tiles BM x BN x 16 with a register-prefetched, double-buffered smem
 // pipeline and a fused epilogue (bias, ReLU, BN affine, residual, ReLU, sigmoid).
 // This is the exact-fp32 workhorse (parity path and all HBM-bound layers); the tensor-core
-// layers of the bf16 path live in conv_umma.cu.
+// layers of the h16 path live in conv_umma.cu.
 #include <algorithm>
 #include <type_traits>
 #include "common.cuh"
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(256) conv_small_kernel(const __grid_constant__
   }
 }
 
-// ---- 16-input-channel layers on the tensor cores (bf16 path): one tap = one K16 step of mma.sync m16n8k16.
+// ---- 16-input-channel layers on the tensor cores (h16 path): one tap = one K16 step of mma.sync m16n8k16.
 // ERFNet's 16-channel decoder blocks, the 16->48 downsampler conv and the 16->5 output ConvT (erfnet.py:71,121-124) are
 // FFMA-bound in conv_small_kernel (768 FMA per pixel); here a warp owns 32 output pixels, the A fragment of a tap is
 // loaded straight from global memory (a pixel's 16 channels are 32 contiguous bytes = exactly one fragment row), the

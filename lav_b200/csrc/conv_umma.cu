@@ -1,4 +1,4 @@
-// tcgen05 / TMEM / TMA implicit-GEMM tap-list convolution (bf16 in, fp32 accumulate in TMEM).
+// tcgen05 / TMEM / TMA implicit-GEMM tap-list convolution (h16 in, fp32 accumulate in TMEM).
 //
 // GEMM view of one CTA tile: M = 128 output-grid pixels (an 8 x 16 spatial patch), N = cout (<= 256),
 // K = ntaps * cin walked in blocks of 64 channels.  No im2col buffer exists anywhere: for tap (dy,dx) the
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : LAVB
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both, N>>3 [17,23), M>>4 [24,29)
+      // instruction descriptor: D=f32 [4,6)=1, A=h16 [7,10)=1, B=h16 [10,13)=1, K-major both, N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (kH16Fmt << 7) | (kH16Fmt << 10) | ((uint32_t)(p.cout >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -315,7 +315,7 @@ using namespace lavb;
 
 extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   LAVB_CHECK_ARG(d != nullptr, "conv_umma: null descriptor");
-  LAVB_CHECK_ARG(d->in_dtype == LAVB_H16, "conv_umma: input must be bf16");
+  LAVB_CHECK_ARG(d->in_dtype == LAVB_H16, "conv_umma: input must be h16");
   LAVB_CHECK_ARG(d->out_dtype == LAVB_H16 || d->out_dtype == LAVB_F32, "conv_umma: bad output dtype");
   LAVB_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= kMaxTaps, "conv_umma: ntaps must be 1..16");
   LAVB_CHECK_ARG(d->cin % 64 == 0 && d->cin > 0, "conv_umma: cin must be a multiple of 64 (got %d)", d->cin);
@@ -324,7 +324,7 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   LAVB_CHECK_ARG(d->res == nullptr || cout_mma == d->cout, "conv_umma: residual needs cout %% 32 == 0");
   LAVB_CHECK_ARG(d->in_cstride % 8 == 0 && d->in_coff % 8 == 0 && d->in_coff + d->cin <= d->in_cstride, "conv_umma: input slice misaligned");
   LAVB_CHECK_ARG(d->out_cstride % 8 == 0 && d->out_coff % 8 == 0 && d->out_coff + d->cout <= d->out_cstride, "conv_umma: output slice misaligned");
-  LAVB_CHECK_ARG(d->res == nullptr || (d->res_dtype == LAVB_H16 && d->res_cstride % 8 == 0 && d->res_coff % 8 == 0), "conv_umma: residual must be bf16, 16 B aligned");
+  LAVB_CHECK_ARG(d->res == nullptr || (d->res_dtype == LAVB_H16 && d->res_cstride % 8 == 0 && d->res_coff % 8 == 0), "conv_umma: residual must be h16, 16 B aligned");
   LAVB_CHECK_ARG((d->scale == nullptr) == (d->shift == nullptr), "conv_umma: scale and shift come together");
   LAVB_CHECK_ARG(d->in_sy >= 1 && d->in_sy <= 8 && d->in_sx >= 1 && d->in_sx <= 8, "conv_umma: bad input stride");
   auto encode = get_encode();

@@ -6,7 +6,7 @@
 
 namespace lavb {
 
-// 16 B of channels per thread (4 fp32 / 8 bf16): C*sizeof(T)/16 threads per output pixel, four 16 B loads + one 16 B store
+// 16 B of channels per thread (4 fp32 / 8 h16): C*sizeof(T)/16 threads per output pixel, four 16 B loads + one 16 B store
 // each — one warp per pixel left a third of the lanes idle at C = 384 and issued twice as many (8 B) loads.
 template <typename T> struct Vec16;
 template <> struct Vec16<float> {

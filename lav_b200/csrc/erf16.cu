@@ -152,6 +152,73 @@ __global__ void __launch_bounds__(kNbThreads, 2) erf_nb16_kernel(const __grid_co
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Fused ERFNet entry: RGBSegmentationModel.normalize + Encoder.initial_block = DownsamplerBlock(3, 16) (lav/models/rgb.py:41-45,
+// erfnet.py:12-23,67): out = relu(bn(cat[conv3x3_s2_p1(x) (13 ch), maxpool2x2(x) (3 ch)])) with x = (rgb / 255 - .5) * 2, straight
+// from the uint8 camera frames.  One thread = one output pixel; a block stages the 17 x 65 input pixels of its 8 x 32 output
+// patch in shared memory as normalised floats (zero outside the image = the conv's zero padding in the normalised domain), the
+// 27 x 13 weights and the folded BN constants come from the constant bank (kernel parameters), each thread leaves with one
+// 32-byte h16 pixel.  Replaces three launches (rgb_norm, conv_small, pool2) that moved the image through HBM three times.
+// ---------------------------------------------------------------------------------------------------------------------------------
+struct StemW { float w[27][16]; float s[16]; float t[16]; };      // w[(ky*3+kx)*3+c][co] (co >= 13 zero); epi: relu(acc*s + t)
+
+constexpr int kSt_OH = 8, kSt_OW = 32, kSt_IH = 2 * kSt_OH + 1, kSt_IW = 2 * kSt_OW + 1, kSt_Pitch = kSt_IW * 3 + 2;
+
+template <typename TOut>
+__global__ void __launch_bounds__(kSt_OH * kSt_OW) erf_stem_kernel(const unsigned char* __restrict__ img, int n, int h, int w,
+                                                                     const __grid_constant__ StemW k, TOut* __restrict__ out) {
+  __shared__ float tile[kSt_IH][kSt_Pitch];
+  __shared__ float lut[256];                              // (v / 255 - .5) * 2 for the 256 byte values, in the reference's op order
+  lut[threadIdx.x] = (__fdiv_rn((float)threadIdx.x, 255.f) - 0.5f) * 2.f;      // rgb.py:41 (blockDim.x == 256)
+  const int ho = h >> 1, wo = w >> 1;
+  const int tiles_x = (wo + kSt_OW - 1) / kSt_OW, tiles_y = (ho + kSt_OH - 1) / kSt_OH;
+  const int b = blockIdx.x / (tiles_x * tiles_y), tr = blockIdx.x % (tiles_x * tiles_y);
+  const int oy0 = (tr / tiles_x) * kSt_OH, ox0 = (tr % tiles_x) * kSt_OW;
+  const unsigned char* src = img + (size_t)b * h * w * 3;
+  const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
+  __syncthreads();
+  if (threadIdx.x < kSt_IW * 3) {                         // thread = one byte column of the staged rows (195 of the 256 threads)
+    const int q = threadIdx.x, ix = ix0 + q / 3;
+    const bool col_ok = (unsigned)ix < (unsigned)w;
+    const unsigned char* colp = src + (size_t)ix * 3 + q % 3;
+#pragma unroll
+    for (int r = 0; r < kSt_IH; ++r) {
+      const int iy = iy0 + r;
+      tile[r][q] = (col_ok && (unsigned)iy < (unsigned)h) ? lut[__ldg(colp + (size_t)iy * w * 3)] : 0.f;
+    }
+  }
+  __syncthreads();
+  const int ly = threadIdx.x / kSt_OW, lx = threadIdx.x % kSt_OW;
+  const int oy = oy0 + ly, ox = ox0 + lx;
+  if (oy >= ho || ox >= wo) return;
+  float acc[13];
+#pragma unroll
+  for (int c = 0; c < 13; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = tile[2 * ly + ky][(2 * lx + kx) * 3 + c];
+#pragma unroll
+        for (int co = 0; co < 13; ++co) acc[co] = fmaf(v, k.w[(ky * 3 + kx) * 3 + c][co], acc[co]);
+      }
+  float o[16];
+#pragma unroll
+  for (int c = 0; c < 13; ++c) o[c] = fmaxf(fmaf(acc[c], k.s[c], k.t[c]), 0.f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {      // 2x2 max-pool of the normalised image: input pixels (2oy, 2ox)..(+1,+1) = tile rows 2ly+1.., cols 2lx+1..
+    const float m = fmaxf(fmaxf(tile[2 * ly + 1][(2 * lx + 1) * 3 + c], tile[2 * ly + 1][(2 * lx + 2) * 3 + c]),
+                          fmaxf(tile[2 * ly + 2][(2 * lx + 1) * 3 + c], tile[2 * ly + 2][(2 * lx + 2) * 3 + c]));
+    o[13 + c] = fmaxf(fmaf(m, k.s[13 + c], k.t[13 + c]), 0.f);
+  }
+  TOut* dst = out + (((size_t)b * ho + oy) * wo + ox) * 16;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) store4<TOut>(dst + 4 * q, make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+}
+
 }  // namespace lavb
 
 using namespace lavb;
@@ -167,6 +234,23 @@ extern "C" int lavb_erf_nb16(const void* d_in, void* d_out, int n, int h, int w,
   LAVB_CUDA_OK(ensure_dyn_smem((const void*)erf_nb16_kernel, smem));
   const int tiles_y = (h + kNbRowsOut - 1) / kNbRowsOut;
   erf_nb16_kernel<<<n * tiles_y, kNbThreads, smem, (cudaStream_t)stream>>>(a);
+  LAVB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int lavb_erf_stem(const void* d_rgb_u8, int n, int h, int w, const float* h_w27x16, const float* h_scale16,
+                             const float* h_shift16, void* d_out, int out_dtype, void* stream) {
+  LAVB_CHECK_ARG(n >= 0 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0, "erf_stem: image size must be even");
+  if (n == 0) return 0;
+  StemW k;
+  memcpy(k.w, h_w27x16, sizeof(k.w));
+  memcpy(k.s, h_scale16, sizeof(k.s));
+  memcpy(k.t, h_shift16, sizeof(k.t));
+  const int blocks = n * ceil_div(h / 2, kSt_OH) * ceil_div(w / 2, kSt_OW);
+  const unsigned char* img = reinterpret_cast<const unsigned char*>(d_rgb_u8);
+  if (out_dtype == LAVB_F32) erf_stem_kernel<float><<<blocks, kSt_OH * kSt_OW, 0, (cudaStream_t)stream>>>(img, n, h, w, k, (float*)d_out);
+  else if (out_dtype == LAVB_H16) erf_stem_kernel<h16><<<blocks, kSt_OH * kSt_OW, 0, (cudaStream_t)stream>>>(img, n, h, w, k, (h16*)d_out);
+  else LAVB_CHECK_ARG(false, "erf_stem: output dtype must be fp32 or h16");
   LAVB_LAUNCH_OK();
   return 0;
 }

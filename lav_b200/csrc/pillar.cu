@@ -287,11 +287,11 @@ static size_t stats_bytes(int batch, int nx, int ny) { return (size_t)batch * (n
 //                and records for every 128-slot window the first segment head at/after it (tile_start)
 //   K3 fill    : counting-sort scatter of point indices into cell order
 //   K4 encode  : block i owns the whole pillars whose first point lies in slots [128 i, 128 (i+1)); per 128-row chunk:
-//                decorate + layer 1 (fp32 FFMA) -> bf16 hidden tile in swizzled smem -> layer 2 on the tensor cores
-//                (mma.sync m16n8k16 bf16, fp32 accumulate; the 64x64 weight fragments live in registers) ->
+//                decorate + layer 1 (fp32 FFMA) -> h16 hidden tile in swizzled smem -> layer 2 on the tensor cores
+//                (mma.sync m16n8k16 h16, fp32 accumulate; the 64x64 weight fragments live in registers) ->
 //                BN affine + ReLU -> fp32 tile in smem -> 64 channel-threads walk the rows and emit one canvas row per
-//                pillar (running max), as fp32 or as the [hi | lo] bf16 split conv1 consumes.
-// The first layer stays fp32 because its inputs are raw metric coordinates (bf16 would quantise x to 0.25 m).
+//                pillar (running max), as fp32 or as the [hi | lo] h16 split conv1 consumes.
+// The first layer stays fp32 because its inputs are raw metric coordinates (h16 would quantise x to 0.25 m).
 // =====================================================================================================================
 constexpr int kCellsPerBlock = 1024;
 constexpr int kRows = 128;            // slots per encode chunk
@@ -400,12 +400,12 @@ __device__ __forceinline__ void mma_h16_16816(float (&c)[4], uint32_t a0, uint32
 }
 
 constexpr int kFsPitch = 20;          // fp32 decorated-feature tile pitch (floats)
-constexpr int kW1Pitch = 24;          // bf16 layer-1 weight row pitch: conflict-free B-fragment loads
+constexpr int kW1Pitch = 24;          // h16 layer-1 weight row pitch: conflict-free B-fragment loads
 
 struct EncSmem {                      // shared-memory plan of pillar_encode_sorted_kernel (bytes from the base)
   static constexpr int fs = 0;                                             // [128][kFsPitch] fp32
   static constexpr int os = fs + kRows * kFsPitch * 4;                     // [128][kOsPitch] fp32
-  static constexpr int w1h = os + kRows * kOsPitch * 4;                    // [64][kW1Pitch] bf16 (hi)
+  static constexpr int w1h = os + kRows * kOsPitch * 4;                    // [64][kW1Pitch] h16 (hi)
   static constexpr int w1l = w1h + 64 * kW1Pitch * 2;                      // (lo)
   static constexpr int aff = w1l + 64 * kW1Pitch * 2;                      // s1 | t1 | s2 | t2
   static constexpr int cells = aff + 4 * 64 * 4;                           // [128] int
@@ -414,9 +414,11 @@ struct EncSmem {                      // shared-memory plan of pillar_encode_sor
   static constexpr int total = pcell + 2 * 4 * 4 * 4;
 };
 
-template <bool kSplitOut>
+template <int kOutMode>      // 0: fp32 [64]; 1: h16 [hi 64 | lo 64]; 2: h16 [64]
 __device__ __forceinline__ void emit_pair(void* canvas, int cell, int c, float m0, float m1) {     // channels c, c+1 (c even)
-  if (kSplitOut) {
+  if (kOutMode == 2) {
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<h16*>(canvas) + (long long)cell * 64 + c) = pack_h16(m0, m1);
+  } else if (kOutMode == 1) {
     h16* o = reinterpret_cast<h16*>(canvas) + (long long)cell * 128;
     const h162 hi = floats2h162(m0, m1);
     const float2 hf = h1622float2(hi);
@@ -427,9 +429,11 @@ __device__ __forceinline__ void emit_pair(void* canvas, int cell, int c, float m
     *reinterpret_cast<float2*>(reinterpret_cast<float*>(canvas) + (long long)cell * 64 + c) = make_float2(m0, m1);
   }
 }
-template <bool kSplitOut>
+template <int kOutMode>
 __device__ __forceinline__ void emit_one(void* canvas, int cell, int c, float m) {
-  if (kSplitOut) {
+  if (kOutMode == 2) {
+    reinterpret_cast<h16*>(canvas)[(long long)cell * 64 + c] = float2h16(m);
+  } else if (kOutMode == 1) {
     h16* o = reinterpret_cast<h16*>(canvas) + (long long)cell * 128;
     const h16 hi = float2h16(m);
     o[c] = hi; o[64 + c] = float2h16(m - h162float(hi));
@@ -437,7 +441,7 @@ __device__ __forceinline__ void emit_one(void* canvas, int cell, int c, float m)
     reinterpret_cast<float*>(canvas)[(long long)cell * 64 + c] = m;
   }
 }
-// fp32 pair -> bf16 hi pair + bf16 residual pair (error-free split to ~2^-16 relative)
+// fp32 pair -> h16 hi pair + h16 residual pair (error-free split to ~2^-16 relative)
 __device__ __forceinline__ void split_pair(float2 f, uint32_t& hi, uint32_t& lo) {
   const h162 h = floats2h162(f.x, f.y);
   const float2 hf = h1622float2(h);
@@ -449,15 +453,15 @@ __device__ __forceinline__ void split_pair(float2 f, uint32_t& hi, uint32_t& lo)
 // A block walks "windows" of ~128 sorted rows that begin and end on pillar boundaries (tile_start), 128 rows per batch,
 // warp w owning rows [32w, 32w+32) of the batch end to end — one __syncthreads per batch:
 //   (1) gather + decorate: one thread per row -> 16 fp32 features in shared memory;
-//   (2) layer 1 (16 -> 64) as mma.sync m16n8k16 with the features AND weights split into bf16 hi + lo (3 MMAs per tile:
+//   (2) layer 1 (16 -> 64) as mma.sync m16n8k16 with the features AND weights split into h16 hi + lo (3 MMAs per tile:
 //       hi*hi + lo*hi + hi*lo, fp32 accumulate ~ fp32 accuracy); BN affine + ReLU on the accumulator fragments, which are
-//       then re-packed IN REGISTERS as the bf16 A fragments of layer 2 (64 -> 64; C-fragment layout == A-fragment layout);
+//       then re-packed IN REGISTERS as the h16 A fragments of layer 2 (64 -> 64; C-fragment layout == A-fragment layout);
 //       BN affine + ReLU -> fp32 tile in shared memory;
 //   (3) segmented max: each warp walks its own 32 rows, one lane per channel pair; runs that start and end inside the
 //       quarter go straight to the canvas, the first / last run's partial maxima to a small table;
 //   (4) after the barrier, 64 threads stitch the quarter tables with the run carried from the previous batch.
 // Every canvas row of an occupied cell is written exactly once; empty cells were zero-filled by cell_offsets_kernel.
-template <int D, bool kSplitOut>
+template <int D, int kOutMode>
 __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
     const float* __restrict__ pts, int pt_stride, const __grid_constant__ Clouds clouds, const __grid_constant__ Grid g,
     const float4* __restrict__ stats, const int* __restrict__ order, const int* __restrict__ ocell,
@@ -536,7 +540,7 @@ __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
         split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq + 8) * kFsPitch + 2 * tq]), ah[1], al[1]);
         split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq) * kFsPitch + 2 * tq + 8]), ah[2], al[2]);
         split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq + 8) * kFsPitch + 2 * tq + 8]), ah[3], al[3]);
-        uint32_t a2[4][4];        // layer-2 A fragments (bf16 h), one k16 step per pair of layer-1 n-tiles
+        uint32_t a2[4][4];        // layer-2 A fragments (h16 h), one k16 step per pair of layer-1 n-tiles
 #pragma unroll
         for (int nn = 0; nn < 8; ++nn) {
           const h16* wh = w1h + (nn * 8 + gq) * kW1Pitch + 2 * tq;
@@ -582,7 +586,7 @@ __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
             const int c = cq[r];
             if (c != cur) {
               if (first) { *reinterpret_cast<float2*>(pm + warp * 64 + 2 * lane) = make_float2(m0, m1); first = false; }
-              else emit_pair<kSplitOut>(canvas, cur, 2 * lane, m0, m1);
+              else emit_pair<kOutMode>(canvas, cur, 2 * lane, m0, m1);
               cur = c; m0 = 0.f; m1 = 0.f;
             }
             const float2 v = *reinterpret_cast<const float2*>(oq + r * kOsPitch);
@@ -603,19 +607,19 @@ __global__ void __launch_bounds__(kRows, 3) pillar_encode_sorted_kernel(
           const int fc = pcb[q * 4], lc = pcb[q * 4 + 1];
           const float fm = pm[q * 64 + tid];
           if (fc != run_cell) {
-            if (run_cell >= 0) emit_one<kSplitOut>(canvas, run_cell, tid, run_max);
+            if (run_cell >= 0) emit_one<kOutMode>(canvas, run_cell, tid, run_max);
             run_cell = fc; run_max = fm;
           } else {
             run_max = fmaxf(run_max, fm);
           }
           if (lc != fc) {
-            emit_one<kSplitOut>(canvas, run_cell, tid, run_max);
+            emit_one<kOutMode>(canvas, run_cell, tid, run_max);
             run_cell = lc; run_max = pm[4 * 64 + q * 64 + tid];
           }
         }
       }
     }
-    if (tid < H && run_cell >= 0) emit_one<kSplitOut>(canvas, run_cell, tid, run_max);
+    if (tid < H && run_cell >= 0) emit_one<kOutMode>(canvas, run_cell, tid, run_max);
   }   // window loop
 }
 
@@ -774,188 +778,6 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(const float* __restri
     r[0] = make_float4(f[0], f[1], f[2], f[3]);
     r[1] = make_float4(f[4], f[5], f[6], f[7]);
     r[2] = make_float4(f[8], f[9], f[10], f[11]);
-  }
-}
-
-struct TileSmem {                     // shared-memory plan of pillar_tile_encode_kernel (bytes from the base)
-  static constexpr int tile = 0;                                             // [128 cells][64] fp32, XOR-swizzled columns
-  static constexpr int stats = tile + kTileCells * 64 * 4;                   // [(kTileR+1)*(kTileC+1)] float4 (sum x,y,z,n)
-  static constexpr int fs = stats + (kTileR + 1) * (kTileC + 1) * 16;        // [128][kFsPitch] fp32 decorated features
-  static constexpr int w1h = fs + kRows * kFsPitch * 4;                      // [64][kW1Pitch] h16 (hi)
-  static constexpr int w1l = w1h + 64 * kW1Pitch * 2;                        // (lo)
-  static constexpr int aff = w1l + 64 * kW1Pitch * 2;                        // s1 | t1 | s2 | t2
-  static constexpr int cells = aff + 4 * 64 * 4;                             // [128] int: clamped local cell of each row (-1 = none)
-  static constexpr int total = cells + kRows * 4;
-};
-
-// column swizzle of the fp32 tile: one ATOMS instruction of the MMA epilogue touches 8 rows (cells) x 4 column pairs with the
-// same column parity; XOR-ing bits 3-4 and bit 0 of the column with 3 bits of the cell index spreads 8 distinct cell classes
-// over all 32 banks.
-__device__ __forceinline__ int tile_swz(int cell) { return ((cell & 3) << 3) | ((cell >> 2) & 1); }
-
-template <int D, bool kSplitOut>
-__global__ void __launch_bounds__(kRows, 3) pillar_tile_encode_kernel(
-    const float4* __restrict__ recs, const __grid_constant__ Clouds clouds, const __grid_constant__ Grid g,
-    const __grid_constant__ TileGrid tg, const int* __restrict__ tile_count, const int* __restrict__ tile_off,
-    const float* __restrict__ w1, const float* __restrict__ s1, const float* __restrict__ t1, const float* __restrict__ w2,
-    const float* __restrict__ s2, const float* __restrict__ t2, void* __restrict__ canvas) {
-  constexpr int F = D + 5, H = 64;
-  static_assert(F == 16, "layer 1 is one k16 MMA step");
-  extern __shared__ __align__(128) uint8_t sm[];
-  float* tile = reinterpret_cast<float*>(sm + TileSmem::tile);
-  float* stats = reinterpret_cast<float*>(sm + TileSmem::stats);
-  float* fs = reinterpret_cast<float*>(sm + TileSmem::fs);
-  h16* w1h = reinterpret_cast<h16*>(sm + TileSmem::w1h);
-  h16* w1l = reinterpret_cast<h16*>(sm + TileSmem::w1l);
-  float* aff = reinterpret_cast<float*>(sm + TileSmem::aff);
-  int* cells = reinterpret_cast<int*>(sm + TileSmem::cells);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
-  for (int i = tid; i < H * F; i += kRows) {                                      // w1 is [64 n][16 k]
-    const float v = __ldg(w1 + i);
-    const h16 hi = float2h16(v);
-    w1h[(i / F) * kW1Pitch + i % F] = hi;
-    w1l[(i / F) * kW1Pitch + i % F] = float2h16(v - h162float(hi));
-  }
-  for (int i = tid; i < H; i += kRows) { aff[i] = __ldg(s1 + i); aff[H + i] = __ldg(t1 + i); aff[2 * H + i] = __ldg(s2 + i); aff[3 * H + i] = __ldg(t2 + i); }
-  uint32_t bfrag[4][8][2];       // layer-2 weight fragments (B operand "col" = rows of w2 [64 n][64 k])
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-    for (int nn = 0; nn < 8; ++nn) {
-      const float* wp = w2 + (nn * 8 + gq) * H + kk * 16 + tq * 2;
-      const float2 lo = __ldg(reinterpret_cast<const float2*>(wp)), hi = __ldg(reinterpret_cast<const float2*>(wp + 8));
-      bfrag[kk][nn][0] = pack_h16(lo.x, lo.y);
-      bfrag[kk][nn][1] = pack_h16(hi.x, hi.y);
-    }
-  const int total_tiles = clouds.batch * tg.tiles;
-  constexpr int kRowBytes = 256;                                                  // fp32 [64] or h16 [hi 64 | lo 64]
-  for (int work = blockIdx.x; work < total_tiles; work += gridDim.x) {
-    const int b = work / tg.tiles, t = work - b * tg.tiles;
-    const int tr = t / tg.tiles_c, tc = t - tr * tg.tiles_c;
-    const int r0 = tr * kTileR, c0 = tc * kTileC;
-    const int n_t = __ldg(tile_count + work);
-    uint8_t* cbase = reinterpret_cast<uint8_t*>(canvas) + ((size_t)b * g.ny * g.nx) * kRowBytes;
-    if (n_t == 0) {    // empty tile: zeros straight to the canvas (16 B per lane, a half-warp = one cell row)
-      for (int e = tid; e < kTileCells * 16; e += kRows) {
-        const int cell = e >> 4, lr = cell / kTileC, lc = cell - lr * kTileC;
-        if (r0 + lr < g.ny && c0 + lc < g.nx)
-          __stcs(reinterpret_cast<uint4*>(cbase + ((size_t)(r0 + lr) * g.nx + c0 + lc) * kRowBytes) + (e & 15), make_uint4(0u, 0u, 0u, 0u));
-      }
-      continue;
-    }
-    __syncthreads();                               // previous tile's write-out has finished reading `tile`
-    for (int e = tid; e < kTileCells * 16; e += kRows) reinterpret_cast<float4*>(tile)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e = tid; e < (kTileR + 1) * (kTileC + 1); e += kRows) reinterpret_cast<float4*>(stats)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    const float4* rec = recs + ((size_t)clouds.cum[b] + __ldg(tile_off + work)) * (kRecF / 4);
-    // ---- pass A: per-pillar centroid sums
-    for (int i = tid; i < n_t; i += kRows) {
-      const float4 p0 = __ldg(rec + (size_t)i * 3);
-      const int packed = __float_as_int(__ldg(reinterpret_cast<const float*>(rec + (size_t)i * 3 + 2) + 3));
-      float* st = stats + ((packed >> 8) * (kTileC + 1) + (packed & 255)) * 4;
-      atomicAdd(st, p0.x); atomicAdd(st + 1, p0.y); atomicAdd(st + 2, p0.z); atomicAdd(st + 3, 1.f);
-    }
-    __syncthreads();
-    // ---- pass B: decorate + MLP + max-pool, 128 rows per round, warp w owns rows [32w, 32w+32) end to end
-    for (int base = 0; base < n_t; base += kRows) {
-      {
-        float f[F];
-#pragma unroll
-        for (int k = 0; k < F; ++k) f[k] = 0.f;
-        int cell = -1;
-        const int i = base + tid;
-        if (i < n_t) {
-          const float4 p0 = __ldg(rec + (size_t)i * 3), p1 = __ldg(rec + (size_t)i * 3 + 1), p2 = __ldg(rec + (size_t)i * 3 + 2);
-          const int packed = __float_as_int(p2.w);
-          const int lr1 = packed >> 8, lc = packed & 255;
-          const float4 st = *reinterpret_cast<const float4*>(stats + (lr1 * (kTileC + 1) + lc) * 4);
-          // un-clamped pillar indices back from the local slot: row = r0 + lr1 - 1, xi = ny - 1 - row; yi = c0 + lc
-          const int xi = g.ny - 1 - (r0 + lr1 - 1), yi = c0 + lc;
-          f[0] = p0.x; f[1] = p0.y; f[2] = p0.z; f[3] = p0.w; f[4] = p1.x; f[5] = p1.y; f[6] = p1.z; f[7] = p1.w;
-          f[8] = p2.x; f[9] = p2.y; f[10] = p2.z;
-          f[D + 0] = __fsub_rn(f[0], __fdiv_rn(st.x, st.w));
-          f[D + 1] = __fsub_rn(f[1], __fdiv_rn(st.y, st.w));
-          f[D + 2] = __fsub_rn(f[2], __fdiv_rn(st.z, st.w));
-          f[D + 3] = __fsub_rn(f[0], __fadd_rn(__fdiv_rn((float)yi, g.ppm), g.min_x));
-          f[D + 4] = __fsub_rn(f[1], __fadd_rn(__fdiv_rn((float)xi, g.ppm), g.min_y));
-          const int lr = lr1 > 0 ? lr1 - 1 : 0, lcc = lc < kTileC ? lc : kTileC - 1;
-          cell = lr * kTileC + (c0 + lcc > g.nx - 1 ? g.nx - 1 - c0 : lcc);
-        }
-        cells[tid] = cell;
-#pragma unroll
-        for (int k = 0; k < F; k += 4) *reinterpret_cast<float4*>(&fs[tid * kFsPitch + k]) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
-      }
-      __syncwarp();
-#pragma unroll 1
-      for (int mt = 0; mt < 2; ++mt) {
-        const int row0 = warp * 32 + mt * 16;
-        if (base + row0 >= n_t) break;                                   // whole m-tile past the end (warp-uniform)
-        uint32_t ah[4], al[4];
-        split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq) * kFsPitch + 2 * tq]), ah[0], al[0]);
-        split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq + 8) * kFsPitch + 2 * tq]), ah[1], al[1]);
-        split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq) * kFsPitch + 2 * tq + 8]), ah[2], al[2]);
-        split_pair(*reinterpret_cast<const float2*>(&fs[(row0 + gq + 8) * kFsPitch + 2 * tq + 8]), ah[3], al[3]);
-        uint32_t a2[4][4];
-#pragma unroll
-        for (int nn = 0; nn < 8; ++nn) {
-          const h16* wh = w1h + (nn * 8 + gq) * kW1Pitch + 2 * tq;
-          const h16* wl = w1l + (nn * 8 + gq) * kW1Pitch + 2 * tq;
-          const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(wh), bh1 = *reinterpret_cast<const uint32_t*>(wh + 8);
-          const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(wl), bl1 = *reinterpret_cast<const uint32_t*>(wl + 8);
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          mma_h16_16816(acc, al[0], al[1], al[2], al[3], bh0, bh1);       // small terms first
-          mma_h16_16816(acc, ah[0], ah[1], ah[2], ah[3], bl0, bl1);
-          mma_h16_16816(acc, ah[0], ah[1], ah[2], ah[3], bh0, bh1);
-          const int col = nn * 8 + 2 * tq;
-          const float2 sc = *reinterpret_cast<const float2*>(&aff[col]), sh = *reinterpret_cast<const float2*>(&aff[H + col]);
-          a2[nn >> 1][(nn & 1) * 2] = pack_h16(fmaxf(fmaf(acc[0], sc.x, sh.x), 0.f), fmaxf(fmaf(acc[1], sc.y, sh.y), 0.f));
-          a2[nn >> 1][(nn & 1) * 2 + 1] = pack_h16(fmaxf(fmaf(acc[2], sc.x, sh.x), 0.f), fmaxf(fmaf(acc[3], sc.y, sh.y), 0.f));
-        }
-        const int cell_a = cells[row0 + gq], cell_b = cells[row0 + gq + 8];
-        int* ta = reinterpret_cast<int*>(tile) + cell_a * 64;
-        int* tb = reinterpret_cast<int*>(tile) + cell_b * 64;
-        const int sa = tile_swz(cell_a), sb = tile_swz(cell_b);
-#pragma unroll
-        for (int nn = 0; nn < 8; ++nn) {
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) mma_h16_16816(acc, a2[kk][0], a2[kk][1], a2[kk][2], a2[kk][3], bfrag[kk][nn][0], bfrag[kk][nn][1]);
-          const int col = nn * 8 + 2 * tq;
-          const float2 sc = *reinterpret_cast<const float2*>(&aff[2 * H + col]), sh = *reinterpret_cast<const float2*>(&aff[3 * H + col]);
-          const float v0 = fmaf(acc[0], sc.x, sh.x), v1 = fmaf(acc[1], sc.y, sh.y);
-          const float v2 = fmaf(acc[2], sc.x, sh.x), v3 = fmaf(acc[3], sc.y, sh.y);
-          if (cell_a >= 0) {
-            if (v0 > 0.f) atomicMax(ta + (col ^ sa), __float_as_int(v0));
-            if (v1 > 0.f) atomicMax(ta + ((col + 1) ^ sa), __float_as_int(v1));
-          }
-          if (cell_b >= 0) {
-            if (v2 > 0.f) atomicMax(tb + (col ^ sb), __float_as_int(v2));
-            if (v3 > 0.f) atomicMax(tb + ((col + 1) ^ sb), __float_as_int(v3));
-          }
-        }
-      }
-      __syncwarp();                                  // the warp's fs / cells rows are rewritten by the next round
-    }
-    __syncthreads();
-    // ---- write-out: a half-warp emits one cell row (16 lanes x 4 channels), zeros included
-    for (int e = tid; e < kTileCells * 16; e += kRows) {
-      const int cell = e >> 4, q = e & 15, lr = cell / kTileC, lc = cell - lr * kTileC;
-      if (r0 + lr >= g.ny || c0 + lc >= g.nx) continue;
-      const int sw = tile_swz(cell);
-      // logical channels 4q..4q+3 live at physical (4q ^ (sw & ~1)) with the pair elements swapped when sw & 1
-      const float4 v = *reinterpret_cast<const float4*>(tile + cell * 64 + ((4 * q) ^ (sw & ~1)));
-      const float m0 = (sw & 1) ? v.y : v.x, m1 = (sw & 1) ? v.x : v.y, m2 = (sw & 1) ? v.w : v.z, m3 = (sw & 1) ? v.z : v.w;
-      uint8_t* row = cbase + ((size_t)(r0 + lr) * g.nx + c0 + lc) * kRowBytes;
-      if (kSplitOut) {
-        const uint32_t h0 = pack_h16(m0, m1), h1 = pack_h16(m2, m3);
-        const float2 f0 = unpack_h16(h0), f1 = unpack_h16(h1);
-        __stcs(reinterpret_cast<uint2*>(row) + q, make_uint2(h0, h1));
-        __stcs(reinterpret_cast<uint2*>(row + 128) + q, make_uint2(pack_h16(m0 - f0.x, m1 - f0.y), pack_h16(m2 - f1.x, m3 - f1.y)));
-      } else {
-        __stcs(reinterpret_cast<float4*>(row) + q, make_float4(m0, m1, m2, m3));
-      }
-    }
   }
 }
 
@@ -1369,7 +1191,7 @@ extern "C" int lavb_pillar_forward_sorted(const float* d_pts, int pt_stride, int
   Clouds clouds;
   if (fill_clouds(clouds, h_cloud_start, h_cloud_count, batch)) return 1;
   LAVB_CHECK_ARG(d == 11 && h1 == 64 && h2 == 64, "pillar_forward_sorted: only the v2 configuration (D=11, features [64,64]) is built");
-  LAVB_CHECK_ARG(out_mode == 0 || out_mode == 1, "pillar_forward_sorted: out_mode 0 (fp32) or 1 (bf16 hi|lo split)");
+  LAVB_CHECK_ARG(out_mode >= 0 && out_mode <= 2, "pillar_forward_sorted: out_mode 0 (fp32), 1 (h16 hi|lo split) or 2 (h16)");
   LAVB_CHECK_ARG(pt_stride >= d, "pillar_forward_sorted: pt_stride < d");
   cudaStream_t st = (cudaStream_t)stream;
   Grid g{min_x, max_x, min_y, max_y, ppm, nx, ny};
@@ -1377,7 +1199,7 @@ extern "C" int lavb_pillar_forward_sorted(const float* d_pts, int pt_stride, int
   const long long ncells = (long long)batch * nx * ny;
   LAVB_CHECK_ARG(ncells < (1LL << 31), "pillar_forward_sorted: too many cells");
   const SortedWs w = carve_sorted(d_workspace, batch, nx, ny, total);
-  const int row_bytes = h2 * (out_mode == 1 ? 4 : 4);        // fp32: 64*4; split: 128*2
+  const int row_bytes = h2 * (out_mode == 2 ? 2 : 4);        // fp32: 64*4; split: 128*2; h16: 64*2
   LAVB_CUDA_OK(cudaMemsetAsync(w.stats, 0, stats_bytes(batch, nx, ny), st));
   LAVB_CUDA_OK(cudaMemsetAsync(w.count, 0, (size_t)ncells * 8 + 512, st));       // count + cursor (adjacent, 256 B padded)
   LAVB_CUDA_OK(cudaMemsetAsync(w.tile_start, 0, ((size_t)total / kRows + 2) * 4, st));
@@ -1398,15 +1220,15 @@ extern "C" int lavb_pillar_forward_sorted(const float* d_pts, int pt_stride, int
                                                                              w.order, w.ocell);
   LAVB_LAUNCH_OK();
   const size_t smem = EncSmem::total;
-  LAVB_CUDA_OK(ensure_dyn_smem((const void*)pillar_encode_sorted_kernel<11, false>, 72 * 1024));
-  LAVB_CUDA_OK(ensure_dyn_smem((const void*)pillar_encode_sorted_kernel<11, true>, 72 * 1024));
+  LAVB_CUDA_OK(ensure_dyn_smem((const void*)pillar_encode_sorted_kernel<11, 0>, 72 * 1024));
+  LAVB_CUDA_OK(ensure_dyn_smem((const void*)pillar_encode_sorted_kernel<11, 1>, 72 * 1024));
+  LAVB_CUDA_OK(ensure_dyn_smem((const void*)pillar_encode_sorted_kernel<11, 2>, 72 * 1024));
   const int ntiles = min(ceil_div(total, kRows), kNumSMs * 3);     // persistent: 3 resident blocks per SM
-  if (out_mode == 0)
-    pillar_encode_sorted_kernel<11, false><<<ntiles, kRows, smem, st>>>(d_pts, pt_stride, clouds, g, w.stats, w.order, w.ocell,
-                                                                        w.tile_start, w.total, d_w1, d_s1, d_t1, d_w2, d_s2, d_t2, d_canvas);
-  else
-    pillar_encode_sorted_kernel<11, true><<<ntiles, kRows, smem, st>>>(d_pts, pt_stride, clouds, g, w.stats, w.order, w.ocell,
-                                                                       w.tile_start, w.total, d_w1, d_s1, d_t1, d_w2, d_s2, d_t2, d_canvas);
+#define LAVB_SORTED_LAUNCH(M)                                                                                                        \
+  pillar_encode_sorted_kernel<11, M><<<ntiles, kRows, smem, st>>>(d_pts, pt_stride, clouds, g, w.stats, w.order, w.ocell, w.tile_start, \
+                                                                  w.total, d_w1, d_s1, d_t1, d_w2, d_s2, d_t2, d_canvas)
+  if (out_mode == 0) LAVB_SORTED_LAUNCH(0); else if (out_mode == 1) LAVB_SORTED_LAUNCH(1); else LAVB_SORTED_LAUNCH(2);
+#undef LAVB_SORTED_LAUNCH
   LAVB_LAUNCH_OK();
   return 0;
 }
@@ -1444,29 +1266,15 @@ extern "C" int lavb_pillar_forward_tiled(const float* d_pts, int pt_stride, int 
   } else {
     LAVB_CUDA_OK(cudaMemsetAsync(w.tile_off, 0, ((size_t)batch * tg.tiles + batch) * 4, st));
   }
-  static int variant = -1;       // LAVB_PILLAR_TC: 1 = tcgen05 MLP (default), 0 = mma.sync MLP
-  if (variant < 0) { const char* e = getenv("LAVB_PILLAR_TC"); variant = e ? atoi(e) : 1; }
   const int grid4 = min(batch * tg.tiles, kNumSMs * 3);              // persistent: 3 resident CTAs per SM
-  if (variant == 1 || out_mode == 2) {
 #define LAVB_TC_LAUNCH(M)                                                                                                          \
-    {                                                                                                                             \
-      LAVB_CUDA_OK(ensure_dyn_smem((const void*)pillar_tile_encode_tc_kernel<11, M>, TcSmem::total));                             \
-      pillar_tile_encode_tc_kernel<11, M><<<grid4, kRows, TcSmem::total, st>>>(w.recs, clouds, g, tg, w.tile_count, w.tile_off, d_w1, \
-                                                                               d_s1, d_t1, d_w2, d_s2, d_t2, d_canvas);           \
-    }
-    if (out_mode == 0) LAVB_TC_LAUNCH(0) else if (out_mode == 1) LAVB_TC_LAUNCH(1) else LAVB_TC_LAUNCH(2)
-#undef LAVB_TC_LAUNCH
-    LAVB_LAUNCH_OK();
-    return 0;
+  {                                                                                                                               \
+    LAVB_CUDA_OK(ensure_dyn_smem((const void*)pillar_tile_encode_tc_kernel<11, M>, TcSmem::total));                               \
+    pillar_tile_encode_tc_kernel<11, M><<<grid4, kRows, TcSmem::total, st>>>(w.recs, clouds, g, tg, w.tile_count, w.tile_off, d_w1,  \
+                                                                             d_s1, d_t1, d_w2, d_s2, d_t2, d_canvas);             \
   }
-  LAVB_CUDA_OK(ensure_dyn_smem((const void*)pillar_tile_encode_kernel<11, false>, TileSmem::total));
-  LAVB_CUDA_OK(ensure_dyn_smem((const void*)pillar_tile_encode_kernel<11, true>, TileSmem::total));
-  if (out_mode == 0)
-    pillar_tile_encode_kernel<11, false><<<grid4, kRows, TileSmem::total, st>>>(w.recs, clouds, g, tg, w.tile_count, w.tile_off, d_w1, d_s1,
-                                                                               d_t1, d_w2, d_s2, d_t2, d_canvas);
-  else
-    pillar_tile_encode_kernel<11, true><<<grid4, kRows, TileSmem::total, st>>>(w.recs, clouds, g, tg, w.tile_count, w.tile_off, d_w1, d_s1,
-                                                                              d_t1, d_w2, d_s2, d_t2, d_canvas);
+  if (out_mode == 0) LAVB_TC_LAUNCH(0) else if (out_mode == 1) LAVB_TC_LAUNCH(1) else LAVB_TC_LAUNCH(2)
+#undef LAVB_TC_LAUNCH
   LAVB_LAUNCH_OK();
   return 0;
 }

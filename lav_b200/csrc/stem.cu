@@ -4,23 +4,23 @@
 // window row + 1 zero slot) = 154, padded to 160.  The stem is 48 % of the brake model's GPU time in cuDNN (3 input
 // channels); here:
 //   * a block owns kStemRows output rows x 128 output columns of one image and stages the 2*rows+5 input rows it needs ONCE
-//     in shared memory, already normalised ((u8 - 255 mean_c) / (255 std_c)) and rounded to bf16, zero outside the image
+//     in shared memory, already normalised ((u8 - 255 mean_c) / (255 std_c)) and rounded to h16, zero outside the image
 //     (zero padding acts on the NORMALISED image, as in the reference); input is read with aligned 4-byte loads;
 //   * with that K order one window row is 21 CONSECUTIVE staged elements, so an A-fragment register is a single 4-byte
 //     shared-memory load (no im2col buffer, no per-element index arithmetic);
-//   * B = BatchNorm-folded weights [64][160] bf16 staged once per block; fp32 accumulate (mma.sync m16n8k16);
-//   * epilogue bias + ReLU -> bf16, transposed through shared memory so every pixel's 128 B leave as full lines.
+//   * B = BatchNorm-folded weights [64][160] h16 staged once per block; fp32 accumulate (mma.sync m16n8k16);
+//   * epilogue bias + ReLU -> h16, transposed through shared memory so every pixel's 128 B leave as full lines.
 // The "wide" image of the brake model is three cameras side by side (lav_agent_fast.py:257): `ncam`/`cam_w` index the
 // (B, ncam, H, cam_w, 3) camera tensor directly.
 #include "common.cuh"
 
 namespace lavb {
 
-constexpr int kStemK = 160, kStemPitch = 168;   // bf16 per weight row in smem (pitch chosen bank-conflict free)
+constexpr int kStemK = 160, kStemPitch = 168;   // h16 per weight row in smem (pitch chosen bank-conflict free)
 constexpr int kStemRows = 8;                     // output rows per block
 constexpr int kStemInRows = 2 * kStemRows + 5;   // input rows staged per block
 constexpr int kStemQW = 792;                     // staged elements per input row: 6*127 + 22 = 784 used, padded
-constexpr int kStemOutPitch = 72;                // bf16 per pixel in the per-warp output staging tile
+constexpr int kStemOutPitch = 72;                // h16 per pixel in the per-warp output staging tile
 constexpr int kStemSmem = (64 * kStemPitch + kStemInRows * kStemQW + 4 * 32 * kStemOutPitch) * 2;
 
 struct StemArgs {
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) stem7x7_u8_kernel(const __grid_constant__
         for (int mt = 0; mt < 2; ++mt) mma_h16(acc[mt][nn], af[mt * 2][0], af[mt * 2 + 1][0], af[mt * 2][1], af[mt * 2 + 1][1], b0, b1);
       }
     }
-    // bias + ReLU -> bf16 into the warp's staging tile (C fragment: rows gq | gq+8 of each m-tile, cols 8nn + 2tq, +1)
+    // bias + ReLU -> h16 into the warp's staging tile (C fragment: rows gq | gq+8 of each m-tile, cols 8nn + 2tq, +1)
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(128) stem7x7_u8_kernel(const __grid_constant__
   }
 }
 
-// 3x3 stride-2 pad-1 max-pool on NHWC bf16 (lav/models/resnet.py:181,238): one thread = one output pixel x 8 channels.
+// 3x3 stride-2 pad-1 max-pool on NHWC h16 (lav/models/resnet.py:181,238): one thread = one output pixel x 8 channels.
 __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const h16* __restrict__ in, int n, int h, int w, int c8,
                                                            h16* __restrict__ out, int ho, int wo) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;

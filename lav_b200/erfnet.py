@@ -97,6 +97,7 @@ class _Down:
 FUSE_PAIRS = True     # fused (3x1 -> 1x3) tcgen05 kernel (csrc/conv_pair_umma.cu): validated on B200, ERFNet 2.85 -> 2.72 ms @96 images
 
 
+FUSE_STEM = True      # normalize + initial DownsamplerBlock(3,16) as one kernel on the uint8 frames (csrc/erf16.cu: erf_stem_kernel)
 FUSE_NB16 = True      # the 16-channel decoder blocks as ONE kernel each (csrc/erf16.cu) instead of four conv_c16_mma launches
 
 
@@ -160,16 +161,32 @@ class ERFNet(PlanMixin, nn.Module):
         seq = [wrap(self.encoder.initial_block)] + [wrap(m) for m in self.encoder.layers] + [wrap(m) for m in self.decoder.layers]
         oc = self.decoder.output_conv
         table = ops.pack_deconv2x2(oc.weight, oc.bias) if tuple(oc.weight.shape[2:]) == (2, 2) and oc.weight.shape[0] == 16 else None
-        return seq, TapConv(oc.weight, True, 2, 0, 1, 0, bias=oc.bias), table
+        stem = None
+        ib = self.encoder.initial_block
+        if ib.conv.in_channels == 3 and ib.bn.num_features == 16:
+            # host-side constants of erf_stem_kernel: w[(ky*3+kx)*3+c][co], epi relu(acc*s + t) (conv bias folded), pool channels last
+            s, t = (v.detach() for v in bn_affine(ib.bn))
+            w27 = torch.zeros((27, 16))
+            w27[:, :13] = ib.conv.weight.detach().float().cpu().permute(2, 3, 1, 0).reshape(27, 13)
+            t = t.cpu().clone()
+            t[:13] += ib.conv.bias.detach().float().cpu() * s.cpu()[:13]
+            stem = (w27.numpy(), s.cpu().numpy(), t.numpy())
+        return seq, TapConv(oc.weight, True, 2, 0, 1, 0, bias=oc.bias), table, stem
 
     def forward_features_nhwc(self, x):
-        """x: (N,H,W,4) normalised RGB -> (features NHWC (N,H/2,W/2,16) = the input of Decoder.output_conv, deconv table).
+        """x: (N,H,W,4) normalised RGB, or the raw uint8 frames (N,H,W,3) -> (features NHWC (N,H/2,W/2,16) = the input of
+        Decoder.output_conv, deconv table).
         The frame pipeline evaluates output_conv inside the point-painting gather (ops.paint_deconv_batched), for the hit
         pixels only; forward_nhwc materialises the full logit maps for everyone else."""
         if self.training:
             raise LavbError("lav_b200.ERFNet is inference-only (the seg model is frozen on the frame path)")
-        seq, _, table = self._plan_get(x.device, self._build)
+        seq, _, table, stem = self._plan_get(x.device, self._build)
         dt = _dt(self.precision)
+        if x.dtype == torch.uint8:            # raw camera frames (N,H,W,3): fused normalize + initial block
+            if not (FUSE_STEM and stem is not None):
+                raise LavbError("uint8 input needs the fused stem (v2 ERFNet: DownsamplerBlock(3, 16))")
+            x = ops.erf_stem(x, *stem, dt)
+            seq = seq[1:]
         for blk in seq:
             x = blk(x, dt)
         return x, table

@@ -162,7 +162,12 @@ def resnet18(pretrained=False, num_channels=3, **kw):
     return ResNet18(num_channels=num_channels)
 
 
-GRU_KERNEL = True     # cluster-persistent plan GRU (csrc/gru_cluster.cu): validated on B200, roll-out 1.06 -> 0.71 ms @192 sequences
+# Cluster-persistent plan GRU (csrc/gru_cluster.cu).  Validated on B200 against nn.GRU (8e-4 of the output scale per 20-step
+# roll-out) and 1.49x faster than cuDNN's 100 launch pairs (1.06 -> 0.71 ms @192 sequences, -10 us/frame).  OFF by default: its
+# recurrent weights and exchanged hidden state are h16, and on the seeded (non-contractive) planner weights the 5 x 20-step
+# plan roll-out amplifies that to 1.7e-2 .. 5e-2 of the waypoint scale at BASELINE config 3 (tests/test_gpu_config_sizes.py,
+# gru_kernel=True is an expected failure there) — outside the 1e-2 the product path is held to.  cuDNN's fp32 GRU stays.
+GRU_KERNEL = False
 
 
 # ----------------------------------------------------------------------------- planners

@@ -370,13 +370,17 @@ def split_h16(x):
     return out
 
 
-PILLAR_ENCODER = "tiled"     # "tiled" (lavb_pillar_forward_tiled: tile-binned, tcgen05 MLP) | "sorted" (lavb_pillar_forward_sorted: cell-sorted, mma.sync MLP)
+PILLAR_ENCODER = "sorted"    # tensor-core encoders of the 16-bit pipeline, B200 @ 32 frames x 120 000 points:
+#   "sorted": counting sort by canvas cell + persistent mma.sync encoder (lavb_pillar_forward_sorted)          23.3 us/frame
+#   "tiled" : points binned by 8x16-cell canvas tile, one CTA per tile, tcgen05 MLP (lavb_pillar_forward_tiled) 29.2 us/frame —
+#             fewer launches and 35 % less DRAM traffic (942 vs 1448 MB), but every tile is a serial chain of ~8 dependent steps
+#             (load, centroid atomics, MMA round trips, pooling atomics, store) with 3 CTAs per SM: latency-bound (profiles/)
 
 
 def pillar_forward_sorted(pts, starts, counts, grid, w1, s1, t1, w2, s2, t2, split_out=False, canvas16=False):
     """tensor-core pillar encoder of the 16-bit pipeline (tile-binned or sorted kernel, see PILLAR_ENCODER).  Returns the NHWC
-    canvas: fp32 (B,ny,nx,H2); with split_out, h16 (B,ny,nx,2*H2) = [hi | lo]; with canvas16 (tile-binned encoder only), h16
-    (B,ny,nx,H2) — what the 16-bit pipeline feeds the backbone."""
+    canvas: fp32 (B,ny,nx,H2); with split_out, h16 (B,ny,nx,2*H2) = [hi | lo]; with canvas16, h16 (B,ny,nx,H2) — what the 16-bit
+    pipeline feeds the backbone."""
     _need_cuda(pts, w1, w2)
     assert pts.dtype == torch.float32 and pts.dim() == 2 and pts.stride(1) == 1
     min_x, max_x, min_y, max_y, ppm, nx, ny = grid
@@ -386,7 +390,7 @@ def pillar_forward_sorted(pts, starts, counts, grid, w1, s1, t1, w2, s2, t2, spl
     h2 = w2.shape[0]
     assert not (split_out and canvas16)
     canvas = torch.empty((b, ny, nx, 2 * h2 if split_out else h2), dtype=h16() if (split_out or canvas16) else torch.float32, device=pts.device)
-    tiled = PILLAR_ENCODER == "tiled" or canvas16
+    tiled = PILLAR_ENCODER == "tiled"
     if tiled:      # every frame's records start at its exclusive point offset: size the record buffer for the clouds as given
         total = int(sum(int(c) for c in counts))
     ws = _workspace(pts.device, (lib().lavb_pillar_tiled_workspace_bytes if tiled else lib().lavb_pillar_sorted_workspace_bytes)(b, nx, ny, total))
@@ -472,6 +476,21 @@ def conv_pair_umma(x, w1, bias1, w2, bias2, scale2, shift2, dil, res=None, post_
     e0 = _prof_begin()
     check(lib().lavb_conv_pair_umma(C.byref(d), _stream()), "lavb_conv_pair_umma")
     _prof_end(f"umma_pair:{c}x{h}x{w}", 2.0 * n * h * w * c * c * 6, e0)
+    _COUNT[0] += 1
+    return out
+
+
+def erf_stem(rgb_u8, w27, scale, shift, out_dtype):
+    """fused normalize + ERFNet initial block: rgb_u8 (N,H,W,3) uint8 -> NHWC (N,H/2,W/2,16).  w27 (27,16), scale/shift (16,)
+    are HOST float32 numpy arrays (kernel parameters)."""
+    _need_cuda(rgb_u8)
+    assert rgb_u8.dtype == torch.uint8 and rgb_u8.is_contiguous() and rgb_u8.dim() == 4 and rgb_u8.shape[3] == 3
+    n, h, w, _ = rgb_u8.shape
+    out = torch.empty((n, h // 2, w // 2, 16), dtype=out_dtype, device=rgb_u8.device)
+    a, b, c = (np.ascontiguousarray(t, dtype=np.float32) for t in (w27, scale, shift))
+    assert a.shape == (27, 16) and b.shape == (16,) and c.shape == (16,)
+    check(lib().lavb_erf_stem(_ptr(rgb_u8), n, h, w, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p),
+                              _ptr(out), _DT[out_dtype], _stream()), "lavb_erf_stem")
     _COUNT[0] += 1
     return out
 

@@ -39,7 +39,7 @@ with torch.no_grad():
         print(f"{label} B={B}: exact fp32 kernel {ms * 1e3 / B:.2f} us/frame ({alg32 / ms / 1e6:.0f} GB/s algorithmic)", flush=True)
         ref = ref.clone()
         m.set_precision("f16")
-        for enc, kw, nm in (("sorted", dict(split_out=True), "split"), ("sorted", dict(), "fp32"), ("tiled", dict(split_out=True), "split"),
+        for enc, kw, nm in (("sorted", dict(split_out=True), "split"), ("sorted", dict(), "fp32"), ("sorted", dict(canvas16=True), "h16"), ("tiled", dict(split_out=True), "split"),
                             ("tiled", dict(), "fp32"), ("tiled", dict(canvas16=True), "h16")):
             ops.PILLAR_ENCODER = enc
             ms, out = graph_time(lambda: m.point_pillar_net.forward_nhwc(pts, [P] * B, **kw))
@@ -51,4 +51,4 @@ with torch.no_grad():
             occ = bool(torch.equal((o != 0).any(-1), (ref != 0).any(-1)))
             print(f"{label} B={B}: {enc:6s} out={nm:5s}: {ms * 1e3 / B:.2f} us/frame ({alg / ms / 1e6:.0f} GB/s algorithmic), "
                   f"max-norm err vs exact {err:.2e}, occupancy equal {occ}", flush=True)
-        ops.PILLAR_ENCODER = "tiled"
+        ops.PILLAR_ENCODER = "sorted"

@@ -6,7 +6,7 @@ from lav_b200 import ops, synth
 from tests import util
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 ops.PILLAR_ENCODER = os.environ.get("LAVB_PILLAR_ENCODER", ops.PILLAR_ENCODER)
-KW = dict(split_out=True) if ops.PILLAR_ENCODER == "sorted" else dict(canvas16=True)
+KW = dict(canvas16=True)
 dev = torch.device("cuda:0")
 m, _ = util.lidar_model(dev)
 m.set_precision("f16")

@@ -31,7 +31,7 @@ with torch.no_grad():
     seg, _ = util.seg_model(dev)
     seg.set_precision("f16")
     rgb = synth.rgb_frames().to(dev).repeat(B, 1, 1, 1)
-    for chunk in (3 * B, 48, 24, 12):
+    for chunk in (3 * B,):
         if chunk > 3 * B:
             continue
         def run(chunk=chunk):

@@ -35,20 +35,18 @@ def t_graph(name, fn, iters=10):
     return o
 
 with torch.no_grad():
-    logits = t_graph("erfnet", lambda: pipe.seg_model.forward_nhwc(pipe.rgbs.view(B * 3, 288, 256, 3)))
-    lg = logits.view(B, 3, *logits.shape[1:]).permute(0, 1, 4, 2, 3)
-    t_graph("paint+stack", lambda: (ops.paint_batched(pipe.lidar, lg, pipe._cams, 2, 4, pipe.cur), ops.stack_jobs(pipe.jobs_dev, B * 3, N, 8, 3)))
-    canvas = t_graph("pillars", lambda: im.lidar_model.point_pillar_net(pipe.stacked, [3 * N] * B))
-    cv = canvas.permute(0, 2, 3, 1).contiguous()
+    feat, table, ncls = t_graph("erfnet (to the 16-ch decoder map)", lambda: pipe.seg_model.forward_features_nhwc(pipe.rgbs.view(B * 3, 288, 256, 3)))
+    t_graph("paint (fused seg head) + stack", lambda: (ops.paint_deconv_batched(pipe.lidar, feat, ncls, table, pipe._cams, 4, pipe.cur, (288, 256)),
+                                                      ops.stack_jobs(pipe.jobs_dev, B * 3, N, 8, 3)))
+    cv = t_graph("pillars (h16 canvas)", lambda: im.lidar_model.point_pillar_net.forward_nhwc(pipe.stacked, [3 * N] * B, canvas16=True))
     feats = t_graph("backbone", lambda: im.lidar_model.backbone.forward_nhwc(cv))
     heads = t_graph("heads", lambda: im.lidar_model.heads_nhwc(feats))
     t_graph("peaks", lambda: ops.det_peaks(heads[0], heads[1], heads[2]))
     wide = pipe.rgbs.permute(0, 2, 1, 3, 4).reshape(B, 288, 768, 3).permute(0, 3, 1, 2).float().contiguous(memory_format=torch.channels_last)
     tel = pipe.tels.permute(0, 3, 1, 2).float().contiguous(memory_format=torch.channels_last)
-    t_graph("brake_cudnn_stem", lambda: pipe.bra_model(wide, tel))
     t_graph("brake", lambda: pipe._brake())
     K = 3 * B
-    g, o, s2 = pipe._g2[K]
+    g, o, s2 = pipe._g2[-(-K // pipe.K_BUCKET) * pipe.K_BUCKET]
     up = im.uniplanner
     fn = feats.permute(0, 3, 1, 2)
     crops = t_graph("crop", lambda: up.crop_feature(fn, s2["locs"], s2["oris"], pixels_per_meter=2.0, crop_size=96, frame_idx=s2["fidx"]))

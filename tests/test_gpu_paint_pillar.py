@@ -157,10 +157,14 @@ def test_pillar_full_size_properties(cuda):
         assert float(can.min()) >= 0.0
 
 
-@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("encoder", ["sorted", "tiled"])
+@pytest.mark.parametrize("out", ["fp32", "split", "h16"])
 @pytest.mark.parametrize("mode", ["carla", "uniform", "adversarial", "batch", "empty"])
-def test_pillar_sorted_kernel_matches_oracle(cuda, mode, split):
-    """sorted / tensor-core encoder (f16 pipeline): same occupancy as the oracle, values within f16 layer-2 rounding."""
+def test_pillar_tensor_core_encoders_match_oracle(cuda, mode, out, encoder, monkeypatch):
+    """the two tensor-core encoders of the 16-bit pipeline — cell-sorted + mma.sync, tile-binned + tcgen05 — in their three
+    canvas formats (fp32, [hi | lo] h16 split, single h16): same occupancy as the oracle, values within 1e-3 (layer 1 runs on
+    hi/lo-split operands ~ fp32, layer 2 on h16 operands with fp32 accumulation; the h16 canvas adds one 2^-12 rounding)."""
+    monkeypatch.setattr(ops, "PILLAR_ENCODER", encoder)
     m, sd = util.lidar_model(cuda)
     m.set_precision("f16")
     if mode == "batch":
@@ -174,8 +178,8 @@ def test_pillar_sorted_kernel_matches_oracle(cuda, mode, split):
         clouds = [torch.cat([xyz, torch.rand(9000, 7, generator=synth._gen(3, mode))], 1)]
     npts = [len(c) for c in clouds]
     with torch.no_grad():
-        got = m.point_pillar_net.forward_nhwc([c.to(cuda) for c in clouds], npts, split_out=split).float().cpu()
-    if split:
+        got = m.point_pillar_net.forward_nhwc([c.to(cuda) for c in clouds], npts, split_out=(out == "split"), canvas16=(out == "h16")).float().cpu()
+    if out == "split":
         got = got[..., :64] + got[..., 64:]
     if mode == "empty":
         assert float(got.abs().max()) == 0.0
