@@ -310,6 +310,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=6)
     ap.add_argument("--train-warmup", type=int, default=3)
     ap.add_argument("--train-amp", action="store_true", default=False, help="bf16 autocast for the training leg (opt-in)")
+    ap.add_argument("--no-train-amp-leg", action="store_true", help="skip the extra bf16-autocast run of the training step")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 
@@ -473,6 +474,10 @@ def main():
         # headline: conv_umma_kernel over ALL its launches of a tick (ERFNet, backbone, heads: ~110 launches, 9 shapes)
         roof["umma"] = entry([r for v in umma.values() for r in v], "tensor", "TFLOP/s", tf_peak, 1e12)
         roof["umma"]["kernel"] = "conv_umma_kernel (all launches of a tick)"
+        tr_ = traffic.get("umma_tick", {})
+        if tr_.get("frames") == Bp and tr_.get("launches"):       # per launch, like `achieved`: DRAM bytes of the tick's launches / their number
+            roof["umma"]["traffic"] = tr_["dram_bytes"] / tr_["launches"]
+            roof["umma"]["traffic_source"] = tr_.get("source")
         # its largest single launch, the fused 4-head conv 384->256: DRAM bytes from the committed ncu --set full
         # capture (profiles/r01_kernels.md §1: 225.5 MB for 8 frames, tensor pipe 83.7 %), scaled to the frames per launch
         hk = [k for k in umma if k.startswith("384->256")]
@@ -502,6 +507,11 @@ def main():
         torch.cuda.empty_cache()
         train = run_train_leg(args, dev, rank, world, lid, uni)
         _dbg(f"train leg done: {train['ms_per_step']:.1f} ms/step")
+        if not args.train_amp and not args.no_train_amp_leg:      # the same step with bf16 autocast (opt-in mode of LAVTrainer), reported beside it
+            a3 = argparse.Namespace(**vars(args))
+            a3.train_amp, a3.train_steps, a3.train_warmup = True, max(3, args.train_steps // 2), 2
+            amp = run_train_leg(a3, dev, rank, world, lid, uni)
+            train["bf16_autocast"] = {k: amp[k] for k in ("value", "unit", "ms_per_step", "precision", "loss", "max_mem_gb")}
     latency, gpu_ref = None, None
     if rank == 0 and world == 1 and not args.no_gpu_reference:
         # batch-1 latency of one agent tick (the CARLA agent runs batch 1 at 20 Hz, lav_agent.py:32): host sensors in, waypoints +

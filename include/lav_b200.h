@@ -112,10 +112,11 @@ int lavb_pillar_forward(const float* d_pts, int pt_stride, int d,
                         const float* d_w2, const float* d_s2, const float* d_t2, int h2,
                         void* d_canvas, int canvas_dtype, void* d_workspace, void* stream);
 
-/* Sorted, atomic-free variant for the tensor-core pipeline: counting sort of the points by canvas cell, layer 1 in
- * fp32, layer 2 on the tensor cores (h16 operands, fp32 accumulate), one canvas row written per pillar and the rows
- * of empty cells zero-filled by the scan pass.  out_mode 0: fp32 canvas [B][ny][nx][h2]; 1: h16 canvas
- * [B][ny][nx][hi(h2) | lo(h2)] (the error-free split lavb_split_h16 produces).  Same semantics otherwise. */
+/* Sorted, atomic-free variant for the tensor-core pipeline (the product encoder): counting sort of the points by canvas cell,
+ * layer 1 on hi/lo-split h16 operands (~ fp32), layer 2 on h16 operands with fp32 accumulation (mma.sync), one canvas row written
+ * per pillar and the rows of empty cells zero-filled by the scan pass.  out_mode 0: fp32 canvas [B][ny][nx][h2]; 1: h16 canvas
+ * [B][ny][nx][hi(h2) | lo(h2)] (the error-free split lavb_split_h16 produces); 2: h16 canvas [B][ny][nx][h2].  Same semantics
+ * otherwise. */
 size_t lavb_pillar_sorted_workspace_bytes(int batch, int nx, int ny, long long total_points);
 int lavb_pillar_forward_sorted(const float* d_pts, int pt_stride, int d,
                                const long long* h_cloud_start, const int* h_cloud_count, int batch,
@@ -159,7 +160,7 @@ int lavb_pillar_scatter_max_bwd(const float* d_gcanvas, const int* d_argmax, con
  *         a=max(a,0); if sigmoid a=1/(1+exp(-a)).   Null pointers skip a step.
  * d_w: [ntaps][cin][cout_pad] fp32 with cout_pad = cout rounded up to 16.
  * A strided Conv2d uses in_s=stride, dy=ky*dil-pad; a ConvTranspose2d is issued once per output phase with
- * in_s=1, out_s=stride (lav_b200/packing.py builds the tap lists). */
+ * in_s=1, out_s=stride (lav_b200/layers.py builds the tap lists). */
 typedef struct {
   const void* in; int in_dtype; int n, hin, win, cin, in_cstride, in_coff;
   void* out; int out_dtype; int hout, wout, cout, out_cstride, out_coff;
@@ -262,6 +263,13 @@ int lavb_conv_pair_umma(const lavb_conv_pair_desc* h_desc, void* stream);
  * (n, h/2, w/2, 16) fp32 or h16. */
 int lavb_erf_stem(const void* d_rgb_u8, int n, int h, int w, const float* h_w27x16, const float* h_scale16,
                   const float* h_shift16, void* d_out, int out_dtype, void* stream);
+
+/* ---------------------------------------------------------------- fused DownsamplerBlock(16, 64)
+ * replaces: Encoder.layers[0] = DownsamplerBlock(16, 64) (lav/models/erfnet.py:12-23,71): relu(bn(cat[conv3x3 s2 p1 (16 -> 48),
+ * maxpool2x2 (16)])).  d_in: h16 NHWC (n, h, w, 16), h and w even, w <= 128; d_out: h16 NHWC (n, h/2, w/2, 64); d_w9: fp32
+ * [9 taps (ky*3+kx)][16 cin][48 cout]; d_st: fp32 [64][2] = (scale, shift), epi(a) = relu(a * scale + shift) with the conv bias
+ * folded into the first 48 shifts (the last 16 apply to the pooled channels, after the max). */
+int lavb_erf_down16(const void* d_in, void* d_out, int n, int h, int w, const float* d_w9, const float* d_st, void* stream);
 
 /* ---------------------------------------------------------------- fused 16-channel non_bottleneck_1d block
  * replaces: non_bottleneck_1d(16, dropprob, dilated=1) of the ERFNet decoder (lav/models/erfnet.py:37-63, Decoder layers 4 and 5) —

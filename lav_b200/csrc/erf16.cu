@@ -219,6 +219,141 @@ __global__ void __launch_bounds__(kSt_OH * kSt_OW) erf_stem_kernel(const unsigne
   for (int q = 0; q < 4; ++q) store4<TOut>(dst + 4 * q, make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Fused DownsamplerBlock(16, 64) (Encoder.layers[0], lav/models/erfnet.py:12-23,71): out = relu(bn(cat[conv3x3 s2 p1 (16 -> 48),
+// maxpool2x2 (16 ch)])) on the h16 16-channel map.  A CTA produces 4 output rows x (up to) 64 output columns: it stages the 9 input
+// rows it needs in shared memory split into EVEN and ODD pixel columns (tap kx = 0 reads O[x-1], kx = 1 reads E[x], kx = 2 reads
+// O[x]: every tap is a stride-1 run of 16 pixels = one ldmatrix.x4), runs the 9 taps x 6 n-tiles on mma.sync with the weight
+// fragments fetched from shared memory once per tap for both of a warp's m-tiles, max-pools the same staged pixels, and leaves the
+// 128-byte output pixels through a shared-memory staging tile as full-line stores.  Replaces conv_c16_mma<9> (147 us at 96
+// images, A fragments straight from global memory) + pool2 (33 us).
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int kDnRows = 4, kDnCols = 64, kDnInRows = 2 * kDnRows + 1, kDnPlane = kDnCols + 1;    // per row: E[0..63] | O[-1..63]
+constexpr int kDnRowPix = kDnCols + kDnPlane;                                                     // 129 pixels of 32 B per staged row
+constexpr int kDnThreads = 256;
+
+struct Dn16Args {
+  const h16* in; h16* out;
+  int n, h, w;              // input size; output (h/2, w/2, 64)
+  const float* w9;          // [9 taps (ky*3+kx)][16 cin][48 cout] fp32
+  const float* st;          // [64][2] (scale, shift): relu(a*s + t), conv bias folded into the first 48 shifts
+};
+
+__global__ void __launch_bounds__(kDnThreads, 2) erf_down16_kernel(const __grid_constant__ Dn16Args p) {
+  extern __shared__ __align__(128) uint8_t dn_sm[];
+  const uint32_t IN = (uint32_t)__cvta_generic_to_shared(dn_sm);                    // [9 rows][129 px][32 B]
+  const uint32_t WS = IN + kDnInRows * kDnRowPix * 32;                              // weights h16 [9][48 n][16 k] (B fragments: k pairs)
+  const uint32_t OUT = WS + 9 * 48 * 16 * 2;                                        // [256 px][128 B] output staging
+  float* stf = reinterpret_cast<float*>(dn_sm + (OUT - IN) + kDnRows * kDnCols * 128);   // [64][2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int ho = p.h >> 1, wo = p.w >> 1;
+  const int tiles_y = (ho + kDnRows - 1) / kDnRows;
+  const int img = blockIdx.x / tiles_y, oy0 = (blockIdx.x - img * tiles_y) * kDnRows;
+  // weights -> shared memory as h16 [tap][n][k]; affine constants
+  for (int e = tid; e < 9 * 48 * 16; e += kDnThreads) {
+    const int tap = e / (48 * 16), r = e - tap * 48 * 16, n = r >> 4, k = r & 15;
+    reinterpret_cast<h16*>(dn_sm + (WS - IN))[e] = float2h16(__ldg(p.w9 + (tap * 16 + k) * 48 + n));
+  }
+  for (int e = tid; e < 128; e += kDnThreads) stf[e] = __ldg(p.st + e);
+  // stage the input rows 2*oy0-1 .. 2*oy0+7: pixel 2x -> E[x], pixel 2x+1 -> O[x] (O[-1] = the left zero padding)
+  const h16* src = p.in + (size_t)img * p.h * p.w * 16;
+  for (int e = tid; e < kDnInRows * (2 * kDnCols + 1) * 2; e += kDnThreads) {
+    const int r = e / ((2 * kDnCols + 1) * 2), q = e - r * ((2 * kDnCols + 1) * 2), px = (q >> 1) - 1, half = q & 1;   // px = -1 .. 127
+    const int iy = 2 * oy0 - 1 + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if ((unsigned)iy < (unsigned)p.h && (unsigned)px < (unsigned)p.w) v = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)iy * p.w + px) * 16) + half);
+    const int slot = (px & 1) ? kDnCols + ((px + 1) >> 1) : (px >> 1);              // odd px -> O plane index (px+1)/2 (O[-1] at 0); even -> E[px/2]
+    const int pix = r * kDnRowPix + (px < 0 ? kDnCols : slot);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(IN + px_off(pix, half)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+  __syncthreads();
+  const int mi = lane & 7, mj = lane >> 3;
+  const int n_mt = kDnRows * (kDnCols / 16);                                        // 16 m-tiles, 2 per warp
+  float acc[2][6][4];
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int nn = 0; nn < 6; ++nn)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[m][nn][e] = 0.f;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap - 3 * ky;
+    uint32_t b[6][2];
+#pragma unroll
+    for (int nn = 0; nn < 6; ++nn) {
+      const uint32_t wa = WS + (uint32_t)(((tap * 48 + nn * 8 + gq) * 16 + 2 * tq) * 2);
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b[nn][0]) : "r"(wa));
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b[nn][1]) : "r"(wa + 16));
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const int mt = warp * 2 + m, ly = mt / (kDnCols / 16), x0 = (mt % (kDnCols / 16)) * 16;
+      // input row 2*ly + ky of the staged 9; plane / first pixel by kx: O[x0-1..] (plane slots x0.., since O[-1] sits at slot 0), E[x0..], O[x0..]
+      const int base = (2 * ly + ky) * kDnRowPix + (kx == 1 ? x0 : kDnCols + x0 + (kx == 2 ? 1 : 0));
+      const int pix = base + mi + ((mj & 1) << 3);
+      uint32_t a[4];
+      ldsm_x4(IN + px_off(pix, mj >> 1), a);
+#pragma unroll
+      for (int nn = 0; nn < 6; ++nn) mma16816(acc[m][nn], a, b[nn][0], b[nn][1]);
+    }
+  }
+  // conv epilogue -> staging tile (pixel = 128 B; 16-byte pieces rotated by the pixel index so fragment stores spread over the banks)
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int mt = warp * 2 + m, ly = mt / (kDnCols / 16), x0 = (mt % (kDnCols / 16)) * 16;
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int opix = ly * kDnCols + x0 + gq + 8 * hrow;
+#pragma unroll
+      for (int nn = 0; nn < 6; ++nn) {
+        const int c = nn * 8 + 2 * tq;
+        const float v0 = fmaxf(fmaf(acc[m][nn][2 * hrow], stf[2 * c], stf[2 * c + 1]), 0.f);
+        const float v1 = fmaxf(fmaf(acc[m][nn][2 * hrow + 1], stf[2 * c + 2], stf[2 * c + 3]), 0.f);
+        const uint32_t addr = OUT + (uint32_t)opix * 128u + (uint32_t)(((nn ^ (opix & 7)) << 4) + tq * 4);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_h16(v0, v1)) : "memory");
+      }
+    }
+  }
+  // pool branch: thread = (output pixel, 8-channel half): max over the 2x2 input pixels -> affine -> ReLU -> channels 48 + 8*half..
+  for (int e = tid; e < kDnRows * kDnCols * 2; e += kDnThreads) {
+    const int opix = e >> 1, half = e & 1, ly = opix / kDnCols, lx = opix - ly * kDnCols;
+    float m8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m8[k] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int pix = (2 * ly + 1 + dy) * kDnRowPix + (dx ? kDnCols + lx + 1 : lx);          // E[lx] / O[lx] of input rows 2oy, 2oy+1
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(IN + px_off(pix, half)));
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = unpack_h16(w4[k]); m8[2 * k] = fmaxf(m8[2 * k], f.x); m8[2 * k + 1] = fmaxf(m8[2 * k + 1], f.y); }
+      }
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = 48 + 8 * half + 2 * k;
+      o[k] = pack_h16(fmaxf(fmaf(m8[2 * k], stf[2 * c], stf[2 * c + 1]), 0.f), fmaxf(fmaf(m8[2 * k + 1], stf[2 * c + 2], stf[2 * c + 3]), 0.f));
+    }
+    const uint32_t addr = OUT + (uint32_t)opix * 128u + (uint32_t)((((6 + half) ^ (opix & 7)) << 4));
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+  }
+  __syncthreads();
+  h16* dst = p.out + (size_t)img * ho * wo * 64;
+  for (int e = tid; e < kDnRows * kDnCols * 8; e += kDnThreads) {
+    const int opix = e >> 3, j = e & 7, ly = opix / kDnCols, lx = opix - ly * kDnCols;
+    const int oy = oy0 + ly;
+    if (oy >= ho || lx >= wo) continue;
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(OUT + (uint32_t)opix * 128u + (uint32_t)((j ^ (opix & 7)) << 4)));
+    *(reinterpret_cast<uint4*>(dst + ((size_t)oy * wo + lx) * 64) + j) = v;
+  }
+}
+
 }  // namespace lavb
 
 using namespace lavb;
@@ -251,6 +386,19 @@ extern "C" int lavb_erf_stem(const void* d_rgb_u8, int n, int h, int w, const fl
   if (out_dtype == LAVB_F32) erf_stem_kernel<float><<<blocks, kSt_OH * kSt_OW, 0, (cudaStream_t)stream>>>(img, n, h, w, k, (float*)d_out);
   else if (out_dtype == LAVB_H16) erf_stem_kernel<h16><<<blocks, kSt_OH * kSt_OW, 0, (cudaStream_t)stream>>>(img, n, h, w, k, (h16*)d_out);
   else LAVB_CHECK_ARG(false, "erf_stem: output dtype must be fp32 or h16");
+  LAVB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int lavb_erf_down16(const void* d_in, void* d_out, int n, int h, int w, const float* d_w9, const float* d_st, void* stream) {
+  LAVB_CHECK_ARG(n >= 0 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0 && w <= 2 * kDnCols, "erf_down16: even input size, width <= %d (got %d x %d)", 2 * kDnCols, h, w);
+  if (n == 0) return 0;
+  Dn16Args a;
+  a.in = reinterpret_cast<const h16*>(d_in); a.out = reinterpret_cast<h16*>(d_out);
+  a.n = n; a.h = h; a.w = w; a.w9 = d_w9; a.st = d_st;
+  const int smem = kDnInRows * kDnRowPix * 32 + 9 * 48 * 16 * 2 + kDnRows * kDnCols * 128 + 128 * 4;
+  LAVB_CUDA_OK(ensure_dyn_smem((const void*)erf_down16_kernel, smem));
+  erf_down16_kernel<<<n * ceil_div(h / 2, kDnRows), kDnThreads, smem, (cudaStream_t)stream>>>(a);
   LAVB_LAUNCH_OK();
   return 0;
 }

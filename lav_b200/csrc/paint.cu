@@ -363,28 +363,49 @@ struct StackJob {            // 72 bytes
 };
 static_assert(sizeof(StackJob) == 72, "StackJob layout is part of the ABI (lav_b200.h)");
 
+// Rows are 8 floats in, 8 + n_time (= 11) floats out: a thread-per-row store pattern scatters every store instruction over 32
+// rows (44-byte stride, 11x the sector transactions).  The block therefore builds its 256 output rows in shared memory and copies
+// them out as one contiguous, fully coalesced run.
+constexpr int kStackMaxCols = 16;
 __global__ void __launch_bounds__(256) stack_jobs_kernel(const StackJob* __restrict__ jobs, int src_cols, int n_time,
                                                          int roof_filter) {
+  __shared__ float rows[256 * kStackMaxCols];
   const StackJob j = jobs[blockIdx.y];
   const int dcols = src_cols + n_time;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.n; i += gridDim.x * blockDim.x) {
-    const float* s = j.src + (size_t)i * src_cols;
-    float* d = j.dst + (size_t)i * dcols;
-    const float x = __ldg(s), y = __ldg(s + 1), z = __ldg(s + 2);
-    float nx = __fmaf_rn(z, j.R[6], __fmaf_rn(y, j.R[3], __fmul_rn(x, j.R[0])));
-    float ny = __fmaf_rn(z, j.R[7], __fmaf_rn(y, j.R[4], __fmul_rn(x, j.R[1])));
-    const float nz = __fmaf_rn(z, j.R[8], __fmaf_rn(y, j.R[5], __fmul_rn(x, j.R[2])));
-    nx = __fadd_rn(nx, j.dx);
-    ny = __fadd_rn(ny, j.dy);
-    if (roof_filter && x > -2.4f && x < 0.f && y > -0.8f && y < 0.8f && z > -1.5f && z < -1.f) nx = __int_as_float(0x7fc00000);
-    d[0] = nx; d[1] = ny; d[2] = nz;
-    for (int k = 3; k < src_cols; ++k) d[k] = __ldg(s + k);
-    for (int k = 0; k < n_time; ++k) d[src_cols + k] = (k == j.time_idx) ? 1.f : 0.f;
+  for (int i0 = blockIdx.x * 256; i0 < j.n; i0 += gridDim.x * 256) {
+    const int i = i0 + threadIdx.x;
+    if (i < j.n) {
+      const float* s = j.src + (size_t)i * src_cols;
+      float* d = rows + threadIdx.x * dcols;
+      float x, y, z;
+      if (src_cols == 8) {            // fused sweeps: two aligned 16-byte loads per row
+        const float4 a = __ldg(reinterpret_cast<const float4*>(s)), b = __ldg(reinterpret_cast<const float4*>(s) + 1);
+        x = a.x; y = a.y; z = a.z;
+        d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+      } else {
+        x = __ldg(s); y = __ldg(s + 1); z = __ldg(s + 2);
+        for (int k = 3; k < src_cols; ++k) d[k] = __ldg(s + k);
+      }
+      float nx = __fmaf_rn(z, j.R[6], __fmaf_rn(y, j.R[3], __fmul_rn(x, j.R[0])));
+      float ny = __fmaf_rn(z, j.R[7], __fmaf_rn(y, j.R[4], __fmul_rn(x, j.R[1])));
+      const float nz = __fmaf_rn(z, j.R[8], __fmaf_rn(y, j.R[5], __fmul_rn(x, j.R[2])));
+      nx = __fadd_rn(nx, j.dx);
+      ny = __fadd_rn(ny, j.dy);
+      if (roof_filter && x > -2.4f && x < 0.f && y > -0.8f && y < 0.8f && z > -1.5f && z < -1.f) nx = __int_as_float(0x7fc00000);
+      d[0] = nx; d[1] = ny; d[2] = nz;
+      for (int k = 0; k < n_time; ++k) d[src_cols + k] = (k == j.time_idx) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    const int nrow = min(256, j.n - i0);
+    float* out = j.dst + (size_t)i0 * dcols;
+    for (int e = threadIdx.x; e < nrow * dcols; e += 256) out[e] = rows[e];
+    __syncthreads();
   }
 }
 
 extern "C" int lavb_stack_jobs(const void* d_jobs, int n_jobs, int max_n, int src_cols, int n_time, int roof_filter, void* stream) {
   LAVB_CHECK_ARG(n_jobs >= 0 && n_jobs <= 65535 && src_cols >= 3 && n_time >= 0, "stack_jobs: bad arguments");
+  LAVB_CHECK_ARG(src_cols + n_time <= kStackMaxCols, "stack_jobs: rows wider than %d floats", kStackMaxCols);
   if (n_jobs == 0 || max_n == 0) return 0;
   dim3 grid(min(ceil_div(max_n, 256), 64), n_jobs);
   stack_jobs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const StackJob*>(d_jobs), src_cols, n_time, roof_filter);

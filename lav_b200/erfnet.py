@@ -83,8 +83,16 @@ class _Down:
         self.conv = TapConv(m.conv.weight, False, 2, 1, bias=m.conv.bias, scale=s[:nconv].clone(), shift=t[:nconv].clone(),
                             post_relu=True, cin_pad=(cin + 3) // 4 * 4)
         self.ps, self.pt = s[nconv:].contiguous(), t[nconv:].contiguous()
+        self.down16 = None
+        if cin == 16 and nconv == 48 and tuple(m.conv.kernel_size) == (3, 3):
+            w9 = m.conv.weight.detach().float().permute(2, 3, 1, 0).reshape(9, 16, 48).contiguous()          # [ky*3+kx][cin][cout]
+            tt = t.detach().clone()
+            tt[:48] += m.conv.bias.detach().float() * s.detach()[:48]
+            self.down16 = (w9, torch.stack([s.detach(), tt], 1).contiguous())
 
     def __call__(self, x, dt):
+        if FUSE_DOWN16 and self.down16 is not None and x.dtype == ops.h16() and dt == x.dtype and x.shape[2] <= 128 and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0:
+            return ops.erf_down16(x, *self.down16)
         n, h, w, _ = x.shape
         out = torch.empty((n, h // 2, w // 2, self.nout), dtype=dt, device=x.device)
         self.conv(x, out=out)
@@ -98,6 +106,7 @@ FUSE_PAIRS = True     # fused (3x1 -> 1x3) tcgen05 kernel (csrc/conv_pair_umma.c
 
 
 FUSE_STEM = True      # normalize + initial DownsamplerBlock(3,16) as one kernel on the uint8 frames (csrc/erf16.cu: erf_stem_kernel)
+FUSE_DOWN16 = True    # DownsamplerBlock(16, 64) as one kernel (csrc/erf16.cu: erf_down16_kernel) instead of conv_c16_mma<9> + pool2
 FUSE_NB16 = True      # the 16-channel decoder blocks as ONE kernel each (csrc/erf16.cu) instead of four conv_c16_mma launches
 
 

@@ -495,6 +495,19 @@ def erf_stem(rgb_u8, w27, scale, shift, out_dtype):
     return out
 
 
+def erf_down16(x, w9, st):
+    """fused DownsamplerBlock(16, 64): x h16 NHWC (n,h,w,16) -> (n,h/2,w/2,64) (lavb_erf_down16)."""
+    _need_cuda(x, w9, st)
+    assert x.dtype == h16() and x.is_contiguous() and x.dim() == 4 and x.shape[3] == 16
+    assert w9.dtype == torch.float32 and tuple(w9.shape) == (9, 16, 48) and w9.is_contiguous()
+    assert st.dtype == torch.float32 and tuple(st.shape) == (64, 2) and st.is_contiguous()
+    n, h, w, _ = x.shape
+    out = torch.empty((n, h // 2, w // 2, 64), dtype=x.dtype, device=x.device)
+    check(lib().lavb_erf_down16(_ptr(x), _ptr(out), n, h, w, _ptr(w9), _ptr(st), _stream()), "lavb_erf_down16")
+    _COUNT[0] += 1
+    return out
+
+
 def erf_nb16(x, w4, st, out=None):
     """fused non_bottleneck_1d(16, dilation 1) block: x h16 NHWC (n,h,w,16) -> same shape (lavb_erf_nb16)."""
     _need_cuda(x, w4, st)

@@ -327,3 +327,24 @@ def test_erf_stem_vs_torch(cuda, shape):
     assert util.rel_err(got, want) < 1e-5
     got16 = ops.erf_stem(rgb.to(cuda), *stem, ops.h16()).float().cpu()
     assert util.rel_err(got16, want) < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(3, 144, 128), (2, 20, 36), (1, 2, 2), (5, 10, 128)])
+def test_erf_down16_block_vs_torch(cuda, shape):
+    """lavb_erf_down16 == DownsamplerBlock(16, 64) in eval mode (lav/models/erfnet.py:12-23): conv3x3 s2 p1 (48) || maxpool2x2
+    (16) -> BN -> ReLU, h16 operands; ragged tiles, narrow images, the left / top zero padding."""
+    from lav_b200.erfnet import DownsamplerBlock, _Down
+    n, h, w = shape
+    blk = DownsamplerBlock(16, 64).eval()
+    sd = synth.fill_state_dict_(blk.state_dict())
+    blk.load_state_dict(sd)
+    x = torch.randn(n, 16, h, w, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        want = O._erf_down(x.to(ops.h16()).float(), {k: v.clone() for k, v in sd.items()}, "").permute(0, 2, 3, 1)
+    plan = _Down(blk.to(cuda))
+    assert plan.down16 is not None
+    got = ops.erf_down16(x.permute(0, 2, 3, 1).contiguous().to(cuda).to(ops.h16()), *plan.down16).float().cpu()
+    assert got.shape == want.shape == (n, h // 2, w // 2, 64)
+    err = (got - want).abs().max().item() / want.abs().max().item()
+    assert err < 3e-3, err
