@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LAVB_ABI_VERSION 2
+#define LAVB_ABI_VERSION 3
 
 int lavb_abi_version(void);
 const char* lavb_last_error(void);
@@ -225,6 +225,11 @@ int lavb_det_peaks(const float* d_center, const float* d_box, const float* d_ori
  * [k][crop][crop][c] in the feature dtype. */
 int lavb_crop_bilinear(const void* d_feat, int dtype, int b, int h, int w, int c, const int* d_frame_idx,
                        const float* d_theta, int k, int crop, void* d_out, void* stream);
+/* gradient of the above with respect to d_feat (fp32 NHWC; training, lav/models/uniplanner.py:56-151 through F.grid_sample):
+ * replaces cudnn_grid_sampler_backward + the index_put of `features[frame]`.  A gather over the crops of each frame — no
+ * atomics, fixed summation order, EVERY element of d_gfeat [b][h][w][c] is written (zeros where no crop samples). */
+int lavb_crop_bilinear_bwd(const float* d_gout, int b, int h, int w, int c, const int* d_frame_idx, const float* d_theta,
+                           int k, int crop, float* d_gfeat, void* stream);
 
 /* dtype / layout helpers */
 /* fp32 [rows][c] -> h16 [rows][hi(c) | lo(c)] with hi = h16(x), lo = h16(x - hi) (error-free split of the canvas so the
@@ -244,14 +249,17 @@ int lavb_conv_umma(const lavb_conv_desc* h_desc, void* stream);
 /* ---------------------------------------------------------------- fused (3x1 -> 1x3) convolution pair
  * replaces: conv3x1_k -> ReLU -> conv1x3_k -> bn_k [-> + input] -> ReLU of non_bottleneck_1d (lav/models/erfnet.py:37-63) in
  * one tcgen05 kernel; the intermediate activation stays in shared memory.
- *   mid = relu(conv3x1_dil(in) + bias1);  out = [relu]((conv1x3_dil(mid) + bias2) * scale2 + shift2 [+ res])
+ *   mid = relu(conv3x1_dil(in) + bias1);  out = [relu](conv1x3_dil(mid) + shift2 [+ res])
+ * The BatchNorm affine (conv + b2) * s + t is folded by the caller: w2 <- w2 * s per output channel, shift2 <- b2 * s + t.
+ * bias1 / shift2 (fp32 [c]) are pre-loaded into the TMEM accumulators, so the epilogues only pack, clamp and add the residual
+ * (16-bit packed arithmetic: the residual add rounds once more than an fp32 add would).
  * in / out / res: h16 NHWC (n, h, w, c) contiguous, c in {64, 128}, w in {32, 64, 128}; w1 / w2: h16 [3 taps][c out][c in];
- * bias2 / scale2 / shift2 / res may be NULL (scale2 and shift2 together). */
+ * res may be NULL. */
 typedef struct lavb_conv_pair_desc {
   const void* in; void* out; const void* res;
   int n, h, w, c, dil, post_relu;
   const void* w1; const float* bias1;
-  const void* w2; const float* bias2; const float* scale2; const float* shift2;
+  const void* w2; const float* shift2;
 } lavb_conv_pair_desc;
 int lavb_conv_pair_umma(const lavb_conv_pair_desc* h_desc, void* stream);
 

@@ -11,6 +11,8 @@ import copy
 import math
 from collections import deque
 
+import os
+
 import numpy as np
 import torch
 
@@ -176,6 +178,7 @@ class StaticFramePipeline(FramePipeline):
     KEEP = NUM_FRAME_STACK * GAP + 1          # ticks t .. t-10
     K_BUCKET = 8                              # detected-vehicle counts are padded to a multiple of this
     G2_CACHE = 6                              # captured G2 graphs kept (least recently used is dropped)
+    COPY_STREAM = os.environ.get("LAVB_COPY_STREAM", "1") != "0"   # stage pinned host inputs on a copy stream (see begin())
 
     def __init__(self, seg_model, lidar_model, uniplanner, bra_model, batch, n_points, camera_x=1.5, camera_z=2.4,
                  device=torch.device("cuda"), precision="f16", use_graphs=True, roof_filter=False):
@@ -201,6 +204,11 @@ class StaticFramePipeline(FramePipeline):
         self.cmds = torch.zeros((B,), dtype=torch.long, device=dev)
         self.tick = 0
         self.stream = torch.cuda.Stream(device=dev)
+        # host inputs are staged by a copy stream into one of two buffer sets, so the H2D transfer of tick t+1 runs under the
+        # planner graph of tick t instead of behind it on the compute stream (the graphs read fixed addresses: one D2D copy)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self._stage = [None, None]
+        self._stage_free = [None, None]
         self._g1 = None
         self._g2 = {}            # Kb -> (graph, outputs, static inputs); insertion order = recency (LRU)
         self._g2_pool = None     # one graph memory pool for every G2[Kb]
@@ -322,8 +330,35 @@ class StaticFramePipeline(FramePipeline):
     @torch.no_grad()
     def begin(self, rgbs_u8, tel_u8, lidars, nxps, cmds, poses=None):
         """stage inputs and launch G1 (asynchronous)."""
+        rgbs_u8, tel_u8, lidars, used = self._stage_host(rgbs_u8, tel_u8, lidars)
         with torch.cuda.stream(self.stream), self._math_mode():
             self._begin(rgbs_u8, tel_u8, lidars, nxps, cmds, poses)
+            if used is not None:
+                self._stage_free[used] = torch.cuda.Event()
+                self._stage_free[used].record(self.stream)
+
+    def _stage_host(self, rgbs_u8, tel_u8, lidars):
+        """pinned host tensors -> the staging set of this tick on the copy stream; returns device tensors (or the arguments
+        unchanged when they are already on the device / ragged) and the staging slot used."""
+        full = torch.is_tensor(lidars) and lidars.shape[1] == self.N
+        host = [t for t in (rgbs_u8, tel_u8, lidars if full else None) if torch.is_tensor(t) and t.device.type == "cpu" and t.is_pinned()]
+        if not host or not self.COPY_STREAM:
+            return rgbs_u8, tel_u8, lidars, None
+        k = self.tick % 2
+        if self._stage[k] is None:
+            self._stage[k] = (torch.empty_like(self.rgbs), torch.empty_like(self.tels), torch.empty_like(self.lidar_raw))
+        out = [rgbs_u8, tel_u8, lidars]
+        with torch.cuda.stream(self.copy_stream):
+            if self._stage_free[k] is not None:
+                self.copy_stream.wait_event(self._stage_free[k])          # the tick that last read this set has consumed it
+            for j, t in enumerate(out):
+                if any(t is h for h in host):
+                    self._stage[k][j].copy_(t, non_blocking=True)
+                    out[j] = self._stage[k][j]
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        self.stream.wait_event(ready)
+        return out[0], out[1], out[2], k
 
     @torch.no_grad()
     def finish(self, fixed_dets=None):

@@ -37,7 +37,7 @@ class ConvPairDesc(C.Structure):
         ("inp", C.c_void_p), ("out", C.c_void_p), ("res", C.c_void_p),
         ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int), ("dil", C.c_int), ("post_relu", C.c_int),
         ("w1", C.c_void_p), ("bias1", C.c_void_p),
-        ("w2", C.c_void_p), ("bias2", C.c_void_p), ("scale2", C.c_void_p), ("shift2", C.c_void_p),
+        ("w2", C.c_void_p), ("shift2", C.c_void_p),
     ]
 
 
@@ -101,6 +101,8 @@ _SIGS = {
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "lavb_crop_bilinear": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_int, C.c_void_p, C.c_void_p]),
+    "lavb_crop_bilinear_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p]),
     "lavb_deconv3x3s2_small": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lavb_conv_umma": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
@@ -126,7 +128,7 @@ def lib():
             fn = getattr(handle, name)          # AttributeError here == header/library drift
             fn.restype = res
             fn.argtypes = args
-        if handle.lavb_abi_version() != 2:
+        if handle.lavb_abi_version() != 3:
             raise LavbError("liblavb200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -6,11 +6,15 @@
 // fused, `mid` never leaves the SM.  A tile is 128 pixels made of FULL-WIDTH image rows (W = 64 -> 2 rows, W = 32 -> 4 rows),
 // so the horizontal conv needs no halo: its zero padding is the image border.
 //   stage 1: tcgen05.mma over 3 vertical taps (A = 4-D TMA boxes shifted by the tap, B = W1 blocks) -> TMEM acc1 (2 buffers)
-//   epilogue 1: acc1 -> relu(+b1) -> h16 -> shared memory, written three times in the SWIZZLE_128B K-major operand layout:
+//   (bias1 / shift2 are PRE-LOADED into the accumulators: the epilogue warps re-arm the TMEM columns they have just drained with
+//    tcgen05.st, every MMA accumulates — so the epilogues carry no per-element fp32 arithmetic at all: pack, clamp, store.
+//    The kernel is bound by the epilogue warps' instruction issue (ncu: tensor pipe 17-19 %, profiles/r02_erf_pair_summary.md):
+//    8.2 -> ~3.8 thread-instructions per output element)
+//   epilogue 1: acc1 -> h16 -> relu -> shared memory, written three times in the SWIZZLE_128B K-major operand layout:
 //               shifted by +d, 0, -d pixels inside each image row (rows that fall off the image border stay zero), i.e. the
 //               three A operands of the horizontal taps
 //   stage 2: tcgen05.mma over the 3 horizontal taps (A = those copies, B = W2 blocks through the same TMA ring) -> TMEM acc2
-//   epilogue 2: affine / residual / ReLU -> h16 NHWC.
+//   epilogue 2: acc2 -> h16 -> (+ residual, ReLU as one packed fma.relu) -> NHWC.  The BatchNorm scale is folded into W2 by the caller.
 // Warp roles as conv_umma.cu (warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue), one CTA per SM, persistent.
 // MMA issue order S1(0), S1(1), S2(0), S1(2), S2(1), ... — the producer feeds the ring in exactly that order — so the
 // stage-1 MMAs of the next tile run while the epilogue warps write `mid` of the current one.
@@ -30,7 +34,7 @@ constexpr int kEpiWarps = 8;
 struct PairArgs {
   int n, h, w, c, kchunks, dil, tile_w, tile_h, tiles_per_img, num_tiles, stages, tmem_cols, post_relu;
   h16* out; const h16* res;
-  const float* bias1; const float* bias2; const float* scale2; const float* shift2;
+  const float* bias1; const float* shift2;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -94,6 +98,37 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
+        "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]),
+        "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// TMEM[this warp's 32 lanes][col0, col0 + 32) <- src[0, 32) (fp32, the same row for every lane): accumulator pre-load
+__device__ __forceinline__ void tmem_fill32(uint32_t taddr, const float* src) {
+  uint32_t b[32];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 f = reinterpret_cast<const float4*>(src)[j];
+    b[4 * j] = __float_as_uint(f.x); b[4 * j + 1] = __float_as_uint(f.y); b[4 * j + 2] = __float_as_uint(f.z); b[4 * j + 3] = __float_as_uint(f.w);
+  }
+  tmem_st32(taddr, b);
+}
+__device__ __forceinline__ uint32_t relu2(uint32_t x) {
+  const h162 v = __hmax2(*reinterpret_cast<const h162*>(&x), floats2h162(0.f, 0.f));
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t add2(uint32_t x, uint32_t r, bool relu) {
+  const h162 a = *reinterpret_cast<const h162*>(&x), b = *reinterpret_cast<const h162*>(&r);
+  const h162 v = relu ? __hfma2_relu(a, floats2h162(1.f, 1.f), b) : __hadd2(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   const h162 v = floats2h162(a, b);
   return *reinterpret_cast<const uint32_t*>(&v);
@@ -116,7 +151,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
   float* ep_b1 = reinterpret_cast<float*>(gen + (tmem_slot - base) + 16);     // bias of conv A
-  float* ep_st = ep_b1 + 128;                                                 // interleaved (scale, shift') of conv B
+  float* ep_t2 = ep_b1 + 128;                                                 // shift of conv B (BatchNorm folded by the caller)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -135,11 +170,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
   }
   for (int c = threadIdx.x; c < p.c; c += blockDim.x) {
     ep_b1[c] = __ldg(p.bias1 + c);
-    const float b = p.bias2 ? __ldg(p.bias2 + c) : 0.f;
-    const float sc = p.scale2 ? __ldg(p.scale2 + c) : 1.f;
-    const float sh = p.shift2 ? __ldg(p.shift2 + c) : 0.f;
-    ep_st[2 * c] = sc;
-    ep_st[2 * c + 1] = fmaf(b, sc, sh);              // (a + b) s + t = a s + (b s + t)
+    ep_t2[c] = p.shift2 ? __ldg(p.shift2 + c) : 0.f;
   }
   // the shifted copies keep zero rows where a tap falls off the image border: clear `mid` once, data rows are rewritten per tile
   for (int i = threadIdx.x; i < mid_bytes / 16; i += blockDim.x)
@@ -150,6 +181,19 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_p;
   const int nkb = 3 * p.kchunks;                                    // K-blocks per stage
+  if (warp >= 2) {
+    // pre-load the three accumulators (acc1[0], acc1[1] <- bias1, acc2 <- shift2): each epilogue warp arms the columns it drains
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c0 = ((warp - 2) >> 2) * 32; c0 < p.c; c0 += 64) {
+      tmem_fill32(lane_addr + (uint32_t)c0, ep_b1 + c0);
+      tmem_fill32(lane_addr + (uint32_t)(p.c + c0), ep_b1 + c0);
+      tmem_fill32(lane_addr + (uint32_t)(2 * p.c + c0), ep_t2 + c0);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -200,7 +244,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
           const uint64_t a_desc = make_sw128_desc(sa), b_desc = make_sw128_desc(sa + kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
-            umma_h16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            umma_h16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, 1u);   // onto the pre-loaded bias
           umma_commit(empty_bar + 8 * slot);
           if (++slot == p.stages) { slot = 0; phase ^= 1; }
         }
@@ -220,7 +264,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
           const uint64_t a_desc = make_sw128_desc(mid + kb * kABytes), b_desc = make_sw128_desc(sa + kABytes);   // kb = t*kchunks + kc
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
-            umma_h16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            umma_h16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, 1u);   // onto the pre-loaded shift
           umma_commit(empty_bar + 8 * slot);
           if (++slot == p.stages) { slot = 0; phase ^= 1; }
         }
@@ -232,8 +276,9 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
     const int half = (warp - 2) >> 2;                // the two warps of a quarter take alternate 32-column chunks
     const int m = q * 32 + lane;                     // tile row = pixel
     const int py = m / p.tile_w, px = m - py * p.tile_w;
-    const float lo_post = p.post_relu ? 0.f : -INFINITY;
     const int d = p.dil;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool relu_out = p.post_relu != 0;
     // destination rows of this pixel's data in the three shifted copies (tap t reads x + (t-1) d): row m - (t-1) d
     const bool ok0 = px + d < p.tile_w, ok2 = px - d >= 0;
     const int r0 = m + d, r2 = m - d;
@@ -244,16 +289,18 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
       const int img = tile / p.tiles_per_img, y = (tile - img * p.tiles_per_img) * p.tile_h + py;
       const bool valid = y < p.h;
       const long long pix = ((long long)img * p.h + y) * p.w + px;
-      // ---- epilogue 1: acc1 -> relu(+b1) -> h16 -> three shifted K-major copies in shared memory
+      // ---- epilogue 1: acc1 (bias included) -> h16 -> relu -> three shifted K-major copies in shared memory
       mbar_wait(tfull1 + 8 * buf, (uint32_t)((i >> 1) & 1));
       tc_fence_after();
       for (int c0 = half * 32; c0 < p.c; c0 += 64) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.c + c0), v);
         uint32_t w[16];
+        {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + (uint32_t)(buf * p.c + c0), v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          w[j] = pack2(fmaxf(__uint_as_float(v[2 * j]) + ep_b1[c0 + 2 * j], 0.f), fmaxf(__uint_as_float(v[2 * j + 1]) + ep_b1[c0 + 2 * j + 1], 0.f));
+          for (int j = 0; j < 16; ++j) w[j] = relu2(pack2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])));
+        }
+        tmem_fill32(lane_addr + (uint32_t)(buf * p.c + c0), ep_b1 + c0);      // re-arm these columns for tile i + 2
         const int kc = c0 >> 6, jj0 = (c0 & 63) >> 3;            // K-block and first 16-byte piece inside the 128-byte row
         uint8_t* blk = midp + kc * kABytes;
 #pragma unroll
@@ -265,11 +312,12 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
           if (ok2) *reinterpret_cast<uint4*>(blk + 2 * p.kchunks * kABytes + r2 * 128 + ((jj ^ (r2 & 7)) << 4)) = val;
         }
       }
+      tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(tempty1 + 8 * buf);                // acc1[buf] may be overwritten by the stage-1 MMAs of tile i+2
+      mbar_arrive(tempty1 + 8 * buf);                // acc1[buf] (re-armed) may take the stage-1 MMAs of tile i+2
       proxy_fence_async();                           // generic-proxy stores -> visible to the tensor core's async-proxy reads
-      mbar_arrive(mid_full);
-      // ---- epilogue 2: acc2 -> affine (+ residual) -> ReLU -> h16 NHWC
+      mbar_arrive(mid_full);                         // also orders this thread's re-arming of acc2 (previous tile) before stage 2
+      // ---- epilogue 2: acc2 (shift included) -> h16 (+ residual) -> ReLU -> NHWC
       uint4 rr[4];
       auto load_res = [&](int c0) {
         const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.c + c0);
@@ -280,37 +328,33 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
       mbar_wait(tfull2, (uint32_t)(i & 1));
       tc_fence_after();
       for (int c0 = half * 32; c0 < p.c; c0 += 64) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * p.c + c0), v);
-        float f[32];
-        const float4* st4 = reinterpret_cast<const float4*>(ep_st + 2 * c0);
+        uint32_t w[16];
+        {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + (uint32_t)(2 * p.c + c0), v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 st = st4[j];
-          f[2 * j] = fmaf(__uint_as_float(v[2 * j]), st.x, st.y);
-          f[2 * j + 1] = fmaf(__uint_as_float(v[2 * j + 1]), st.z, st.w);
+          for (int j = 0; j < 16; ++j) w[j] = pack2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
         }
+        tmem_fill32(lane_addr + (uint32_t)(2 * p.c + c0), ep_t2 + c0);        // re-arm acc2 for the next tile
         if (valid) {
           if (p.res) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t wv[4] = {rr[j].x, rr[j].y, rr[j].z, rr[j].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 t2 = h1622float2(*reinterpret_cast<const h162*>(&wv[e]));
-                f[j * 8 + e * 2] += t2.x; f[j * 8 + e * 2 + 1] += t2.y;
-              }
+              w[4 * j] = add2(w[4 * j], rr[j].x, relu_out); w[4 * j + 1] = add2(w[4 * j + 1], rr[j].y, relu_out);
+              w[4 * j + 2] = add2(w[4 * j + 2], rr[j].z, relu_out); w[4 * j + 3] = add2(w[4 * j + 3], rr[j].w, relu_out);
             }
             if (c0 + 64 < p.c) load_res(c0 + 64);
+          } else if (relu_out) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = relu2(w[j]);
           }
           uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.c + c0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            op[j] = make_uint4(pack2(fmaxf(f[8 * j], lo_post), fmaxf(f[8 * j + 1], lo_post)), pack2(fmaxf(f[8 * j + 2], lo_post), fmaxf(f[8 * j + 3], lo_post)),
-                               pack2(fmaxf(f[8 * j + 4], lo_post), fmaxf(f[8 * j + 5], lo_post)), pack2(fmaxf(f[8 * j + 6], lo_post), fmaxf(f[8 * j + 7], lo_post)));
+          for (int j = 0; j < 4; ++j) op[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
         }
       }
-      tc_fence_before();                             // acc2 reads are ordered before this thread's next mid_full arrival
+      tmem_st_wait();
+      tc_fence_before();                             // acc2 reads and its re-arming are ordered before this thread's next mid_full arrival
     }
   }
   tc_fence_before();
@@ -345,7 +389,6 @@ extern "C" int lavb_conv_pair_umma(const lavb_conv_pair_desc* d, void* stream) {
   LAVB_CHECK_ARG(d->dil >= 1 && d->dil < d->w, "conv_pair_umma: dilation must be in [1, width)");
   LAVB_CHECK_ARG(d->n >= 0 && d->h >= 1, "conv_pair_umma: bad shape");
   LAVB_CHECK_ARG(d->w1 && d->w2 && d->bias1 && d->in && d->out, "conv_pair_umma: null operand");
-  LAVB_CHECK_ARG((d->scale2 == nullptr) == (d->shift2 == nullptr), "conv_pair_umma: scale and shift come together");
   if (d->n == 0) return 0;
   auto encode = get_encode();
   LAVB_CHECK_ARG(encode != nullptr, "conv_pair_umma: cuTensorMapEncodeTiled not available from the driver");
@@ -357,7 +400,7 @@ extern "C" int lavb_conv_pair_umma(const lavb_conv_pair_desc* d, void* stream) {
   a.num_tiles = d->n * a.tiles_per_img;
   a.post_relu = d->post_relu;
   a.out = reinterpret_cast<h16*>(d->out); a.res = reinterpret_cast<const h16*>(d->res);
-  a.bias1 = d->bias1; a.bias2 = d->bias2; a.scale2 = d->scale2; a.shift2 = d->shift2;
+  a.bias1 = d->bias1; a.shift2 = d->shift2;
   const int slot_bytes = kABytes + d->c * kBlockK * 2;
   const int mid_bytes = 3 * a.kchunks * kABytes;
   // C = 64: TWO co-resident CTAs per SM (3 x 64 TMEM columns -> 256 each, ~100 KB of shared memory each): two independent tile

@@ -115,7 +115,7 @@ class _NB1D:
         d = m.conv3x1_2.dilation[0]
         s1, t1 = bn_affine(m.bn1)
         s2, t2 = bn_affine(m.bn2)
-        self.nb16 = None
+        self.nb16 = self.pair = None
         if m.conv3x1_1.in_channels == 16 and d == 1:
             # [conv][tap][cin][cout] and (scale, shift) with the bias folded: relu(a*s + t)
             ws = [m.conv3x1_1.weight[:, :, :, 0], m.conv1x3_1.weight[:, :, 0, :], m.conv3x1_2.weight[:, :, :, 0], m.conv1x3_2.weight[:, :, 0, :]]
@@ -134,10 +134,15 @@ class _NB1D:
         if FUSE_NB16 and self.nb16 is not None and x.dtype == ops.h16() and x.shape[2] % 16 == 0 and x.shape[2] <= 256:
             return ops.erf_nb16(x, *self.nb16)
         if FUSE_PAIRS and x.dtype == ops.h16() and self.a.umma_ok and x.shape[3] in (64, 128) and x.shape[2] in (32, 64, 128):
-            # experimental: each (3x1 -> 1x3) pair in one tcgen05 kernel, the intermediate stays in shared memory
-            a, b, c, d = (t.phases[0]["w_umma"] for t in (self.a, self.b, self.c, self.d))
-            y = ops.conv_pair_umma(x, a, self.a.bias, b, self.b.bias, self.b.scale, self.b.shift, 1)
-            return ops.conv_pair_umma(y, c, self.c.bias, d, self.d.bias, self.d.scale, self.d.shift, self.c.dilation[0], res=x)
+            # each (3x1 -> 1x3) pair in one tcgen05 kernel, the intermediate stays in shared memory
+            if self.pair is None:
+                def folded(t):       # (conv + b) * s + t' = conv_{w*s} + (b*s + t'): scale into the weights (fp32, rounded once)
+                    w = t.phases[0]["w"][:, :, :t.cout] * t.scale[None, None, :]
+                    return w.permute(0, 2, 1).to(ops.h16()).contiguous(), ((t.bias if t.bias is not None else 0) * t.scale + t.shift).contiguous()
+                self.pair = (self.a.phases[0]["w_umma"], self.a.bias, *folded(self.b), self.c.phases[0]["w_umma"], self.c.bias, *folded(self.d))
+            a, ab, b, bt, c, cb, d, dt_ = self.pair
+            y = ops.conv_pair_umma(x, a, ab, b, bt, 1)
+            return ops.conv_pair_umma(y, c, cb, d, dt_, self.c.dilation[0], res=x)
         y = self.a(x)
         y = self.b(y)
         y = self.c(y)

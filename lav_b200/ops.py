@@ -288,6 +288,36 @@ def crop_bilinear(feats_nhwc, frame_idx, theta, crop_size):
     return out
 
 
+def crop_bilinear_bwd(gout_nhwc, frame_idx, theta, feat_shape):
+    """gout_nhwc (K,crop,crop,C) fp32 contiguous -> gradient of crop_bilinear w.r.t. the (B,H,W,C) fp32 feature map."""
+    _need_cuda(gout_nhwc, frame_idx, theta)
+    assert gout_nhwc.is_contiguous() and gout_nhwc.dtype == torch.float32
+    b, h, w, c = feat_shape
+    k, crop = gout_nhwc.shape[0], gout_nhwc.shape[1]
+    gfeat = torch.empty((b, h, w, c), dtype=torch.float32, device=gout_nhwc.device)
+    check(lib().lavb_crop_bilinear_bwd(_ptr(gout_nhwc), b, h, w, c, _ptr(frame_idx), _ptr(theta), k, crop, _ptr(gfeat), _stream()),
+          "lavb_crop_bilinear_bwd")
+    _COUNT[0] += 1
+    return gfeat
+
+
+class CropBilinear(torch.autograd.Function):
+    """crop_bilinear with its hand-written backward (gradient to the feature map only: the crop poses are data)."""
+
+    @staticmethod
+    def forward(ctx, feats_nhwc, frame_idx, theta, crop_size):
+        frame_idx = frame_idx.to(torch.int32).contiguous()
+        theta = theta.detach().float().contiguous()
+        ctx.save_for_backward(frame_idx, theta)
+        ctx.feat_shape = tuple(feats_nhwc.shape)
+        return crop_bilinear(feats_nhwc, frame_idx, theta, crop_size)
+
+    @staticmethod
+    def backward(ctx, gout):
+        frame_idx, theta = ctx.saved_tensors
+        return crop_bilinear_bwd(gout.contiguous(), frame_idx, theta, ctx.feat_shape), None, None, None
+
+
 def deconv3x3s2_small(x, groups, cin_g, w, bias, n_outs, sigmoids):
     """x NHWC (N,H,W,Ctot); w fp32 (G,cin_g,9,4); bias (G,4) -> list of fp32 NHWC (N,2H,2W,n_out[g])."""
     _need_cuda(x, w, bias)
@@ -453,23 +483,23 @@ def maxpool3x3s2_nhwc(x):
     return out
 
 
-def conv_pair_umma(x, w1, bias1, w2, bias2, scale2, shift2, dil, res=None, post_relu=True):
-    """EXPERIMENTAL fused pair: relu(conv3x1_dil(x) + bias1) -> conv1x3_dil -> (+bias2) * scale2 + shift2 [+ res] [-> relu].
-    x / res: contiguous f16 NHWC (n, h, w, c), c in {64, 128}, w in {32, 64, 128}; w1 / w2: (3, c, c) f16 [tap][cout][cin]."""
+def conv_pair_umma(x, w1, bias1, w2, shift2, dil, res=None, post_relu=True):
+    """fused pair: mid = relu(conv3x1_dil(x) + bias1); out = [relu](conv1x3_dil(mid) + shift2 [+ res]).  A BatchNorm affine after
+    the second conv is folded by the caller: w2 <- w2 * s (per output channel), shift2 <- b2 * s + t.
+    x / res: contiguous f16 NHWC (n, h, w, c), c in {64, 128}, w in {32, 64, 128}; w1 / w2: (3, c, c) f16 [tap][cout][cin];
+    bias1 / shift2: fp32 (c,)."""
     from .capi import ConvPairDesc
-    _need_cuda(x, w1, w2)
+    _need_cuda(x, w1, w2, bias1, shift2)
     n, h, w, c = x.shape
     assert x.dtype == h16() and x.is_contiguous() and w1.is_contiguous() and w2.is_contiguous()
     assert tuple(w1.shape) == (3, c, c) and tuple(w2.shape) == (3, c, c) and w1.dtype == w2.dtype == h16()
+    assert bias1.dtype == shift2.dtype == torch.float32 and bias1.numel() == shift2.numel() == c
     out = torch.empty_like(x)
     d = ConvPairDesc()
     d.inp, d.out = x.data_ptr(), out.data_ptr()
     d.n, d.h, d.w, d.c, d.dil, d.post_relu = n, h, w, c, int(dil), int(post_relu)
     d.w1, d.bias1 = w1.data_ptr(), bias1.data_ptr()
-    d.w2 = w2.data_ptr()
-    d.bias2 = bias2.data_ptr() if bias2 is not None else None
-    d.scale2 = scale2.data_ptr() if scale2 is not None else None
-    d.shift2 = shift2.data_ptr() if shift2 is not None else None
+    d.w2, d.shift2 = w2.data_ptr(), shift2.data_ptr()
     if res is not None:
         assert res.is_contiguous() and res.shape == x.shape and res.dtype == h16()
         d.res = res.data_ptr()

@@ -32,11 +32,44 @@ def lidar_model_train_forward(model, lidars, num_points):
     x2 = bb.conv2(x1)
     x3 = bb.conv3(x2)
     feats = torch.cat([bb.upconv1(x1), bb.upconv2(x2), bb.upconv3(x3)], dim=1)
+    heads = (model.center_head, model.box_head, model.ori_head, model.seg_head)
+    hidden = _heads_trunk_fused(heads, feats) if FUSE_HEADS_TRAIN else None
     outs = []
-    for h in (model.center_head, model.box_head, model.ori_head, model.seg_head):
-        y = h.net(feats)
+    for i, h in enumerate(heads):
+        y = h.net(feats) if hidden is None else h.net[3](hidden[i])
         outs.append(h.output_activation(y) if h.output_activation else y)
     return (feats, *outs)
+
+
+FUSE_HEADS_TRAIN = True
+
+
+def _heads_trunk_fused(heads, feats):
+    """Conv(384->64) -> ReLU -> BatchNorm of the four heads (lidar.py:14-27) as ONE 384->256 convolution and one 256-channel
+    batch norm (statistics are per channel, so this is the same function): the 1.26 GB feature map is read by one fprop and
+    one wgrad instead of four, and one dgrad writes its gradient instead of four dgrads + three full-size additions.  The
+    parameters stay the heads' own (state_dict unchanged); running statistics are written back to each head's BatchNorm.
+    Returns the per-head hidden maps, or None when the heads do not share one configuration."""
+    convs, bns = [h.net[0] for h in heads], [h.net[2] for h in heads]
+    c0, b0 = convs[0], bns[0]
+    same = all(isinstance(c, nn.Conv2d) and c.bias is None and c.weight.shape == c0.weight.shape and c.stride == c0.stride and
+               c.padding == c0.padding and c.dilation == c0.dilation and c.groups == 1 for c in convs)
+    same = same and all(isinstance(b, nn.BatchNorm2d) and b.training and b.affine and b.track_running_stats and b.momentum is not None
+                        and b.momentum == b0.momentum and b.eps == b0.eps for b in bns)
+    same = same and all(isinstance(h.net[1], nn.ReLU) and len(h.net) == 4 for h in heads)
+    if not same:
+        return None
+    y = F.conv2d(feats, torch.cat([c.weight for c in convs]), None, c0.stride, c0.padding, c0.dilation)
+    y = F.relu_(y)
+    mean, var = torch.cat([b.running_mean for b in bns]), torch.cat([b.running_var for b in bns])
+    y = F.batch_norm(y, mean, var, torch.cat([b.weight for b in bns]), torch.cat([b.bias for b in bns]), True, b0.momentum, b0.eps)
+    with torch.no_grad():
+        n = b0.num_features
+        for i, b in enumerate(bns):
+            b.running_mean.copy_(mean[i * n:(i + 1) * n])
+            b.running_var.copy_(var[i * n:(i + 1) * n])
+            b.num_batches_tracked += 1
+    return y.split(b0.num_features, dim=1)
 
 
 # --------------------------------------------------------------------------- losses
@@ -168,12 +201,14 @@ class GradAllReducer:
         if cur:
             self.buckets.append(cur)
         self._flat = [torch.zeros(sum(p.numel() for p in b), dtype=b[0].dtype, device=b[0].device) for b in self.buckets]
-        self._where = {}
+        self._where, self._views = {}, []
         for bi, b in enumerate(self.buckets):
-            off = 0
+            off, views = 0, []
             for p in b:
                 self._where[p] = (bi, off)
+                views.append(self._flat[bi][off:off + p.numel()].view_as(p))
                 off += p.numel()
+            self._views.append(views)
         self._pending = [0] * len(self.buckets)
         self._works = [None] * len(self.buckets)
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
@@ -185,16 +220,25 @@ class GradAllReducer:
         self._next = 0            # buckets are reduced STRICTLY in index order: every rank issues the same collectives in the
                                   # same order even when the set of parameters that received a gradient differs between ranks
 
+    def _pack(self, bi):
+        """gradients of bucket bi -> its flat buffer: ONE multi-tensor copy (zeros for parameters that received no gradient)"""
+        have = [(v, p.grad) for v, p in zip(self._views[bi], self.buckets[bi]) if p.grad is not None]
+        for v, p in zip(self._views[bi], self.buckets[bi]):
+            if p.grad is None:
+                v.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+
     def _launch_ready(self):
         while self._next < len(self.buckets) and self._pending[self._next] == 0:
             bi = self._next
             if self.world > 1:
+                self._pack(bi)
                 self._works[bi] = dist.all_reduce(self._flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self._next += 1
 
     def _on_grad(self, p):
-        bi, off = self._where[p]
-        self._flat[bi][off:off + p.numel()].copy_(p.grad.reshape(-1))
+        bi, _ = self._where[p]
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
             self._launch_ready()
@@ -202,25 +246,19 @@ class GradAllReducer:
     def finish(self):
         """wait for the exchanges and write the averaged gradients back into ``p.grad``; call before optimizer.step().
         Buckets with a parameter that received no gradient this step are completed with zeros and reduced here, still in
-        index order."""
-        for bi, b in enumerate(self.buckets):
-            if self._pending[bi] != 0:
-                for p in b:
-                    if p.grad is None:
-                        _, off = self._where[p]
-                        self._flat[bi][off:off + p.numel()].zero_()
-                self._pending[bi] = 0
+        index order.  With one rank nothing is copied or reduced: the gradients stay where autograd put them."""
+        for bi in range(len(self.buckets)):
+            self._pending[bi] = 0
         self._launch_ready()
-        for bi, b in enumerate(self.buckets):
-            if self._works[bi] is not None:
-                self._works[bi].wait()
-            if self.world > 1:
+        if self.world > 1:
+            for bi, b in enumerate(self.buckets):
+                if self._works[bi] is not None:
+                    self._works[bi].wait()
                 self._flat[bi].div_(self.world)
-                for p in b:
-                    _, off = self._where[p]
+                for v, p in zip(self._views[bi], b):
                     if p.grad is None:
                         p.grad = torch.empty_like(p)
-                    p.grad.copy_(self._flat[bi][off:off + p.numel()].view_as(p))
+                torch._foreach_copy_([p.grad for p in b], self._views[bi])
         self.reset()
 
     def close(self):
@@ -279,20 +317,21 @@ class LAVTrainer:
         self.cfg = LossConfig(box_weight, ori_weight, seg_weight, perception_weight, other_weight, cmd_weight, cmd_smooth,
                               tuple(branch_weights), distill, perceive_only, motion_only)
         self.perceive_only, self.motion_only = perceive_only, motion_only
-        # amp=True: model forwards under bf16 autocast (fp32 master weights, losses and Adam in fp32).  The reference trains in
-        # fp32 (cuDNN TF32); this is an opt-in throughput mode, off by default and not yet measured.
+        # amp=True: LiDAR-model forward under bf16 autocast (fp32 master weights; planner, losses and Adam in fp32).  The
+        # reference trains in fp32 (cuDNN TF32); opt-in, off by default: measured no faster (the step is not conv-bound).
         self.amp = bool(amp)
 
     def losses(self, lidars, num_points, heatmaps, sizemaps, orimaps, bev, ego_locs, cmds, nxps, bras, locs, oris, typs):
         up = self.uniplanner
         bev = bev.float()
+        # amp: only the LiDAR model (pillars, backbone, heads — the convolutions) runs under bf16 autocast; the planner (cuDNN
+        # GRUs, crops, embedder) and every loss stay fp32 — cuDNN's bf16 RNN path faulted on these shapes (B200, cuDNN 9)
         ctx = torch.autocast("cuda", dtype=torch.bfloat16) if self.amp else contextlib.nullcontext()
         with ctx:
             outs = self.lidar_model(lidars, num_points)
-            planner_out = up(outs[0], bev, ego_locs.float(), locs.float(), oris.float(), nxps.float(), typs)
-        if self.amp:       # losses in fp32
+        if self.amp:
             outs = tuple(t.float() for t in outs)
-            planner_out = tuple(t.float() if torch.is_floating_point(t) else t for t in planner_out)
+        planner_out = up(outs[0], bev, ego_locs.float(), locs.float(), oris.float(), nxps.float(), typs)
         loss, parts = train_losses(outs, planner_out, heatmaps, sizemaps, orimaps, bev, ego_locs, cmds, bras, self.seg_mask, self.cfg,
                                    self.branch_weights)
         return loss, {k: v.detach() for k, v in parts.items()}

@@ -250,7 +250,8 @@ def test_brake_forward_u8_matches_forward(cuda):
 @pytest.mark.parametrize("cfg", [(3, 72, 64, 64, 1, True), (2, 36, 32, 128, 2, True), (2, 36, 32, 128, 16, True), (1, 7, 64, 64, 1, False),
                                  (24, 72, 64, 64, 1, True), (96, 36, 32, 128, 4, True)])   # last two: several tiles per CTA (persistent loop)
 def test_conv_pair_umma_vs_torch(cuda, cfg):
-    """lavb_conv_pair_umma == relu(conv3x1) -> conv1x3 -> affine (+res) -> relu of erfnet.py:37-63, f16 operands, tol 1e-2."""
+    """lavb_conv_pair_umma == relu(conv3x1) -> conv1x3 -> affine (+res) -> relu of erfnet.py:37-63, f16 operands, tol 1e-2.
+    The caller folds the BatchNorm scale into the second conv's weights (in fp32, rounded once) and passes b2*s + t as shift."""
     n, h, w, c, dil, use_res = cfg
     g = torch.Generator().manual_seed(4)
     x = torch.randn(n, c, h, w, generator=g)
@@ -260,14 +261,15 @@ def test_conv_pair_umma_vs_torch(cuda, cfg):
     s2, t2 = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
     bf = lambda t: t.to(ops.h16()).float()
     mid = bf(F.relu(F.conv2d(bf(x), bf(w1), b1, padding=(dil, 0), dilation=(dil, 1))))
-    ref = F.conv2d(mid, bf(w2), b2, padding=(0, dil), dilation=(1, dil)) * s2[None, :, None, None] + t2[None, :, None, None]
+    w2 = w2 * s2[:, None, None, None]                                                  # the fold: (conv + b) s + t = conv_{w s} + (b s + t)
+    ref = F.conv2d(mid, bf(w2), b2 * s2 + t2, padding=(0, dil), dilation=(1, dil))
     if use_res:
         ref = ref + bf(x)
     ref = F.relu(ref).permute(0, 2, 3, 1)
     xd = x.permute(0, 2, 3, 1).contiguous().to(ops.h16()).cuda()
     w1u = w1[:, :, :, 0].permute(2, 0, 1).contiguous().to(ops.h16()).cuda()       # [tap][cout][cin]
     w2u = w2[:, :, 0, :].permute(2, 0, 1).contiguous().to(ops.h16()).cuda()
-    out = ops.conv_pair_umma(xd, w1u, b1.cuda(), w2u, b2.cuda(), s2.cuda(), t2.cuda(), dil, res=xd if use_res else None).float().cpu()
+    out = ops.conv_pair_umma(xd, w1u, b1.cuda(), w2u, (b2 * s2 + t2).cuda(), dil, res=xd if use_res else None).float().cpu()
     err = (out - ref).abs().max().item() / ref.abs().max().item()
     assert err < 1e-2, err
 

@@ -31,6 +31,50 @@ def test_crop_kernel_vs_grid_sample(cuda, dtype):
     assert util.rel_err(got, want) < (1e-5 if dtype == torch.float32 else 1e-2)
 
 
+@pytest.mark.parametrize("case", ["c64", "c400_many"])
+def test_crop_backward_kernel_vs_grid_sample_grad(cuda, case):
+    """ops.CropBilinear (gather backward, no atomics) against autograd through F.grid_sample on the CPU: windows that leave the
+    map, several crops per frame, > 32 crops on one frame (second pass of the per-block crop list), channel counts below
+    one warp pass (64) and above one channel pass (400)."""
+    from lav_b200.heads import crop_theta
+    g = synth._gen(5, "cropbwd" + case)
+    C, K = (64, 7) if case == "c64" else (400, 41)
+    B, H, W, S = 3, 40, 48, 24
+    feats = torch.randn(B, C, H, W, generator=g)
+    locs = torch.randn(K, 2, generator=g) * 8
+    oris = torch.rand(K, generator=g) * 6.28 - 3.14
+    fidx = torch.randint(0, B, (K,), generator=g).to(torch.int32) if case == "c64" else torch.cat([torch.zeros(36, dtype=torch.int32), torch.tensor([1, 2, 1, 2, 2], dtype=torch.int32)])
+    theta = crop_theta(locs, oris, H, W, 2.0, S, torch.tensor(0.), torch.tensor(0.75))
+    gout = torch.randn(K, C, S, S, generator=g)
+    f_cpu = feats.clone().requires_grad_(True)
+    grids = F.affine_grid(theta, torch.Size((K, C, S, S)), align_corners=True)
+    want_out = F.grid_sample(f_cpu[fidx.long()], grids, align_corners=True)
+    want_out.backward(gout)
+    f_gpu = feats.to(cuda).requires_grad_(True)
+    got_out = ops.CropBilinear.apply(f_gpu.permute(0, 2, 3, 1).contiguous(), fidx.to(cuda), theta.to(cuda), S).permute(0, 3, 1, 2)
+    got_out.backward(gout.to(cuda))
+    assert util.rel_err(got_out.detach().cpu(), want_out.detach()) < 1e-5
+    assert util.rel_err(f_gpu.grad.cpu(), f_cpu.grad) < 1e-5
+    # the training forward of UniPlanner.crop_feature takes this path and agrees with its grid_sample fallback
+    import lav_b200.heads as Hd
+    up, _ = uniplanner()
+    up = up.to(cuda)
+    f2 = feats[:, :64].to(cuda).requires_grad_(True)
+    rel_locs, rel_oris = (torch.randn(5, 2, generator=g) * 3).to(cuda), (torch.rand(5, generator=g) - 0.5).to(cuda)
+    fr = torch.tensor([0, 2, 1, 1, 0], device=cuda)
+    outs = []
+    for flag in (True, False):
+        Hd.TRAIN_CROP_KERNEL = flag
+        try:
+            f2.grad = None
+            o = up.crop_feature(f2, rel_locs, rel_oris, pixels_per_meter=2, crop_size=S, frame_idx=fr)
+            o.square().sum().backward()
+            outs.append((o.detach().clone(), f2.grad.clone()))
+        finally:
+            Hd.TRAIN_CROP_KERNEL = True
+    assert util.rel_err(outs[0][0], outs[1][0]) < 1e-5 and util.rel_err(outs[0][1], outs[1][1]) < 1e-5
+
+
 def test_infer_model_matches_oracle(cuda):
     from lav_b200.model_inference import InferModel
     lm, lsd = util.lidar_model(cuda)

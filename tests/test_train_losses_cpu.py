@@ -48,3 +48,36 @@ def test_detloss_module_signature():
     a = T.DetLoss()(ph, hm, ph, hm, ph, hm)
     b = T.detection_losses(ph, hm, ph, hm, ph, hm)
     assert all(torch.equal(x, y) for x, y in zip(a, b)) and len(a) == 3
+
+
+def test_fused_heads_trunk_equals_per_head_layers():
+    """train.py:_heads_trunk_fused (one 4x-wide conv + one batch norm) against the heads' own Conv -> ReLU -> BatchNorm:
+    outputs, gradients (features, conv and BN parameters) and the running statistics written back."""
+    import copy
+    from lav_b200.lidar import Head
+    from lav_b200 import train as T
+    torch.manual_seed(3)
+    heads = [Head(24, n, num_hidden=8) for n in (1, 2, 2, 3)]
+    for h in heads:
+        h.train()
+        h.net[2].weight.data.uniform_(0.5, 1.5); h.net[2].bias.data.normal_()
+    ref = copy.deepcopy(heads)
+    feats = torch.randn(3, 24, 10, 12)
+    fa, fb = feats.clone().requires_grad_(True), feats.clone().requires_grad_(True)
+    hidden = T._heads_trunk_fused(heads, fa)
+    assert hidden is not None
+    got = [h.net[3](x) for h, x in zip(heads, hidden)]
+    want = [h.net(fb) for h in ref]
+    sum(o.square().sum() for o in got).backward()
+    sum(o.square().sum() for o in want).backward()
+    for g, w in zip(got, want):
+        assert torch.allclose(g, w, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(fa.grad, fb.grad, rtol=1e-3, atol=1e-4)
+    for h, r in zip(heads, ref):
+        for (n, p), (_, q) in zip(h.named_parameters(), r.named_parameters()):
+            assert torch.allclose(p.grad, q.grad, rtol=1e-3, atol=1e-4), n
+        assert torch.allclose(h.net[2].running_mean, r.net[2].running_mean, atol=1e-6)
+        assert torch.allclose(h.net[2].running_var, r.net[2].running_var, atol=1e-6)
+        assert int(h.net[2].num_batches_tracked) == int(r.net[2].num_batches_tracked) == 1
+    heads[1].net[2].eps = 1e-2                                 # heads that differ fall back to the per-head path
+    assert T._heads_trunk_fused(heads, fa) is None
