@@ -262,6 +262,9 @@ typedef struct lavb_conv_pair_desc {
   const void* w2; const float* shift2;
 } lavb_conv_pair_desc;
 int lavb_conv_pair_umma(const lavb_conv_pair_desc* h_desc, void* stream);
+/* profiling aid: while d_buf is non-NULL every lavb_conv_pair_umma launch writes clock64 stamps of its pipeline events,
+ * d_buf[cta][tile iteration < tiles_per_cta][8] int64 (conv_pair_umma.cu: PAIR_STAMP).  NULL switches it off (the default). */
+int lavb_conv_pair_set_trace(void* d_buf, int tiles_per_cta);
 
 /* ---------------------------------------------------------------- fused ERFNet entry block on the raw camera bytes
  * replaces: RGBSegmentationModel.normalize ((x/255 - .5) * 2, lav/models/rgb.py:41-45) + Encoder.initial_block =

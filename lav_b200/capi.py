@@ -101,6 +101,7 @@ _SIGS = {
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "lavb_crop_bilinear": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_int, C.c_void_p, C.c_void_p]),
+    "lavb_conv_pair_set_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "lavb_crop_bilinear_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p]),
     "lavb_deconv3x3s2_small": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

@@ -35,7 +35,14 @@ struct PairArgs {
   int n, h, w, c, kchunks, dil, tile_w, tile_h, tiles_per_img, num_tiles, stages, tmem_cols, post_relu;
   h16* out; const h16* res;
   const float* bias1; const float* shift2;
+  long long* trace; int trace_tiles;      // profiling aid (lavb_conv_pair_set_trace): per-CTA, per-tile clock64 stamps, or null
 };
+// stamps of tile iteration i of this CTA: [0..3] epilogue warp 2 (acc1 ready, mid written, acc2 ready, tile stored),
+// [4..7] MMA thread (stage-1 of the next tile issued, mid_full observed, stage-2 issued, -)
+#define PAIR_STAMP(slot, i)                                                                                         \
+  do {                                                                                                              \
+    if (p.trace && (i) < p.trace_tiles) p.trace[((long long)blockIdx.x * p.trace_tiles + (i)) * 8 + (slot)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -145,7 +152,8 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
   const int slot_bytes = kABytes + w_bytes;
   const uint32_t mid = base + p.stages * slot_bytes;                // [3 taps][kchunks] x 16 KB, K-major SW128
   const int mid_bytes = 3 * p.kchunks * kABytes;
-  const uint32_t ctrl = mid + mid_bytes;
+  const uint32_t stage_out = mid + mid_bytes;                       // kEpiWarps x 1 KB: per-warp transposition buffer of epilogue 2
+  const uint32_t ctrl = stage_out + kEpiWarps * 1024;
   const uint32_t full_bar = ctrl, empty_bar = ctrl + 8 * kMaxStages, tfull1 = ctrl + 16 * kMaxStages, tempty1 = tfull1 + 16,
                  mid_full = tempty1 + 16, tfull2 = mid_full + 8, tmem_slot = tfull2 + 8;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -181,6 +189,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_p;
   const int nkb = 3 * p.kchunks;                                    // K-blocks per stage
+  const int bpf = slot_bytes / w_bytes;                             // W2 K-blocks per ring slot in stage 2
   if (warp >= 2) {
     // pre-load the three accumulators (acc1[0], acc1[1] <- bias1, acc2 <- shift2): each epilogue warp arms the columns it drains
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -210,15 +219,21 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
             if (++slot == p.stages) { slot = 0; phase ^= 1; }
           }
       };
+      // stage 2 needs only weights: a ring slot (A part + W part) takes bpf = slot_bytes / w_bytes whole W2 K-blocks, so the
+      // stage is 1 fill (c = 64) or 3 fills (c = 128) instead of 3 / 6 — with 2-3 slots in the ring the fills of a stage cannot
+      // all be in flight, and each extra round trip is a TMA latency on the tile's critical path (clock64 trace)
       auto load_stage2 = [&]() {
-        for (int t = 0; t < 3; ++t)
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(empty_bar + 8 * slot, phase ^ 1);
-            const uint32_t sa = base + slot * slot_bytes;
-            mbar_expect_tx(full_bar + 8 * slot, w_bytes);
-            tma_load_2d(sa + kABytes, &tmap_w2, full_bar + 8 * slot, kc * kBlockK, t * p.c);
-            if (++slot == p.stages) { slot = 0; phase ^= 1; }
+        for (int kb0 = 0; kb0 < nkb; kb0 += bpf) {
+          mbar_wait(empty_bar + 8 * slot, phase ^ 1);
+          const uint32_t sa = base + slot * slot_bytes;
+          const int nb = min(bpf, nkb - kb0);
+          mbar_expect_tx(full_bar + 8 * slot, nb * w_bytes);
+          for (int b = 0; b < nb; ++b) {
+            const int kb = kb0 + b, t = kb / p.kchunks, kc = kb - t * p.kchunks;
+            tma_load_2d(sa + b * w_bytes, &tmap_w2, full_bar + 8 * slot, kc * kBlockK, t * p.c);
           }
+          if (++slot == p.stages) { slot = 0; phase ^= 1; }
+        }
       };
       if ((int)blockIdx.x < p.num_tiles) load_stage1(blockIdx.x);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -254,21 +269,27 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
       int i = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++i) {
         if (tile + (int)gridDim.x < p.num_tiles) stage1((i + 1) & 1);
+        PAIR_STAMP(4, i);
         mbar_wait(mid_full, (uint32_t)(i & 1));      // the epilogue warps have written the three shifted copies of `mid`
         tc_fence_after();
+        PAIR_STAMP(5, i);
         const uint32_t d_tmem = tmem_base + (uint32_t)(2 * p.c);
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb0 = 0; kb0 < nkb; kb0 += bpf) {
           mbar_wait(full_bar + 8 * slot, phase);
           tc_fence_after();
           const uint32_t sa = base + slot * slot_bytes;
-          const uint64_t a_desc = make_sw128_desc(mid + kb * kABytes), b_desc = make_sw128_desc(sa + kABytes);   // kb = t*kchunks + kc
+          const int nb = min(bpf, nkb - kb0);
+          for (int b = 0; b < nb; ++b) {
+            const uint64_t a_desc = make_sw128_desc(mid + (kb0 + b) * kABytes), b_desc = make_sw128_desc(sa + b * w_bytes);   // kb = t*kchunks + kc
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_h16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, 1u);   // onto the pre-loaded shift
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_h16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, 1u);   // onto the pre-loaded shift
+          }
           umma_commit(empty_bar + 8 * slot);
           if (++slot == p.stages) { slot = 0; phase ^= 1; }
         }
         umma_commit(tfull2);                         // acc2 complete; also: `mid` may be rewritten
+        PAIR_STAMP(6, i);
       }
     }
   } else {
@@ -292,6 +313,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
       // ---- epilogue 1: acc1 (bias included) -> h16 -> relu -> three shifted K-major copies in shared memory
       mbar_wait(tfull1 + 8 * buf, (uint32_t)((i >> 1) & 1));
       tc_fence_after();
+      if (threadIdx.x == 64) PAIR_STAMP(0, i);
       for (int c0 = half * 32; c0 < p.c; c0 += 64) {
         uint32_t w[16];
         {
@@ -317,16 +339,21 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
       mbar_arrive(tempty1 + 8 * buf);                // acc1[buf] (re-armed) may take the stage-1 MMAs of tile i+2
       proxy_fence_async();                           // generic-proxy stores -> visible to the tensor core's async-proxy reads
       mbar_arrive(mid_full);                         // also orders this thread's re-arming of acc2 (previous tile) before stage 2
+      if (threadIdx.x == 64) PAIR_STAMP(1, i);
       // ---- epilogue 2: acc2 (shift included) -> h16 (+ residual) -> ReLU -> NHWC
+      // residual: loaded with the coalesced mapping (4 lanes per pixel, rr[2 hp + k] = pixel 16 hp + 8 k + lane/4, piece lane%4)
+      // well before the accumulator is ready; transposed to "lane = pixel" through the warp's staging buffer at use
       uint4 rr[4];
+      const h16* rrow = p.res + (pix - lane) * p.c;
       auto load_res = [&](int c0) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.c + c0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rr[j] = __ldg(rp + j);
+        for (int e = 0; e < 4; ++e)
+          rr[e] = __ldg(reinterpret_cast<const uint4*>(rrow + (long long)((e >> 1) * 16 + 8 * (e & 1) + (lane >> 2)) * p.c + c0 + (lane & 3) * 8));
       };
       if (p.res && valid) load_res(half * 32);       // requested before the accumulator wait
       mbar_wait(tfull2, (uint32_t)(i & 1));
       tc_fence_after();
+      if (threadIdx.x == 64) PAIR_STAMP(2, i);
       for (int c0 = half * 32; c0 < p.c; c0 += 64) {
         uint32_t w[16];
         {
@@ -336,25 +363,63 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kMinBlocks) conv_pair_umm
           for (int j = 0; j < 16; ++j) w[j] = pack2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
         }
         tmem_fill32(lane_addr + (uint32_t)(2 * p.c + c0), ep_t2 + c0);        // re-arm acc2 for the next tile
+        uint8_t* stg = gen + (stage_out - base) + (warp - 2) * 1024;
         if (valid) {
           if (p.res) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              w[4 * j] = add2(w[4 * j], rr[j].x, relu_out); w[4 * j + 1] = add2(w[4 * j + 1], rr[j].y, relu_out);
-              w[4 * j + 2] = add2(w[4 * j + 2], rr[j].z, relu_out); w[4 * j + 3] = add2(w[4 * j + 3], rr[j].w, relu_out);
+            for (int hp = 0; hp < 2; ++hp) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const int r = 8 * k + (lane >> 2), j = lane & 3;
+                *reinterpret_cast<uint4*>(stg + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)) = rr[2 * hp + k];
+              }
+              __syncwarp();
+              if ((lane >> 4) == hp) {
+                const int r = lane & 15;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 q4 = *reinterpret_cast<const uint4*>(stg + r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
+                  w[4 * j] = add2(w[4 * j], q4.x, relu_out); w[4 * j + 1] = add2(w[4 * j + 1], q4.y, relu_out);
+                  w[4 * j + 2] = add2(w[4 * j + 2], q4.z, relu_out); w[4 * j + 3] = add2(w[4 * j + 3], q4.w, relu_out);
+                }
+              }
+              __syncwarp();
             }
             if (c0 + 64 < p.c) load_res(c0 + 64);
           } else if (relu_out) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) w[j] = relu2(w[j]);
           }
-          uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.c + c0);
+        }
+        // Store through a per-warp shared-memory transposition: a lane owns 64 contiguous bytes of ITS pixel, so a direct
+        // 16-byte store per lane touches 32 different 128-byte lines (half a sector each) per instruction — measured as the
+        // longest phase of the tile (clock64 trace, scripts/pair_trace.py).  Re-mapped, 4 lanes cover the 64 bytes of one pixel
+        // and an instruction writes 8 pixels x 64 B in full sectors.  16 pixels per pass (1 KB per warp), swizzled so that both
+        // the row-wise writes and the 4-lanes-per-row reads are bank-conflict free.  The warp's 32 pixels are consecutive in x.
+        h16* orow = p.out + (pix - lane) * p.c + c0;              // pixel of lane 0, this chunk's channels
 #pragma unroll
-          for (int j = 0; j < 4; ++j) op[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        for (int hp = 0; hp < 2; ++hp) {
+          if ((lane >> 4) == hp) {
+            const int r = lane & 15;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(stg + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          }
+          __syncwarp();
+          if (valid) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int r = 8 * k + (lane >> 2), j = lane & 3;
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
+              *reinterpret_cast<uint4*>(orow + (long long)(hp * 16 + r) * p.c + j * 8) = val;
+            }
+          }
+          __syncwarp();
         }
       }
       tmem_st_wait();
       tc_fence_before();                             // acc2 reads and its re-arming are ordered before this thread's next mid_full arrival
+      if (threadIdx.x == 64) PAIR_STAMP(3, i);
     }
   }
   tc_fence_before();
@@ -382,6 +447,14 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 using namespace lavb;
 using namespace lavb::pair;
 
+static long long* g_pair_trace = nullptr;
+static int g_pair_trace_tiles = 0;
+extern "C" int lavb_conv_pair_set_trace(void* d_buf, int tiles_per_cta) {
+  g_pair_trace = reinterpret_cast<long long*>(d_buf);
+  g_pair_trace_tiles = d_buf ? tiles_per_cta : 0;
+  return 0;
+}
+
 extern "C" int lavb_conv_pair_umma(const lavb_conv_pair_desc* d, void* stream) {
   LAVB_CHECK_ARG(d != nullptr, "conv_pair_umma: null descriptor");
   LAVB_CHECK_ARG(d->c == 64 || d->c == 128, "conv_pair_umma: channels must be 64 or 128 (got %d)", d->c);
@@ -401,6 +474,7 @@ extern "C" int lavb_conv_pair_umma(const lavb_conv_pair_desc* d, void* stream) {
   a.post_relu = d->post_relu;
   a.out = reinterpret_cast<h16*>(d->out); a.res = reinterpret_cast<const h16*>(d->res);
   a.bias1 = d->bias1; a.shift2 = d->shift2;
+  a.trace = g_pair_trace; a.trace_tiles = g_pair_trace_tiles;
   const int slot_bytes = kABytes + d->c * kBlockK * 2;
   const int mid_bytes = 3 * a.kchunks * kABytes;
   // C = 64: TWO co-resident CTAs per SM (3 x 64 TMEM columns -> 256 each, ~100 KB of shared memory each): two independent tile
@@ -408,7 +482,7 @@ extern "C" int lavb_conv_pair_umma(const lavb_conv_pair_desc* d, void* stream) {
   static int two_mode = -1;
   if (two_mode < 0) { const char* e = getenv("LAVB_PAIR_TWO"); two_mode = e ? atoi(e) : 1; }
   const bool two = two_mode && d->c == 64;
-  a.stages = min(kMaxStages, ((two ? 100 : 200) * 1024 - mid_bytes) / slot_bytes);
+  a.stages = min(kMaxStages, ((two ? 108 : 218) * 1024 - mid_bytes - kEpiWarps * 1024) / slot_bytes);
   a.tmem_cols = d->c == 64 ? 256 : 512;          // acc1 x 2 + acc2 = 3c columns, power of two
   CUtensorMap tmap_a, tmap_w1, tmap_w2;
   {
@@ -431,7 +505,7 @@ extern "C" int lavb_conv_pair_umma(const lavb_conv_pair_desc* d, void* stream) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LAVB_CHECK_ARG(r == CUDA_SUCCESS, "conv_pair_umma: cuTensorMapEncodeTiled(W%d) failed with %d", which + 1, (int)r);
   }
-  const size_t smem = (size_t)a.stages * slot_bytes + mid_bytes + 1024 /*align*/ + 16 * kMaxStages + 96 + 3 * 128 * sizeof(float);
+  const size_t smem = (size_t)a.stages * slot_bytes + mid_bytes + kEpiWarps * 1024 + 1024 /*align*/ + 16 * kMaxStages + 96 + 3 * 128 * sizeof(float);
   if (two) {
     LAVB_CUDA_OK(ensure_dyn_smem((const void*)conv_pair_umma_kernel<2>, 113 * 1024));
     conv_pair_umma_kernel<2><<<min(a.num_tiles, 2 * kNumSMs), 64 + 32 * kEpiWarps, smem, (cudaStream_t)stream>>>(tmap_a, tmap_w1, tmap_w2, a);

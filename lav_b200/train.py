@@ -296,8 +296,13 @@ class LAVTrainer:
 
     def __init__(self, lidar_model, uniplanner, lr=3e-4, device=None, box_weight=1.0, ori_weight=1.0, seg_weight=2.0,
                  perception_weight=4.0, other_weight=0.5, cmd_weight=0.1, branch_weights=(5, 5, 5, 1, 1, 1), distill=True,
-                 cmd_smooth=0.2, perceive_only=False, motion_only=False, bucket_bytes=25 << 20, amp=False):
+                 cmd_smooth=0.2, perceive_only=False, motion_only=False, bucket_bytes=25 << 20, amp=False, channels_last=True):
         self.lidar_model, self.uniplanner = lidar_model.train(), uniplanner.train()
+        if channels_last and next(lidar_model.parameters()).is_cuda:
+            # NHWC convolution weights (values and state_dict unchanged): cuDNN's sm_100 kernels are NHWC — this removes most of
+            # the nchw<->nhwc conversion kernels around them (B200: 75.4 -> 73.8 ms per 32-sample step)
+            lidar_model.to(memory_format=torch.channels_last)
+            uniplanner.to(memory_format=torch.channels_last)
         uniplanner.bev_planner.eval()
         for p in uniplanner.bev_planner.parameters():
             p.requires_grad_(False)

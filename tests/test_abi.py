@@ -20,7 +20,7 @@ def test_header_symbols_exported():
 
 def test_abi_version_and_error_string():
     lib = capi.lib()
-    assert lib.lavb_abi_version() == 2
+    assert lib.lavb_abi_version() == 3
     assert isinstance(lib.lavb_last_error(), bytes)
 
 
