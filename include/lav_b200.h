@@ -293,9 +293,10 @@ int lavb_erf_nb16(const void* d_in, void* d_out, int n, int h, int w, const floa
 /* ---------------------------------------------------------------- cluster-persistent GRU roll-out
  * replaces: one call of plan_gru = nn.GRU(4, 512, batch_first=True) (team_code_v2/models/uniplanner.py:45,247-259;
  * lav/models/bev_planner_v2.py) over `steps` time steps for `nseq` sequences.
- * d_u (nseq, steps, 4) fp32; d_h0 (nseq, 512) fp32; d_whh_h16 = weight_hh_l0 (1536, 512) as h16; d_wih = weight_ih_l0
- * (1536, 4), d_bih / d_bhh (1536,) fp32; d_out (nseq, steps, 512) fp32 = the GRU's output sequence. */
-int lavb_gru_h512(const float* d_u, const float* d_h0, const void* d_whh_h16, const float* d_wih, const float* d_bih,
+ * d_u (nseq, steps, 4) fp32; d_h0 (nseq, 512) fp32; d_whh = weight_hh_l0 (1536, 512) fp32; d_wih = weight_ih_l0
+ * (1536, 4), d_bih / d_bhh (1536,) fp32; d_out (nseq, steps, 512) fp32 = the GRU's output sequence.
+ * fp32-class arithmetic: the recurrent product runs on the 16-bit tensor cores with both operands split into hi + lo parts. */
+int lavb_gru_h512(const float* d_u, const float* d_h0, const float* d_whh, const float* d_wih, const float* d_bih,
                   const float* d_bhh, float* d_out, int nseq, int steps, void* stream);
 
 #ifdef __cplusplus

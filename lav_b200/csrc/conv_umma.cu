@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : LAVB
   const bool wres = p.wres != 0;
   const int stage_bytes = wres ? kABytes : kABytes + b_bytes;     // the ring carries A only when the weights are resident
   const uint32_t bres = base + p.stages * stage_bytes;            // resident weights: [ntaps*kchunks][cout x 64] (wres)
-  const uint32_t ctrl = bres + (wres ? p.ntaps * p.kchunks * b_bytes : 0);
+  const uint32_t stage_out = bres + (wres ? p.ntaps * p.kchunks * b_bytes : 0);   // kEpiWarps x 1 KB store-transposition buffers
+  const uint32_t ctrl = stage_out + kEpiWarps * 1024;
   const uint32_t full_bar = ctrl, empty_bar = ctrl + 8 * kMaxStages, tfull_bar = ctrl + 16 * kMaxStages,
                  tempty_bar = tfull_bar + 16, tmem_slot = tempty_bar + 16, wbar = tmem_slot + 8;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -217,7 +218,8 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : LAVB
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
-      const int gy = (r / p.tiles_x) * kTileH + py, gx = (r % p.tiles_x) * kTileW + px;
+      const int ty0 = (r / p.tiles_x) * kTileH, tx0 = (r % p.tiles_x) * kTileW;
+      const int gy = ty0 + py, gx = tx0 + px;
       const int oy = gy * p.out_sy + p.out_oy, ox = gx * p.out_sx + p.out_ox;
       const bool valid = gy < p.hog && gx < p.wog && oy < p.hout && ox < p.wout;
       const long long pix = ((long long)img * p.hout + oy) * p.wout + ox;
@@ -270,18 +272,41 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : LAVB
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               if (c0 + 4 * j < p.cout_store) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<h16*>(p.out) + pix * p.out_cstride + p.out_coff + c0);
+          }
+        }
+        if (!kD2S && !kOutF32) {
+          // h16 NHWC store through a per-warp shared-memory transposition (same scheme as conv_pair_umma.cu): a lane owns 64
+          // contiguous bytes of ITS pixel, so a direct 16-byte store per lane touches 32 different lines per instruction;
+          // re-mapped, 4 lanes cover the 64 bytes of one pixel and an instruction writes 8 pixels in full sectors.  One pass =
+          // the 16 pixels of one spatial row of the 8 x 16 tile (tile row 2q + hp), 1 KB per warp, bank-conflict free both ways.
+          uint32_t w16[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t w[4];
+          for (int j = 0; j < 16; ++j) {
+            const h162 b2 = floats2h162(f[2 * j], f[2 * j + 1]);
+            w16[j] = *reinterpret_cast<const uint32_t*>(&b2);
+          }
+          uint8_t* stg = gen + (stage_out - base) + (warp - 2) * 1024;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const h162 b2 = floats2h162(f[j * 8 + e * 2], f[j * 8 + e * 2 + 1]);
-                w[e] = *reinterpret_cast<const uint32_t*>(&b2);
-              }
-              if (c0 + 8 * j < p.cout_store) op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int hp = 0; hp < 2; ++hp) {
+            if ((lane >> 4) == hp) {
+              const int rr_ = lane & 15;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(stg + rr_ * 64 + ((j ^ ((rr_ >> 1) & 3)) << 4)) = make_uint4(w16[4 * j], w16[4 * j + 1], w16[4 * j + 2], w16[4 * j + 3]);
             }
+            __syncwarp();
+            const int gy2 = ty0 + 2 * q + hp, oy2 = gy2 * p.out_sy + p.out_oy;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int rr_ = 8 * k + (lane >> 2), j = lane & 3;
+              const int gx2 = tx0 + rr_, ox2 = gx2 * p.out_sx + p.out_ox;
+              if (gy2 < p.hog && gx2 < p.wog && oy2 < p.hout && ox2 < p.wout && c0 + 8 * j < p.cout_store) {
+                const uint4 val = *reinterpret_cast<const uint4*>(stg + rr_ * 64 + ((j ^ ((rr_ >> 1) & 3)) << 4));
+                *reinterpret_cast<uint4*>(reinterpret_cast<h16*>(p.out) + (((long long)img * p.hout + oy2) * p.wout + ox2) * p.out_cstride +
+                                          p.out_coff + c0 + 8 * j) = val;
+              }
+            }
+            __syncwarp();
           }
         }
       }
@@ -390,7 +415,7 @@ extern "C" int lavb_conv_umma(const lavb_conv_desc* d, void* stream) {
   a.out = d->out; a.res = reinterpret_cast<const h16*>(d->res);
   a.bias = d->bias; a.scale = d->scale; a.shift = d->shift;
   if (a.num_tiles == 0) return 0;
-  const size_t smem = (size_t)a.stages * stage_bytes + (a.wres ? res_bytes : 0) + 1024 /*align*/ + 16 * kMaxStages + 64 + 3 * 256 * sizeof(float);
+  const size_t smem = (size_t)a.stages * stage_bytes + (a.wres ? res_bytes : 0) + (two_per_sm ? 4 : 8) * 1024 /*store staging: 1 KB per epilogue warp*/ + 1024 /*align*/ + 16 * kMaxStages + 64 + 3 * 256 * sizeof(float);
   const int grid = min(a.num_tiles, two_per_sm ? 2 * kNumSMs : kNumSMs);
   if (a.d2s_nout) {
 #define LAVB_D2S(S)                                                                                                     \

@@ -552,17 +552,18 @@ def erf_nb16(x, w4, st, out=None):
     return out
 
 
-def gru_h512(u, h0, whh_h16, wih, bih, bhh):
-    """EXPERIMENTAL cluster-persistent GRU(4 -> 512) roll-out.  u (N, T, 4) fp32, h0 (N, 512) fp32, whh_h16 (1536, 512) f16,
-    wih (1536, 4), bih / bhh (1536,) fp32 -> out (N, T, 512) fp32 (the output sequence of nn.GRU(batch_first=True))."""
-    _need_cuda(u, h0, whh_h16)
+def gru_h512(u, h0, whh, wih, bih, bhh):
+    """cluster-persistent GRU(4 -> 512) roll-out (csrc/gru_cluster.cu), fp32-class arithmetic.  u (N, T, 4), h0 (N, 512),
+    whh (1536, 512), wih (1536, 4), bih / bhh (1536,), all fp32 -> out (N, T, 512) fp32 (the output sequence of
+    nn.GRU(batch_first=True))."""
+    _need_cuda(u, h0, whh)
     n, t, k = u.shape
-    assert k == 4 and tuple(h0.shape) == (n, 512) and tuple(whh_h16.shape) == (1536, 512) and whh_h16.dtype == h16()
-    assert u.dtype == h0.dtype == wih.dtype == bih.dtype == bhh.dtype == torch.float32
+    assert k == 4 and tuple(h0.shape) == (n, 512) and tuple(whh.shape) == (1536, 512)
+    assert u.dtype == h0.dtype == whh.dtype == wih.dtype == bih.dtype == bhh.dtype == torch.float32
     u, h0 = u.contiguous(), h0.contiguous()
-    assert whh_h16.is_contiguous() and wih.is_contiguous()
+    assert whh.is_contiguous() and wih.is_contiguous()
     out = torch.empty((n, t, 512), dtype=torch.float32, device=u.device)
-    check(lib().lavb_gru_h512(_ptr(u), _ptr(h0), _ptr(whh_h16), _ptr(wih), _ptr(bih), _ptr(bhh), _ptr(out), n, t, _stream()),
+    check(lib().lavb_gru_h512(_ptr(u), _ptr(h0), _ptr(whh), _ptr(wih), _ptr(bih), _ptr(bhh), _ptr(out), n, t, _stream()),
           "lavb_gru_h512")
     _COUNT[0] += 1
     return out
