@@ -226,6 +226,20 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : LAVB
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       for (int c0 = half * 32; c0 < p.cout; c0 += kChunkStride) {
+        uint8_t* stg = gen + (stage_out - base) + (warp - 2) * 1024;
+        // residual, loaded with the coalesced mapping (4 lanes x 16 B per pixel; rr[2 hp + k] = pixel 8k + lane/4 of tile row
+        // 2q + hp, piece lane%4) before the accumulator read, transposed to "lane = pixel" through the staging buffer below
+        uint4 rr[4];
+        if (kRes) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int gy2 = ty0 + 2 * q + (e >> 1), gx2 = tx0 + 8 * (e & 1) + (lane >> 2);
+            const int oy2 = gy2 * p.out_sy + p.out_oy, ox2 = gx2 * p.out_sx + p.out_ox;
+            rr[e] = make_uint4(0u, 0u, 0u, 0u);
+            if (gy2 < p.hog && gx2 < p.wog && oy2 < p.hout && ox2 < p.wout)
+              rr[e] = __ldg(reinterpret_cast<const uint4*>(p.res + (((long long)img * p.hout + oy2) * p.wout + ox2) * p.res_cstride + p.res_coff + c0 + 8 * (lane & 3)));
+          }
+        }
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.cout + c0), v);
         float f[32];
@@ -238,20 +252,32 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : LAVB
           f[2 * j] = fmaf(fmaxf(x0, lo_pre), st.x, st.y);
           f[2 * j + 1] = fmaf(fmaxf(x1, lo_pre), st.z, st.w);
         }
-        if (valid) {
-          if (kRes) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_cstride + p.res_coff + c0);
+        if (kRes) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 rr = __ldg(rp + j);
-              const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+          for (int hp = 0; hp < 2; ++hp) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 t2 = h1622float2(*reinterpret_cast<const h162*>(&w[e]));
-                f[j * 8 + e * 2] += t2.x; f[j * 8 + e * 2 + 1] += t2.y;
+            for (int k = 0; k < 2; ++k) {
+              const int rr_ = 8 * k + (lane >> 2), j = lane & 3;
+              *reinterpret_cast<uint4*>(stg + rr_ * 64 + ((j ^ ((rr_ >> 1) & 3)) << 4)) = rr[2 * hp + k];
+            }
+            __syncwarp();
+            if ((lane >> 4) == hp) {
+              const int rr_ = lane & 15;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 q4 = *reinterpret_cast<const uint4*>(stg + rr_ * 64 + ((j ^ ((rr_ >> 1) & 3)) << 4));
+                const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t2 = h1622float2(*reinterpret_cast<const h162*>(&w[e]));
+                  f[j * 8 + e * 2] += t2.x; f[j * 8 + e * 2 + 1] += t2.y;
+                }
               }
             }
+            __syncwarp();
           }
+        }
+        if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             f[j] = fmaxf(f[j], lo_post);
@@ -285,7 +311,6 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, kEpiWarps == 4 ? 2 : LAVB
             const h162 b2 = floats2h162(f[2 * j], f[2 * j + 1]);
             w16[j] = *reinterpret_cast<const uint32_t*>(&b2);
           }
-          uint8_t* stg = gen + (stage_out - base) + (warp - 2) * 1024;
 #pragma unroll
           for (int hp = 0; hp < 2; ++hp) {
             if ((lane >> 4) == hp) {

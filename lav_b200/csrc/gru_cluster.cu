@@ -2,18 +2,20 @@
 // (team_code_v2/models/uniplanner.py:227-259: nn.GRU(4, 512), 20 steps, 6*B sequences, called 5 times per tick) as ONE
 // cluster-persistent kernel per call instead of 20 x (cuDNN GEMM + cell kernel): those 100 sequential launch pairs per tick are
 // latency-bound (~10 us each whatever the batch: 1.0 ms per tick, 31 us/frame at 32 frames).
-//   * a thread-block cluster of 16 CTAs owns 16 sequences for all T steps; CTA r produces the r/z/n gates of hidden units
+//   * a thread-block cluster of 16 CTAs owns 32 sequences for all T steps; CTA r produces the r/z/n gates of hidden units
 //     [32r, 32r+32): 96 rows of W_hh, resident for the whole roll-out;
 //   * fp32-class arithmetic on the 16-bit tensor cores: both operands are split error-free into h16 hi + lo parts and
 //     h.W = h_hi W_hi + h_lo W_hi + h_hi W_lo (fp32 accumulate; the dropped lo*lo term is 2^-22 relative).  The plan roll-out
 //     feeds its own output back five times and is not contractive on untrained weights, so plain 16-bit operands (the first
 //     version of this kernel) ended 1.7e-2..5e-2 away from the fp32 reference; this one agrees to ~1e-6 per roll-out.
 //     W_hi lives in shared memory (96 KB), W_lo in REGISTERS as the warp's mma B fragments (64 registers per thread: warp w
-//     owns gate columns [8w, 8w+8) for all 512 k), the hidden state as hi/lo h16 copies in shared memory, double buffered;
-//   * per step every CTA multiplies the full hidden state of its 16 sequences with its weight slice (mma.sync m16n8k16),
-//     applies the gate math in fp32 on its 32 units (fp32 master copy of h stays local), writes the step's output rows and
-//     PUSHES the hi/lo h16 slices of h' into the next-step buffers of all 16 CTAs through distributed shared memory; one
-//     cluster barrier per step.
+//     owns gate columns [8w, 8w+8) for all 512 k), the hidden state as hi/lo h16 copies in shared memory (one buffer:
+//     96 KB + 65 KB leave no room for a second);
+//   * per step every CTA multiplies the full hidden state of its 32 sequences with its weight slice (mma.sync m16n8k16, six
+//     independent accumulator chains per warp), ARRIVES at the cluster barrier ("done reading h"), applies the gate math in
+//     fp32 on its 32 units (fp32 master copy of h stays local) and writes the step's output rows while the barrier completes,
+//     then PUSHES the hi/lo h16 slices of h' into the buffers of all 16 CTAs through distributed shared memory and closes the
+//     step with a second cluster barrier.
 // PyTorch gate order and formulas (r, z, n; n = tanh(W_in x + b_in + r * (W_hn h + b_hn)); h' = (1 - z) n + z h).
 #include <cooperative_groups.h>
 #include "common.cuh"
@@ -22,7 +24,7 @@ namespace cg = cooperative_groups;
 
 namespace lavb {
 
-constexpr int kGruH = 512, kGruSeq = 16, kGruUnits = 32, kGruCluster = 16, kGruCols = 96, kGruIn = 4;
+constexpr int kGruH = 512, kGruSeq = 32, kGruUnits = 32, kGruCluster = 16, kGruCols = 96, kGruIn = 4;
 constexpr int kGruWarps = kGruCols / 8;                            // one n-tile (8 gate columns) per warp
 constexpr int kGruThreads = 32 * kGruWarps;                        // 384
 constexpr int kGruWPitch = kGruH + 8, kGruHPitch = kGruH + 8;     // h16 elements; +8 keeps ldmatrix / fragment loads conflict-free
@@ -30,9 +32,9 @@ constexpr int kGruGPitch = kGruCols + 4;                           // fp32 gate 
 
 struct GruSmem {
   static constexpr int w = 0;                                                   // [96][kGruWPitch] h16: W_hi
-  static constexpr int hb = w + kGruCols * kGruWPitch * 2;                      // [2 buffers][hi, lo][16][kGruHPitch] h16
-  static constexpr int g = hb + 2 * 2 * kGruSeq * kGruHPitch * 2;               // [16][kGruGPitch] fp32
-  static constexpr int hm = g + kGruSeq * kGruGPitch * 4;                       // [16][32] fp32 master copy of this CTA's units
+  static constexpr int hb = w + kGruCols * kGruWPitch * 2;                      // [hi, lo][32][kGruHPitch] h16
+  static constexpr int g = hb + 2 * kGruSeq * kGruHPitch * 2;                   // [32][kGruGPitch] fp32
+  static constexpr int hm = g + kGruSeq * kGruGPitch * 4;                       // [32][32] fp32 master copy of this CTA's units
   static constexpr int wih = hm + kGruSeq * kGruUnits * 4;                      // [96][4] fp32
   static constexpr int bih = wih + kGruCols * kGruIn * 4;                       // [96]
   static constexpr int bhh = bih + kGruCols * 4;                                // [96]
@@ -65,14 +67,14 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_cluster_kernel(const float
   const int rank = (int)cluster.block_rank();                       // which 32 hidden units this CTA owns
   const int seq0 = ((int)blockIdx.x / kGruCluster) * kGruSeq;       // first sequence of this cluster
   h16* Ws = reinterpret_cast<h16*>(gsm + GruSmem::w);
-  h16* Hb = reinterpret_cast<h16*>(gsm + GruSmem::hb);              // buffer b, part p (0 hi, 1 lo): Hb + ((b * 2 + p) * 16) * pitch
+  h16* Hb = reinterpret_cast<h16*>(gsm + GruSmem::hb);              // part p (0 hi, 1 lo) at Hb + p * kPart
   float* G = reinterpret_cast<float*>(gsm + GruSmem::g);
   float* Hm = reinterpret_cast<float*>(gsm + GruSmem::hm);
   float* Wi = reinterpret_cast<float*>(gsm + GruSmem::wih);
   float* Bi = reinterpret_cast<float*>(gsm + GruSmem::bih);
   float* Bh = reinterpret_cast<float*>(gsm + GruSmem::bhh);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
-  constexpr int kPart = kGruSeq * kGruHPitch;                       // h16 elements of one (buffer, part)
+  constexpr int kPart = kGruSeq * kGruHPitch;                       // h16 elements of one part
 
   // ---- one-time staging: local row c = gate*32 + j  <->  global row gate*512 + 32*rank + j
   for (int i = tid; i < kGruCols * (kGruH / 2); i += kGruThreads) {
@@ -118,40 +120,50 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_cluster_kernel(const float
   }
   cluster.sync();                                                   // every CTA of the cluster is resident and initialised
 
-  const int gs = tid >> 4, gu = (tid & 15) * 2;                     // gate role (threads 0..255): sequence, first of 2 hidden units
-  const bool gate_thread = tid < kGruSeq * 16;
+  const int gs = tid >> 3, gu = (tid & 7) * 4;                      // gate role (threads 0..255): sequence, first of 4 hidden units
+  const bool gate_thread = tid < kGruSeq * 8;
   const bool seq_ok = gate_thread && seq0 + gs < nseq;
+  const uint32_t a_hi = (uint32_t)__cvta_generic_to_shared(Hb + (lane & 15) * kGruHPitch + (lane >> 4) * 8);
+  const uint32_t a_lo = a_hi + kPart * 2;
+  const h16* wp = Ws + (warp * 8 + gq) * kGruWPitch + 2 * tq;
   for (int t = 0; t < steps; ++t) {
-    const h16* hc = Hb + (t & 1) * 2 * kPart;
-    h16* hn = Hb + ((t & 1) ^ 1) * 2 * kPart;
-    // ---- (1) G[16 seq][96] = h (16 x 512) . Wslice^T: warp w -> columns [8w, 8w+8), three split products per k-tile
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const uint32_t a_hi = (uint32_t)__cvta_generic_to_shared(hc + (lane & 15) * kGruHPitch + (lane >> 4) * 8);
-    const uint32_t a_lo = a_hi + kPart * 2;
-    const h16* wp = Ws + (warp * 8 + gq) * kGruWPitch + 2 * tq;
+    // ---- (1) G[32 seq][96] = h (32 x 512) . Wslice^T: warp w -> columns [8w, 8w+8), both 16-sequence m-tiles, three split
+    //          products per k-tile into six independent accumulators
+    float acc[2][3][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[m][c][0] = acc[m][c][1] = acc[m][c][2] = acc[m][c][3] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < kGruH / 16; ++kk) {
-      uint32_t h0_, h1_, h2_, h3_, l0_, l1_, l2_, l3_;
-      gru_ldmatrix_x4(a_hi + kk * 32, h0_, h1_, h2_, h3_);
-      gru_ldmatrix_x4(a_lo + kk * 32, l0_, l1_, l2_, l3_);
       const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wp + kk * 16), b1 = *reinterpret_cast<const uint32_t*>(wp + kk * 16 + 8);
-      gru_mma(acc, h0_, h1_, h2_, h3_, b0, b1);
-      gru_mma(acc, l0_, l1_, l2_, l3_, b0, b1);
-      gru_mma(acc, h0_, h1_, h2_, h3_, wlo[2 * kk], wlo[2 * kk + 1]);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        uint32_t h0_, h1_, h2_, h3_, l0_, l1_, l2_, l3_;
+        gru_ldmatrix_x4(a_hi + m * 16 * kGruHPitch * 2 + kk * 32, h0_, h1_, h2_, h3_);
+        gru_ldmatrix_x4(a_lo + m * 16 * kGruHPitch * 2 + kk * 32, l0_, l1_, l2_, l3_);
+        gru_mma(acc[m][0], h0_, h1_, h2_, h3_, b0, b1);
+        gru_mma(acc[m][1], l0_, l1_, l2_, l3_, b0, b1);
+        gru_mma(acc[m][2], h0_, h1_, h2_, h3_, wlo[2 * kk], wlo[2 * kk + 1]);
+      }
     }
-    {
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
       const int col = warp * 8 + 2 * tq;
-      *reinterpret_cast<float2*>(&G[gq * kGruGPitch + col]) = make_float2(acc[0], acc[1]);
-      *reinterpret_cast<float2*>(&G[(gq + 8) * kGruGPitch + col]) = make_float2(acc[2], acc[3]);
+      *reinterpret_cast<float2*>(&G[(m * 16 + gq) * kGruGPitch + col]) =
+          make_float2(acc[m][0][0] + (acc[m][1][0] + acc[m][2][0]), acc[m][0][1] + (acc[m][1][1] + acc[m][2][1]));
+      *reinterpret_cast<float2*>(&G[(m * 16 + gq + 8) * kGruGPitch + col]) =
+          make_float2(acc[m][0][2] + (acc[m][1][2] + acc[m][2][2]), acc[m][0][3] + (acc[m][1][3] + acc[m][2][3]));
     }
     __syncthreads();
-    // ---- (2) gate math in fp32 for (sequence gs, units gu, gu+1), output row, push of the hi/lo h16 slices to all 16 CTAs
+    cluster.barrier_arrive();                                       // this CTA has finished reading h(t)
+    // ---- (2) gate math in fp32 for (sequence gs, units gu..gu+3) and the output row, while the barrier completes
+    float hnew[4] = {0.f, 0.f, 0.f, 0.f};
     if (gate_thread) {
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       if (seq_ok) x = __ldg(reinterpret_cast<const float4*>(u + ((long long)(seq0 + gs) * steps + t) * kGruIn));
-      float hnew[2];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
+      for (int e = 0; e < 4; ++e) {
         const int j = gu + e;
         const float* wr = Wi + j * kGruIn; const float* wz = Wi + (32 + j) * kGruIn; const float* wn = Wi + (64 + j) * kGruIn;
         const float ir = fmaf(wr[0], x.x, fmaf(wr[1], x.y, fmaf(wr[2], x.z, fmaf(wr[3], x.w, Bi[j]))));
@@ -165,18 +177,23 @@ __global__ void __launch_bounds__(kGruThreads, 1) gru_cluster_kernel(const float
         Hm[gs * kGruUnits + j] = hnew[e];
       }
       if (seq_ok)
-        *reinterpret_cast<float2*>(out + ((long long)(seq0 + gs) * steps + t) * kGruH + rank * kGruUnits + gu) = make_float2(hnew[0], hnew[1]);
-      uint32_t hi, lo;
-      gru_split2(hnew[0], hnew[1], hi, lo);
-      h16* dst = hn + gs * kGruHPitch + rank * kGruUnits + gu;       // same offset in every CTA's shared memory
+        *reinterpret_cast<float4*>(out + ((long long)(seq0 + gs) * steps + t) * kGruH + rank * kGruUnits + gu) = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
+    }
+    cluster.barrier_wait();                                         // every CTA of the cluster has finished reading h(t)
+    // ---- (3) push the hi/lo h16 slices of h(t+1) to all 16 CTAs
+    if (gate_thread) {
+      uint2 hi, lo;
+      gru_split2(hnew[0], hnew[1], hi.x, lo.x);
+      gru_split2(hnew[2], hnew[3], hi.y, lo.y);
+      h16* dst = Hb + gs * kGruHPitch + rank * kGruUnits + gu;      // same offset in every CTA's shared memory
 #pragma unroll
       for (int peer = 0; peer < kGruCluster; ++peer) {
         h16* rp = cluster.map_shared_rank(dst, peer);
-        *reinterpret_cast<uint32_t*>(rp) = hi;
-        *reinterpret_cast<uint32_t*>(rp + kPart) = lo;
+        *reinterpret_cast<uint2*>(rp) = hi;
+        *reinterpret_cast<uint2*>(rp + kPart) = lo;
       }
     }
-    cluster.sync();      // pushes visible everywhere; nobody still reads this step's h or G
+    cluster.sync();      // pushes visible everywhere; nobody still reads this step's G
   }
 }
 

@@ -167,11 +167,13 @@ def resnet18(pretrained=False, num_channels=3, **kw):
 
 
 # Cluster-persistent plan GRU (csrc/gru_cluster.cu): one launch per 20-step roll-out instead of cuDNN's 20 GEMM + cell launch
-# pairs (100 per tick, latency-bound at ~10 us each).  fp32-class arithmetic — both operands of the recurrent product are split
-# into h16 hi + lo parts on the tensor cores — because the 5 x 20-step plan roll-out is not contractive on untrained weights: the
-# first version of the kernel (plain h16 operands, 8e-4 per roll-out) ended 1.7e-2 .. 5e-2 from the reference at BASELINE
-# config 3.  Serves the fp32 and the 16-bit pipeline alike; cuDNN's GRU remains for training and non-CUDA callers.
-GRU_KERNEL = True
+# pairs.  fp32-class arithmetic — both operands of the recurrent product are split into h16 hi + lo parts (3 mma.sync products) —
+# because the 5 x 20-step plan roll-out is not contractive on untrained weights: the first version of the kernel (plain h16
+# operands, 8e-4 per roll-out, 0.71 ms per tick) ended 1.7e-2 .. 5e-2 from the reference at BASELINE config 3.  This version
+# agrees with nn.GRU to 2e-5 over 20 steps and passes every parity test of both pipelines, but the three products run on the
+# legacy mma.sync path and 64 KB of hidden state cross DSMEM per CTA and step: 1.18 ms per tick of 32 frames against cuDNN's
+# 0.98 ms (B200).  OFF by default for that reason; the tcgen05 form (W_lo as a TMEM A operand) is the open item in DESIGN.md.
+GRU_KERNEL = False
 
 
 # ----------------------------------------------------------------------------- planners
