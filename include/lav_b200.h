@@ -299,6 +299,15 @@ int lavb_erf_nb16(const void* d_in, void* d_out, int n, int h, int w, const floa
 int lavb_gru_h512(const float* d_u, const float* d_h0, const float* d_whh, const float* d_wih, const float* d_bih,
                   const float* d_bhh, float* d_out, int nseq, int steps, void* stream);
 
+/* ---------------------------------------------------------------- motion-forecast ("cast") heads in one launch
+ * replaces: UniPlanner.cast / BEVPlanner.cast (team_code_v2/models/uniplanner.py:286-301, lav/models/bev_planner_v2.py:226-236):
+ * for each of ncmd branches, nn.GRU(512, 64, batch_first=True) over the embedding repeated `steps` times, nn.Linear(64, 2) and the
+ * cumulative sum over the steps — 6 x (GRU + Linear + cumsum) calls in the reference.  fp32 FFMA.
+ * d_embd (n, 512); d_wih_t (ncmd, 512, 192) = weight_ih_l0 TRANSPOSED; d_whh_t (ncmd, 64, 192) = weight_hh_l0 transposed;
+ * d_bih / d_bhh (ncmd, 192); d_wmlp (ncmd, 2, 64); d_bmlp (ncmd, 2); d_out (n, ncmd, steps, 2) fp32. */
+int lavb_cast_gru(const float* d_embd, int n, const float* d_wih_t, const float* d_whh_t, const float* d_bih, const float* d_bhh,
+                  const float* d_wmlp, const float* d_bmlp, int ncmd, int steps, float* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -175,6 +175,31 @@ def resnet18(pretrained=False, num_channels=3, **kw):
 # 0.98 ms (B200).  OFF by default for that reason; the tcgen05 form (W_lo as a TMEM A operand) is the open item in DESIGN.md.
 GRU_KERNEL = False
 
+# The cast branches (6 x GRU(512, 64) + Linear(64, 2) + cumsum over the repeated embedding) as ONE fp32 kernel (csrc/cast_gru.cu)
+# instead of ~100 dependent cuDNN / ATen launches per call (B200: 0.29 -> 0.05 ms per tick).  Inference only.
+CAST_KERNEL = True
+
+
+def _cast_branches(owner, grus, mlps, embd, num_plan):
+    """cast() of both planners.  Kernel path for CUDA fp32 inference (transposed weights packed once per parameter version);
+    the module path otherwise (training, CPU, non-fp32)."""
+    w0 = grus[0].weight_ih_l0
+    if (CAST_KERNEL and embd.is_cuda and not torch.is_grad_enabled() and embd.dtype == torch.float32 and w0.dtype == torch.float32
+            and grus[0].hidden_size == 64 and grus[0].input_size == 512 and mlps[0].out_features == 2):
+        params = [p for g in grus for p in (g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0)] + [p for m in mlps for p in (m.weight, m.bias)]
+        key = tuple((p.data_ptr(), p._version) for p in params) + (str(embd.device),)
+        cached = owner.__dict__.get("_cast_pack")
+        if cached is None or cached[0] != key:                       # re-pack after load_state_dict / .to() / an optimizer step
+            with torch.no_grad():
+                pack = (torch.stack([g.weight_ih_l0.t() for g in grus]).contiguous(), torch.stack([g.weight_hh_l0.t() for g in grus]).contiguous(),
+                        torch.stack([g.bias_ih_l0 for g in grus]).contiguous(), torch.stack([g.bias_hh_l0 for g in grus]).contiguous(),
+                        torch.stack([m.weight for m in mlps]).contiguous(), torch.stack([m.bias for m in mlps]).contiguous())
+            cached = owner.__dict__["_cast_pack"] = (key, pack)
+        return ops.cast_gru(embd.contiguous(), *cached[1], num_plan)
+    B = embd.size(0)
+    u = embd.expand(num_plan, B, -1).permute(1, 0, 2).contiguous()
+    return torch.stack([torch.cumsum(mlp(gru(u)[0]), dim=1) for gru, mlp in zip(grus, mlps)], dim=1)
+
 
 # ----------------------------------------------------------------------------- planners
 def transform_points(locs, oris):
@@ -222,9 +247,7 @@ class BEVPlanner(nn.Module):
         return F.grid_sample(features, grids, align_corners=True)
 
     def cast(self, embd):
-        B = embd.size(0)
-        u = embd.expand(self.num_plan, B, -1).permute(1, 0, 2).contiguous()
-        return torch.stack([torch.cumsum(mlp(gru(u)[0]), dim=1) for gru, mlp in zip(self.cast_grus, self.cast_mlps)], dim=1)
+        return _cast_branches(self, self.cast_grus, self.cast_mlps, embd, self.num_plan)
 
     def plan(self, embd, nxp, cast_locs=None, pixels_per_meter=4, crop_size=96):
         return _plan_rollout(self.plan_gru, self.plan_mlp, self.num_cmds, self.num_plan, self.num_plan_iter, embd, nxp,
@@ -320,13 +343,8 @@ class UniPlanner(nn.Module):
         return F.grid_sample(features, grids, align_corners=True)
 
     def cast(self, embd, mode='ego'):
-        B = embd.size(0)
-        u = embd.expand(self.num_plan, B, -1).permute(1, 0, 2)
-        locs = []
-        for gru, mlp in zip(self.cast_grus_ego, self.cast_mlps_ego):     # 'other' re-uses the ego GRUs (uniplanner.py:296-300)
-            out, _ = gru(u.contiguous())
-            locs.append(torch.cumsum(mlp(out), dim=1))
-        return torch.stack(locs, dim=1)
+        # 'other' re-uses the ego GRUs (uniplanner.py:296-300)
+        return _cast_branches(self, self.cast_grus_ego, self.cast_mlps_ego, embd, self.num_plan)
 
     def plan(self, embd, nxp, cast_locs=None, pixels_per_meter=4, crop_size=96):
         return _plan_rollout(self.plan_gru, self.plan_mlp, self.num_cmds, self.num_plan, self.num_plan_iter, embd, nxp,

@@ -552,6 +552,22 @@ def erf_nb16(x, w4, st, out=None):
     return out
 
 
+def cast_gru(embd, wih_t, whh_t, bih, bhh, wmlp, bmlp, steps):
+    """the 6 cast branches in one launch (csrc/cast_gru.cu).  embd (N, 512) fp32; wih_t (ncmd, 512, 192), whh_t (ncmd, 64, 192) the
+    TRANSPOSED GRU weights; bih / bhh (ncmd, 192); wmlp (ncmd, 2, 64); bmlp (ncmd, 2) -> (N, ncmd, steps, 2) fp32 cumulative waypoints."""
+    _need_cuda(embd, wih_t, whh_t)
+    n, ncmd = embd.shape[0], wih_t.shape[0]
+    assert tuple(embd.shape) == (n, 512) and tuple(wih_t.shape) == (ncmd, 512, 192) and tuple(whh_t.shape) == (ncmd, 64, 192)
+    assert tuple(bih.shape) == tuple(bhh.shape) == (ncmd, 192) and tuple(wmlp.shape) == (ncmd, 2, 64) and tuple(bmlp.shape) == (ncmd, 2)
+    for t in (embd, wih_t, whh_t, bih, bhh, wmlp, bmlp):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    out = torch.empty((n, ncmd, steps, 2), dtype=torch.float32, device=embd.device)
+    check(lib().lavb_cast_gru(_ptr(embd), n, _ptr(wih_t), _ptr(whh_t), _ptr(bih), _ptr(bhh), _ptr(wmlp), _ptr(bmlp), ncmd, steps,
+                              _ptr(out), _stream()), "lavb_cast_gru")
+    _COUNT[0] += 1
+    return out
+
+
 def gru_h512(u, h0, whh, wih, bih, bhh):
     """cluster-persistent GRU(4 -> 512) roll-out (csrc/gru_cluster.cu), fp32-class arithmetic.  u (N, T, 4), h0 (N, 512),
     whh (1536, 512), wih (1536, 4), bih / bhh (1536,), all fp32 -> out (N, T, 512) fp32 (the output sequence of

@@ -75,6 +75,40 @@ def test_crop_backward_kernel_vs_grid_sample_grad(cuda, case):
     assert util.rel_err(outs[0][0], outs[1][0]) < 1e-5 and util.rel_err(outs[0][1], outs[1][1]) < 1e-5
 
 
+@pytest.mark.parametrize("n", [1, 37, 128])
+def test_cast_kernel_matches_gru_modules(cuda, n):
+    """lavb_cast_gru (6 branches x GRU(512,64) + Linear + cumsum in one launch) == the nn.GRU / nn.Linear module path of
+    UniPlanner.cast and BEVPlanner.cast (uniplanner.py:286-301), fp32, 1e-5 of the waypoint scale; the packed weights follow
+    parameter updates."""
+    import lav_b200.heads as Hd
+    up, _ = uniplanner()
+    up = up.to(cuda).eval()
+    g = synth._gen(6, f"cast{n}")
+    embd = (torch.randn(n, 512, generator=g) * 0.7).to(cuda)
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            for planner in (up, up.bev_planner):
+                got = planner.cast(embd)
+                Hd.CAST_KERNEL = False
+                try:
+                    want = planner.cast(embd)
+                finally:
+                    Hd.CAST_KERNEL = True
+                assert got.shape == want.shape == (n, planner.num_cmds, planner.num_plan, 2)
+                assert util.rel_err(got, want) < 1e-5, util.rel_err(got, want)
+            up.cast_mlps_ego[2].bias.add_(1.0)                        # in-place update -> the pack must be rebuilt
+            got, Hd.CAST_KERNEL = up.cast(embd), False
+            try:
+                want = up.cast(embd)
+            finally:
+                Hd.CAST_KERNEL = True
+            assert util.rel_err(got, want) < 1e-5
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def test_infer_model_matches_oracle(cuda):
     from lav_b200.model_inference import InferModel
     lm, lsd = util.lidar_model(cuda)
