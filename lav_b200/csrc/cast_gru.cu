@@ -15,7 +15,7 @@ namespace lavb {
 
 constexpr int kCgIn = 512, kCgH = 64, kCgCols = 192, kCgSeq = 16;
 
-struct CastSmem {
+struct __align__(16) CastSmem {
   float whh[kCgH][kCgCols];        // W_hh^T
   float gi[kCgSeq][kCgCols];
   float gh[kCgSeq][kCgCols];
@@ -49,11 +49,14 @@ __global__ void __launch_bounds__(kCgCols) cast_gru_kernel(const float* __restri
     const float b = __ldg(bih + cmd * kCgCols + c);
 #pragma unroll
     for (int s = 0; s < kCgSeq; ++s) acc[s] = b;
-#pragma unroll 4
-    for (int k = 0; k < kCgIn; ++k) {
-      const float w = __ldg(wi + k * kCgCols + c);
+    for (int k = 0; k < kCgIn; k += 4) {            // 4 k per pass: the embeddings come as broadcast LDS.128
+      const float w0 = __ldg(wi + k * kCgCols + c), w1 = __ldg(wi + (k + 1) * kCgCols + c), w2 = __ldg(wi + (k + 2) * kCgCols + c),
+                  w3 = __ldg(wi + (k + 3) * kCgCols + c);
 #pragma unroll
-      for (int s = 0; s < kCgSeq; ++s) acc[s] = fmaf(sm.x[s][k], w, acc[s]);
+      for (int s = 0; s < kCgSeq; ++s) {
+        const float4 x4 = *reinterpret_cast<const float4*>(&sm.x[s][k]);
+        acc[s] = fmaf(x4.w, w3, fmaf(x4.z, w2, fmaf(x4.y, w1, fmaf(x4.x, w0, acc[s]))));
+      }
     }
 #pragma unroll
     for (int s = 0; s < kCgSeq; ++s) sm.gi[s][c] = acc[s];
@@ -69,10 +72,13 @@ __global__ void __launch_bounds__(kCgCols) cast_gru_kernel(const float* __restri
 #pragma unroll
       for (int s = 0; s < kCgSeq; ++s) acc[s] = bh;
 #pragma unroll 4
-      for (int j = 0; j < kCgH; ++j) {
-        const float w = sm.whh[j][c];
+      for (int j = 0; j < kCgH; j += 4) {
+        const float w0 = sm.whh[j][c], w1 = sm.whh[j + 1][c], w2 = sm.whh[j + 2][c], w3 = sm.whh[j + 3][c];
 #pragma unroll
-        for (int s = 0; s < kCgSeq; ++s) acc[s] = fmaf(sm.h[s][j], w, acc[s]);
+        for (int s = 0; s < kCgSeq; ++s) {
+          const float4 h4 = *reinterpret_cast<const float4*>(&sm.h[s][j]);
+          acc[s] = fmaf(h4.w, w3, fmaf(h4.z, w2, fmaf(h4.y, w1, fmaf(h4.x, w0, acc[s]))));
+        }
       }
 #pragma unroll
       for (int s = 0; s < kCgSeq; ++s) sm.gh[s][c] = acc[s];
