@@ -281,7 +281,7 @@ def run_train_leg(args, dev, rank, world, lid, uni):
            if world > 1 else "none (1 rank)",
            "exposed_after_backward_ms": float(red), "h2d_bytes_per_step": int(h2d_bytes), "h2d": "pinned, side stream, one step ahead",
            "precision": "bf16 autocast forward/backward (cuDNN), fp32 master weights, losses and Adam" if args.train_amp else "fp32 tensors, PyTorch defaults (cuDNN convolutions may use TF32, as in the reference trainer)",
-           "conv_backend": "cuDNN (pillar decorate / scatter-max fwd+bwd: lav_b200 CUDA kernels)",
+           "conv_backend": "cuDNN convolutions (channels-last); lav_b200 CUDA kernels: pillar decorate / scatter-max fwd+bwd, rotated crop fwd + gather backward; the four heads' first layers run as one 384->256 convolution",
            "loss": float(loss), "max_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
     tr.reducer.close()
     del tr, slots
