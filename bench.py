@@ -199,7 +199,7 @@ def workload_config(B, precision, P=1):
             "planner_detections": "decode runs on the predicted maps; planner is fed a fixed K=3 list (SURVEY 8d)",
             "l2": "per-step working set (B x 26 MB canvas + B x 39 MB features + ...) exceeds the 126 MB L2; inputs rotate over 2 sets",
             "parallelism": "replicas (one process per GPU, no data-path collective)",
-            "execution": "two CUDA graphs per step (perception+heads+brake; planner), host decode of detections in between"}
+            "execution": "two CUDA graphs per step (perception+heads+brake; planner), host decode of detections in between; e2e: each step's pinned host inputs go through a copy stream into staging buffers (H2D inside the timed region, overlapping the other agent group's kernels), results read back every step"}
 
 
 def run_train_leg(args, dev, rank, world, lid, uni):
