@@ -97,3 +97,19 @@ def test_uniplanner_train_forward_matches_reference_golden(golden_dir):
     for n, o in zip(names, out):
         np.testing.assert_allclose(o.detach().numpy(), gold[n], atol=5e-4 * (np.abs(gold[n]).max() + 1), err_msg=n)
     assert out[6].requires_grad and not out[9].requires_grad          # student carries grad, teacher does not
+
+
+def test_cast_module_path_equals_oracle_cast():
+    """heads._cast_branches on CPU tensors (the module path that training and non-CUDA callers take; the CUDA kernel is compared
+    with it in tests/test_gpu_frame.py) == the oracle's cast of uniplanner.py:286-301, for both planners."""
+    up, sd = uniplanner()
+    embd = torch.randn(5, 512, generator=torch.Generator().manual_seed(3)) * 0.6
+    with torch.no_grad():
+        got = up.cast(embd)
+        want = O.up_cast(sd, embd)
+        assert got.shape == (5, 6, 20, 2)
+        assert util.rel_err(got, want) < 1e-5
+        t = up.bev_planner.cast(embd)
+        branches = [torch.cumsum(m(g(embd.expand(up.bev_planner.num_plan, 5, -1).permute(1, 0, 2).contiguous())[0]), dim=1)
+                    for g, m in zip(up.bev_planner.cast_grus, up.bev_planner.cast_mlps)]
+        assert torch.allclose(t, torch.stack(branches, dim=1), atol=1e-6)
